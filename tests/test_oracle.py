@@ -1,0 +1,119 @@
+"""Pins the oracle (oracle/) against the reference's own outputs stored in tests/golden/.
+
+CPU only.  The fixtures were produced by the unmodified reference (tests/golden/make_golden.py);
+when /root/reference is present the live reference is also compared for the native NMS.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from tests.common import GOLDEN, synthetic_heads, post_config, unpack_masks
+from oracle.post_oracle import PostProcessOracle, nms_oracle, bilinear_x4
+from oracle.forward_oracle import forward_oracle
+from orienmask_b200.synthetic import synthetic_state_dict, synthetic_images
+
+
+def _oracle(height, width, thr):
+    cfg = post_config(height, width, thr)
+    return PostProcessOracle(cfg['grid_size'], cfg['image_size'], cfg['anchors'], cfg['anchor_mask'],
+                             cfg['num_classes'], conf_thresh=cfg['conf_thresh'], nms_threshold=0.5,
+                             nms_pre=cfg['nms_pre'], nms_post=cfg['nms_post'], orien_thresh=cfg['orien_thresh'])
+
+
+def _match_rows(bbox, cls, gbbox, gcls, tol=2e-6):
+    """Match detections as a set on (cls, box, score); returns permutation of gold rows or None."""
+    if bbox.shape[0] != gbbox.shape[0]:
+        return None
+    used = np.zeros(gbbox.shape[0], dtype=bool)
+    perm = []
+    for i in range(bbox.shape[0]):
+        d = np.abs(gbbox - bbox[i]).max(1) + (gcls != cls[i]) * 1e3 + used * 1e3
+        j = int(np.argmin(d))
+        if d[j] > tol:
+            return None
+        used[j] = True
+        perm.append(j)
+    return np.asarray(perm, dtype=np.int64)
+
+
+def test_nms_oracle_matches_reference_fixture():
+    g = np.load(GOLDEN + '/nms_cases.npz')
+    for i in range(int(g['n_cases'])):
+        for thr in (0.5, 0.3):
+            keep = nms_oracle(g['dets_%d' % i], thr)
+            ref = g['keep_%d_%s' % (i, str(thr).replace('.', 'p'))]
+            assert np.array_equal(keep, ref), (i, thr)
+
+
+def test_nms_oracle_matches_live_reference_when_present():
+    from oracle import build_ref
+    if not build_ref.reference_available():
+        pytest.skip('reference tree not present')
+    nms = build_ref.load_ref_nms()
+    g = torch.Generator().manual_seed(11)
+    for n in (3, 50, 400):
+        d = torch.cat([torch.rand(n, 2, generator=g), torch.rand(n, 2, generator=g) * 0.3 + 0.01,
+                       torch.rand(n, 1, generator=g)], 1)
+        assert np.array_equal(nms_oracle(d.numpy(), 0.5), nms.nms(d, 0.5).numpy())
+
+
+def test_bilinear_matches_torch():
+    x = torch.randn(2, 6, 9, 13, generator=torch.Generator().manual_seed(0))
+    ref = torch.nn.functional.interpolate(x, scale_factor=4.0, mode='bilinear', align_corners=False).numpy()
+    got = bilinear_x4(x.numpy())
+    assert np.abs(got - ref).max() <= 1e-6          # bit-exact on FMA-capable hosts, 1-ulp otherwise
+
+
+@pytest.mark.parametrize('name', ['topk', 'few', 'none'])
+def test_post_oracle_small_fixture(name):
+    g = np.load(GOLDEN + '/small_fwd_post.npz')
+    post = _oracle(64, 96, float(g[name + '_thresh']))
+    heads = [(g['bbox_%d' % i], g['orien_%d' % i]) for i in range(3)]
+    res = post(heads)
+    for b, r in enumerate(res):
+        gb, gc = g['%s_bbox_%d' % (name, b)], g['%s_cls_%d' % (name, b)]
+        perm = _match_rows(r['bbox'], r['cls'], gb, gc)
+        assert perm is not None, 'kept set differs from the reference'
+        if name != 'none':
+            gm = unpack_masks(g, name, b)[perm]
+            inter = (gm & r['mask']).sum()
+            union = (gm | r['mask']).sum()
+            assert inter >= 0.9999 * union
+        if name == 'few':   # <= nms_pre candidates: reference order is (prediction, class) row-major
+            assert np.array_equal(perm, np.arange(len(perm)))
+
+
+def test_post_oracle_north_star_digest():
+    g = np.load(GOLDEN + '/post_544_digest.npz')
+    heads = synthetic_heads(2, 544, 544, seed=int(g['seed']))
+    post = _oracle(544, 544, 0.005)
+    res = post([(b.numpy(), o.numpy()) for b, o in heads])
+    for b, r in enumerate(res):
+        perm = _match_rows(r['bbox'], r['cls'], g['ns_bbox_%d' % b], g['ns_cls_%d' % b])
+        assert perm is not None
+        assert np.array_equal(perm, np.arange(len(perm)))     # score-descending order, same as reference
+        area = r['mask'].sum(axis=(1, 2))
+        assert np.abs(area - g['ns_area_%d' % b]).max() <= 2
+        sha = hashlib.sha256(np.packbits(r['mask'].reshape(-1)).tobytes()).digest()
+        if np.array_equal(area, g['ns_area_%d' % b]):
+            assert sha == g['ns_sha_%d' % b].tobytes()
+
+
+def test_forward_oracle_small_fixture():
+    g = np.load(GOLDEN + '/small_fwd_post.npz')
+    sd = synthetic_state_dict(0)
+    out = forward_oracle(sd, synthetic_images(2, 64, 96, seed=1))
+    for i, (bbox, orien) in enumerate(out):
+        assert np.abs(bbox.numpy() - g['bbox_%d' % i]).max() < 2e-4
+        assert np.abs(orien.numpy() - g['orien_%d' % i]).max() < 2e-4
+
+
+def test_forward_oracle_544_probe():
+    g = np.load(GOLDEN + '/fwd_544_probe.npz')
+    sd = synthetic_state_dict(0)
+    out = forward_oracle(sd, synthetic_images(1, 544, 544, seed=1))
+    for i, (bbox, orien) in enumerate(out):
+        assert np.abs(bbox.numpy().reshape(-1)[::97] - g['bbox_%d' % i]).max() < 5e-4
+        assert np.abs(orien.numpy().reshape(-1)[::97] - g['orien_%d' % i]).max() < 5e-4
