@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the OrienMask hot path at 544x544, batch 32 per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One step = DarkNet-53+FPNPlus forward -> decode/select -> class-wise NMS -> mask assembly on one
+synthetic batch (random-init weights of the reference architecture, uniform-noise images; no
+datasets or checkpoints are reachable offline).  N > 1: one process per GPU under torchrun, the
+batch dimension is sharded (weak scaling: 32 images per rank) and the only collective is the NCCL
+all-gather of the padded detection records.  Prints ONE JSON line on rank 0 (contract in the task
+statement): `value` is device-resident throughput, `e2e` goes through the public API from pinned
+host memory, `roofline` is the conv engine against the measured tensor peak, `cpu_baseline` /
+`--impl reference` time the CPU restatement of the reference (oracle/) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 544
+BATCH = 32
+GFLOP_PER_IMAGE = 173.845           # 2 * 86.9226 GMAC over the 90 convolutions
+METRIC = 'images/sec @544x544 bs32 (forward + decode + NMS + masks)'
+ANCHORS = [[12, 16], [19, 36], [40, 28], [36, 75], [76, 55], [72, 146], [142, 110], [192, 243], [459, 401]]
+ANCHOR_MASK = [[6, 7, 8], [3, 4, 5], [0, 1, 2]]
+
+
+def post_kwargs():
+    return dict(grid_size=[[H // s, W // s] for s in (32, 16, 8)], image_size=[H, W], anchors=ANCHORS,
+                anchor_mask=ANCHOR_MASK, num_classes=80, conf_thresh=0.005, nms_pre=400, nms_post=100, orien_thresh=0.3)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return dict(tflops=float(d.get('bf16_tflops_sustained') or d.get('bf16_tflops')), hbm=float(d.get('hbm_gbs')),
+                        source='MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)')
+        except Exception:
+            pass
+    return dict(tflops=1400.0, hbm=6650.0, source='fallback of B200_PROFILING.md (1.4 PFLOP/s sustained, 6.65 TB/s)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        if not rows:
+            return None
+        sm = [float(r[0]) for r in rows if r[0].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in rows)]
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(rows[0][1]) if rows[0][1].isdigit() else None,
+                'reasons': reasons, 'samples': len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(n_images, sd, post, threads):
+    """One pass of the CPU restatement of the reference (oracle/) over n_images; returns seconds."""
+    import torch
+    from oracle.forward_oracle import forward_oracle
+    from orienmask_b200.synthetic import synthetic_images
+    torch.set_num_threads(threads)
+    x = synthetic_images(n_images, H, W, seed=1)
+    t0 = time.perf_counter()
+    heads = forward_oracle(sd, x)
+    post([(b.numpy(), o.numpy()) for b, o in heads])
+    return time.perf_counter() - t0
+
+
+def make_cpu_reference():
+    from oracle.post_oracle import PostProcessOracle
+    from orienmask_b200.synthetic import synthetic_state_dict
+    kw = post_kwargs()
+    post = PostProcessOracle(kw['grid_size'], kw['image_size'], kw['anchors'], kw['anchor_mask'], kw['num_classes'],
+                             conf_thresh=kw['conf_thresh'], nms_threshold=0.5, nms_pre=kw['nms_pre'],
+                             nms_post=kw['nms_post'], orien_thresh=kw['orien_thresh'])
+    return synthetic_state_dict(0), post
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sd, post = make_cpu_reference()
+    sample = 2
+    for _ in range(args.warmup):
+        cpu_reference_step(sample, sd, post, threads)
+    t = sum(cpu_reference_step(sample, sd, post, threads) for _ in range(args.steps))
+    v = sample * args.steps / t
+    desc = {'value': v, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
+            'sample': '%d images of 544x544 per step (forward via torch CPU/oneDNN fp32 + numpy/C post-process)' % sample}
+    print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/sec', 'n_gpus': args.gpus,
+                      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
+                      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': {'workload': 'bs=32 544x544 forward+decode+NMS+masks (bounded CPU sample of %d images/step)' % sample},
+                      'cpu_baseline': desc,
+                      'e2e': {'value': v, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        return run_reference(args, rank)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import functools
+    import orienmask_b200 as ob
+    from orienmask_b200 import _lib
+    from orienmask_b200.sharding import gather_detections
+    from orienmask_b200.synthetic import synthetic_state_dict, synthetic_images
+
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (the product path has no CPU fallback)')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    B = args.batch
+    model = ob.OrienMaskYOLOFPNPlus(3, 80)
+    model.load_state_dict(synthetic_state_dict(0), strict=True)
+    model.precision = args.precision
+    model = model.to(dev).eval()
+    post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5), device=dev, **post_kwargs())
+    # two distinct resident batches, alternated (per-step activation traffic is >> the 126 MB L2 anyway)
+    host = [synthetic_images(B, H, W, seed=1 + rank * 2 + i).pin_memory() for i in range(2)]
+    resident = [h.to(dev) for h in host]
+    lib = _lib.lib()
+
+    def step(x):
+        heads = model(x)
+        out = post.apply_padded(heads)
+        det, cls, cnt = gather_detections(out.det, out.cls, out.count)
+        return out, det, cls, cnt
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(resident[i % 2])
+    barrier()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib.om_launch_count_reset()
+    barrier()
+    t0 = time.time()
+    e0.record()
+    for i in range(args.steps):
+        fwd_ev[i][0].record()
+        heads = model(resident[i % 2])
+        fwd_ev[i][1].record()
+        out = post.apply_padded(heads)
+        gather_detections(out.det, out.cls, out.count)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    launches = int(lib.om_launch_count())
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
+    k_avg = int(out.count.float().mean().item())
+
+    # ---- end to end through the public API from pinned host memory -----------------------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [torch.empty_like(resident[0]) for _ in range(2)]
+    rec_host = torch.empty(B * world, 100, 5, dtype=torch.float32).pin_memory()
+    cnt_host = torch.empty(B * world, dtype=torch.int32).pin_memory()
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(n):
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(copy_stream):
+            bufs[0].copy_(host[0], non_blocking=True)
+            ready[0].record(copy_stream)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(freed[1 - s])
+                    bufs[1 - s].copy_(host[(i + 1) % 2], non_blocking=True)
+                    ready[1 - s].record(copy_stream)
+            cur.wait_event(ready[s])
+            _, det, cls, cnt = step(bufs[s])
+            freed[s].record(cur)
+            rec_host.copy_(det, non_blocking=True)
+            cnt_host.copy_(cnt, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_loop(3)
+    barrier()
+    w0 = time.perf_counter()
+    e2e_loop(args.steps)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - w0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        value = world * B * args.steps / (total_ms * 1e-3)
+        achieved = B * GFLOP_PER_IMAGE / fwd_ms          # GFLOP / ms == TFLOP/s
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16' if args.precision == 'fp16' else 'f32', 'data': 'synthetic',
+            'config': {'workload': 'bs=%d 544x544 per GPU: DarkNet-53+FPNPlus forward + decode + batched NMS + mask assembly' % B,
+                       'global_batch': B * world, 'parallelism': 'dp%d' % world, 'weights': 'synthetic_state_dict(seed 0)',
+                       'l2': 'two alternating resident batches; per-step activation traffic (>10 GB) >> 126 MB L2',
+                       'precision': 'fp16 storage / fp32 accumulate convs, fp32 heads + post-process' if args.precision == 'fp16' else 'fp32',
+                       'avg_instances_per_image': k_avg},
+            'e2e': {'value': world * B * args.steps / e2e_s, 'unit': 'images/sec',
+                    'h2d_bytes_per_step': int(host[0].numel() * 4), 'd2h_bytes_per_step': int(rec_host.numel() * 4 + cnt_host.numel() * 4),
+                    'note': 'pinned fp32 NCHW images -> model() -> postprocess -> detection records + counts to host; copies double-buffered on a side stream'},
+            'gpu_launches': launches,
+            'clocks': clocks,
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                         'frac': achieved / peaks['tflops'], 'traffic': None,
+                         'kernel': 'conv engine (conv_tc_kernel launches + stem) = the model forward, %.3f ms of %.3f ms per step'
+                                   % (fwd_ms, total_ms / args.steps),
+                         'algorithmic': '%.3f GFLOP/image x %d images per forward' % (GFLOP_PER_IMAGE, B),
+                         'peak_source': peaks['source']},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sd, cpost = make_cpu_reference()
+            cpu_reference_step(1, sd, cpost, threads)
+            n_img, reps = 4, 3
+            t = sum(cpu_reference_step(n_img, sd, cpost, threads) for _ in range(reps))
+            line['cpu_baseline'] = {'value': n_img * reps / t, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
+                                    'sample': '%d passes over %d images of 544x544 (oracle: torch CPU fp32 forward + numpy/C post-process)' % (reps, n_img)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,183 @@
+/*
+ * orienmask_b200 -- C ABI of the B200-native OrienMask inference hot path.
+ *
+ * Plain pointers and sizes only (no torch types).  Every pointer named "device" is a CUDA device
+ * pointer; every function enqueues work on `stream` (a cudaStream_t passed as void*), performs no
+ * allocation and no host synchronisation, and returns OM_OK or a negative error code whose text is
+ * available from om_last_error().
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * repository root, duwt/OrienMask):
+ *
+ *   om_nms                 eval/src/nms_cuda.cpp:8-17  (pybind `nms(dets, threshold)`), and
+ *                          eval/src/nms_cpu.cpp:65-75  whose semantics (>=, ascending indices) it keeps
+ *   om_decode_select       eval/orienmask_yolo_postprocess.py:75-114,126-139 (get_boxes, confidence
+ *                          filter, pre-NMS top-k) for the whole batch at once
+ *   om_batched_nms         eval/function.py:77-103 (batched_nms) + eval/orienmask_yolo_postprocess.py:146-154
+ *   om_mask_assemble       eval/orienmask_yolo_postprocess.py:69-72,99,141-144,156-164 (bilinear x4,
+ *                          get_orien_grid, per-instance orientation thresholding)
+ *   om_stem_conv, om_conv_*  model/base.py:104-137 (ConvBNRelu, BN folded), model/backbone/darknet.py:6-15
+ *                          (residual add), model/base.py:95-101 + torch.cat in
+ *                          model/orienmask_yolo_fpnplus.py:78-79,85-86 (nearest upsample + concat, done
+ *                          algebraically in the consumer's epilogue)
+ */
+#ifndef ORIENMASK_B200_H_
+#define ORIENMASK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OM_OK 0
+#define OM_ERR_INVALID (-1)      /* bad argument / unsupported shape */
+#define OM_ERR_CUDA (-2)         /* a CUDA runtime / driver call failed */
+#define OM_ERR_UNSUPPORTED (-3)  /* valid request that this build cannot serve */
+
+#define OM_MAX_SCALES 4
+#define OM_MAX_ANCHORS 16
+
+/* Version of this ABI (bumped on any signature change). */
+int32_t om_abi_version(void);
+/* Text of the last error raised on the calling thread. */
+const char* om_last_error(void);
+/* Number of kernel launches enqueued by this library on the calling thread since the last reset. */
+int64_t om_launch_count(void);
+void om_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Post-process: decode + select + NMS + mask assembly                                           */
+/* ------------------------------------------------------------------------------------------- */
+
+/* Constructor arguments of OrienMaskYOLOPostProcess (eval/orienmask_yolo_postprocess.py:9-36). */
+typedef struct om_post_config {
+    int32_t num_scales;                         /* len(grid_size), <= OM_MAX_SCALES               */
+    int32_t num_classes;
+    int32_t image_h, image_w;                   /* image_size                                     */
+    int32_t grid_h[OM_MAX_SCALES];              /* grid_size[i][0]                                */
+    int32_t grid_w[OM_MAX_SCALES];              /* grid_size[i][1]                                */
+    int32_t anchors_per_scale[OM_MAX_SCALES];   /* len(anchor_mask[i]), <= 4                      */
+    int32_t anchor_index[OM_MAX_SCALES][4];     /* anchor_mask                                    */
+    int32_t total_anchors;                      /* len(anchors), <= OM_MAX_ANCHORS                */
+    float anchor_w[OM_MAX_ANCHORS];             /* anchors[a][0], pixels                          */
+    float anchor_h[OM_MAX_ANCHORS];             /* anchors[a][1], pixels                          */
+    float conf_thresh;
+    float nms_thresh;                           /* threshold bound into nms_func by the builder   */
+    float orien_thresh;
+    int32_t nms_pre;                            /* <= 1024                                        */
+    int32_t nms_post;                           /* <= nms_pre                                     */
+} om_post_config;
+
+/* Bytes of device scratch om_decode_select needs for `batch` images. */
+int32_t om_post_workspace_bytes(const om_post_config* cfg, int32_t batch, size_t* bytes);
+
+/*
+ * Box/score decode of every (prediction, class), confidence filter and pre-NMS top-k, for the whole batch.
+ *   bbox[s]            device, fp32 NCHW [batch, A_s*(5+C), grid_h[s], grid_w[s]] (model head layout);
+ *                      image b starts at bbox[s] + b*bbox_batch_stride[s] (elements)
+ *   workspace          device scratch of om_post_workspace_bytes() bytes
+ * Outputs (device), rows beyond cand_count[b] are zero-filled:
+ *   cand_count [batch]            int32   number of candidates kept (<= nms_pre)
+ *   cand_det   [batch,nms_pre,5]  fp32    cx, cy, w, h (normalised), score
+ *   cand_cls   [batch,nms_pre]    int32
+ *   cand_pred  [batch,nms_pre]    int32   flat prediction index (scale-major, then anchor, y, x)
+ * Order inside an image follows the reference: score-descending when more than nms_pre pairs clear
+ * conf_thresh (ties: lower (prediction, class) first), otherwise (prediction, class) row-major.
+ */
+int32_t om_decode_select(const om_post_config* cfg, const float* const* bbox, const int64_t* bbox_batch_stride,
+                         int32_t batch, void* workspace, int32_t* cand_count, float* cand_det,
+                         int32_t* cand_cls, int32_t* cand_pred, void* stream);
+
+/*
+ * Class-wise greedy NMS (centres shifted by cls*2.0 in fp32, IoU >= nms_thresh suppresses) followed by
+ * the post-NMS top-k.  Inputs are om_decode_select's outputs.  Outputs (device), zero-filled past det_count[b]:
+ *   det_count  [batch]             int32
+ *   det        [batch,nms_post,5]  fp32   un-shifted cx, cy, w, h, score
+ *   det_cls    [batch,nms_post]    int64
+ *   det_anchor [batch,nms_post]    int32  global anchor index of the prediction (selects the orientation map)
+ *   det_keep   [batch,nms_post]    int32  index into the candidate list (the reference's `keep`)
+ */
+int32_t om_batched_nms(const om_post_config* cfg, const int32_t* cand_count, const float* cand_det,
+                       const int32_t* cand_cls, const int32_t* cand_pred, int32_t batch, int32_t* det_count,
+                       float* det, int64_t* det_cls, int32_t* det_anchor, int32_t* det_keep, void* stream);
+
+/*
+ * Instance masks: mask[b,k,y,x] = |pix_x - xc| < t*w*nW  &&  |pix_y - yc| < t*h*nH on the x4 bilinear
+ * up-sampling of the low-resolution orientation maps (never materialised).
+ *   orien[s]   device, fp32 [batch, 2*A_s, image_h/4, image_w/4]; image b at orien[s] + b*orien_batch_stride[s]
+ *   mask       device, uint8 (0/1) [batch, nms_post, image_h, image_w]; only rows k < det_count[b] are written
+ */
+int32_t om_mask_assemble(const om_post_config* cfg, const float* const* orien, const int64_t* orien_batch_stride,
+                         const int32_t* det_count, const float* det, const int32_t* det_anchor, int32_t batch,
+                         uint8_t* mask, void* stream);
+
+/*
+ * Stand-alone greedy NMS over one box list (drop-in for the reference's native `nms(dets, threshold)`).
+ *   dets [n,5] device fp32 (cx, cy, w, h, score), n <= 1024
+ *   keep [n]   device int64, out: surviving indices in ascending order (nms_cpu.cpp:62); *keep_count device int32
+ */
+int32_t om_nms(const float* dets, int32_t n, float threshold, int64_t* keep, int32_t* keep_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Convolution engine                                                                            */
+/* ------------------------------------------------------------------------------------------- */
+
+/*
+ * Activation layout ("padded-row NHWC"): a feature map of B images, H x W x C, is stored as
+ * [B * rows_per_image, W, C] with rows_per_image >= H + 1; rows H..rows_per_image-1 of every image
+ * are zero and are never written, so a 3x3 window that leaves an image vertically reads zeros
+ * without any bounds logic (horizontal padding comes from TMA out-of-bounds fill).  Stride-2
+ * convolutions need rows_per_image(in) == 2 * rows_per_image(out).
+ */
+#define OM_PREC_F32 0   /* parity engine: fp32 storage, FFMA                                     */
+#define OM_PREC_F16 1   /* production engine: fp16 storage, tcgen05 tensor cores, fp32 accumulate */
+
+#define OM_OUT_ACT 0      /* padded-row NHWC activation in the engine precision                    */
+#define OM_OUT_PARTIAL 1  /* padded-row NHWC fp32 pre-activation partial sum (no bias, no act)     */
+#define OM_OUT_NCHW 2     /* dense fp32 NCHW [B, cout, H, W] (model head output), bias, no act     */
+
+typedef struct om_conv_desc {
+    int32_t precision;             /* OM_PREC_*                                                   */
+    int32_t batch;
+    int32_t in_h, in_w, in_rows;   /* input map and its rows_per_image                            */
+    int32_t out_h, out_w, out_rows;
+    int32_t cin, cout;             /* cin % 32 == 0 (fp16 engine)                                 */
+    int32_t cout_stride;           /* channel pitch of the output (>= cout), OM_OUT_ACT/PARTIAL   */
+    int32_t ksize;                 /* 1 or 3 (padding ksize/2)                                    */
+    int32_t stride;                /* 1 or 2                                                      */
+    int32_t leaky;                 /* LeakyReLU(0.1) after bias (+upadd)                          */
+    int32_t out_kind;              /* OM_OUT_*                                                    */
+    const void* input;             /* device, engine precision                                    */
+    const void* weights;           /* device: F16 -> [k*k][cout_pad][cin] half, cout_pad = cout rounded up
+                                      to 16 (to 32 when cout < 32);  F32 -> [k*k][cin][cout] float */
+    const float* bias;             /* device [cout] or NULL                                       */
+    const void* residual;          /* device, same layout/precision as an OM_OUT_ACT output, added AFTER the
+                                      activation (darknet.py:15), or NULL                         */
+    const float* upadd;            /* device fp32 padded-row NHWC [B*up_rows, out_w/2, cout] added BEFORE bias and
+                                      activation at (y/2, x/2) (nearest x2 up-sampling), or NULL  */
+    int32_t up_rows;
+    void* output;
+} om_conv_desc;
+
+typedef struct om_conv om_conv;
+
+/* Validates the descriptor and precomputes launch geometry and TMA descriptors. */
+int32_t om_conv_create(const om_conv_desc* desc, om_conv** out);
+int32_t om_conv_run(const om_conv* conv, void* stream);
+void om_conv_destroy(om_conv* conv);
+
+/*
+ * First layer (3 -> cout, 3x3, stride 1, BN folded, LeakyReLU) straight from the caller's image.
+ *   image    device fp32 NCHW [batch,3,h,w]
+ *   weights  device fp32 [27][cout] (tap-major: (ky*3+kx)*3+ci), bias fp32 [cout]; cout == 32
+ *   output   padded-row NHWC [batch*rows, w, cout] in `precision`
+ */
+int32_t om_stem_conv(int32_t precision, const float* image, const float* weights, const float* bias, void* output,
+                     int32_t batch, int32_t h, int32_t w, int32_t rows, int32_t cout, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORIENMASK_B200_H_ */

@@ -1,0 +1,96 @@
+"""ctypes binding of the C-ABI library (include/orienmask_b200.h).
+
+There is no fallback: if ``liborienmask_b200.so`` is missing or a call fails, a RuntimeError is
+raised.  Build it with ``python -m orienmask_b200.build`` (or ``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'liborienmask_b200.so')
+
+OM_MAX_SCALES = 4
+OM_MAX_ANCHORS = 16
+PREC_F32, PREC_F16 = 0, 1
+OUT_ACT, OUT_PARTIAL, OUT_NCHW = 0, 1, 2
+
+c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class PostConfig(ctypes.Structure):
+    _fields_ = [
+        ('num_scales', c_i32), ('num_classes', c_i32), ('image_h', c_i32), ('image_w', c_i32),
+        ('grid_h', c_i32 * OM_MAX_SCALES), ('grid_w', c_i32 * OM_MAX_SCALES),
+        ('anchors_per_scale', c_i32 * OM_MAX_SCALES), ('anchor_index', (c_i32 * 4) * OM_MAX_SCALES),
+        ('total_anchors', c_i32), ('anchor_w', c_f32 * OM_MAX_ANCHORS), ('anchor_h', c_f32 * OM_MAX_ANCHORS),
+        ('conf_thresh', c_f32), ('nms_thresh', c_f32), ('orien_thresh', c_f32),
+        ('nms_pre', c_i32), ('nms_post', c_i32),
+    ]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [
+        ('precision', c_i32), ('batch', c_i32),
+        ('in_h', c_i32), ('in_w', c_i32), ('in_rows', c_i32),
+        ('out_h', c_i32), ('out_w', c_i32), ('out_rows', c_i32),
+        ('cin', c_i32), ('cout', c_i32), ('cout_stride', c_i32),
+        ('ksize', c_i32), ('stride', c_i32), ('leaky', c_i32), ('out_kind', c_i32),
+        ('input', c_vp), ('weights', c_vp), ('bias', c_vp), ('residual', c_vp), ('upadd', c_vp),
+        ('up_rows', c_i32), ('output', c_vp),
+    ]
+
+
+# name -> (restype, argtypes); every symbol declared in include/orienmask_b200.h
+SIGNATURES = {
+    'om_abi_version': (c_i32, []),
+    'om_last_error': (ctypes.c_char_p, []),
+    'om_launch_count': (c_i64, []),
+    'om_launch_count_reset': (None, []),
+    'om_post_workspace_bytes': (c_i32, [ctypes.POINTER(PostConfig), c_i32, ctypes.POINTER(ctypes.c_size_t)]),
+    'om_decode_select': (c_i32, [ctypes.POINTER(PostConfig), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), c_i32,
+                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'om_batched_nms': (c_i32, [ctypes.POINTER(PostConfig), c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'om_mask_assemble': (c_i32, [ctypes.POINTER(PostConfig), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),
+                                 c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    'om_nms': (c_i32, [c_vp, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    'om_conv_create': (c_i32, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_vp)]),
+    'om_conv_run': (c_i32, [c_vp, c_vp]),
+    'om_conv_destroy': (None, [c_vp]),
+    'om_stem_conv': (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises RuntimeError (never falls back) when it is unavailable."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('orienmask_b200: %s is missing -- run `python -m orienmask_b200.build`; '
+                               'there is no CPU or eager fallback' % LIB_PATH)
+        try:
+            handle = ctypes.CDLL(LIB_PATH)
+        except OSError as e:
+            raise RuntimeError('orienmask_b200: cannot load %s: %s' % (LIB_PATH, e))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so does not export it
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().om_last_error()
+        raise RuntimeError('orienmask_b200.%s failed (%d): %s' % (what, rc, msg.decode() if msg else ''))
+
+
+def stream_ptr():
+    import torch
+    return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return c_vp(t.data_ptr()) if t is not None else c_vp(0)

@@ -1,0 +1,73 @@
+// C-ABI plumbing: error text, launch accounting, convolution plan objects.
+#include <cstdarg>
+#include <cstring>
+
+#include "common.cuh"
+#include "conv_plan.h"
+
+namespace om {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+char* error_buffer() { return g_err; }
+
+int32_t fail(int32_t code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launch(int n) { g_launches += n; }
+
+}  // namespace om
+
+struct om_conv {
+    om_conv_desc desc;
+    void* tc_plan;
+};
+
+extern "C" int32_t om_abi_version(void) { return 1; }
+extern "C" const char* om_last_error(void) { return om::error_buffer(); }
+extern "C" int64_t om_launch_count(void) { return om::g_launches; }
+extern "C" void om_launch_count_reset(void) { om::g_launches = 0; }
+
+extern "C" int32_t om_conv_create(const om_conv_desc* d, om_conv** out) {
+    if (!d || !out) return om::fail(OM_ERR_INVALID, "om_conv_create: null argument");
+    if (d->precision != OM_PREC_F32 && d->precision != OM_PREC_F16) return om::fail(OM_ERR_INVALID, "unknown precision %d", d->precision);
+    if (d->ksize != 1 && d->ksize != 3) return om::fail(OM_ERR_UNSUPPORTED, "ksize must be 1 or 3 (got %d)", d->ksize);
+    if (d->stride != 1 && d->stride != 2) return om::fail(OM_ERR_UNSUPPORTED, "stride must be 1 or 2 (got %d)", d->stride);
+    if (d->batch < 1 || d->in_h < 1 || d->in_w < 1 || d->out_h < 1 || d->out_w < 1 || d->cin < 1 || d->cout < 1)
+        return om::fail(OM_ERR_INVALID, "om_conv_create: non-positive dimension");
+    if (d->in_rows <= d->in_h) return om::fail(OM_ERR_INVALID, "in_rows must exceed in_h (zero rows between images)");
+    if (d->out_kind != OM_OUT_NCHW && d->out_rows <= d->out_h) return om::fail(OM_ERR_INVALID, "out_rows must exceed out_h");
+    if (d->out_kind < OM_OUT_ACT || d->out_kind > OM_OUT_NCHW) return om::fail(OM_ERR_INVALID, "unknown out_kind %d", d->out_kind);
+    if (d->out_h != (d->in_h + d->stride - 1) / d->stride || d->out_w != (d->in_w + d->stride - 1) / d->stride)
+        return om::fail(OM_ERR_INVALID, "output geometry does not match 'same' padding with stride %d", d->stride);
+    if (!d->input || !d->weights || !d->output) return om::fail(OM_ERR_INVALID, "om_conv_create: null tensor pointer");
+    if (d->residual && d->out_kind != OM_OUT_ACT) return om::fail(OM_ERR_INVALID, "residual only with activation outputs");
+    if (d->upadd && d->up_rows < 1) return om::fail(OM_ERR_INVALID, "upadd needs up_rows");
+    om_conv* c = new om_conv();
+    c->desc = *d;
+    c->tc_plan = nullptr;
+    if (d->precision == OM_PREC_F16) {
+        int32_t rc = om::tc_plan_create(*d, &c->tc_plan);
+        if (rc != OM_OK) { delete c; return rc; }
+    }
+    *out = c;
+    return OM_OK;
+}
+
+extern "C" int32_t om_conv_run(const om_conv* c, void* stream) {
+    if (!c) return om::fail(OM_ERR_INVALID, "om_conv_run: null plan");
+    if (c->desc.precision == OM_PREC_F16) return om::tc_plan_run(c->tc_plan, (cudaStream_t)stream);
+    return om::f32_conv_run(c->desc, (cudaStream_t)stream);
+}
+
+extern "C" void om_conv_destroy(om_conv* c) {
+    if (!c) return;
+    if (c->tc_plan) om::tc_plan_destroy(c->tc_plan);
+    delete c;
+}

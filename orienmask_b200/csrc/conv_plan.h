@@ -1,0 +1,18 @@
+// Internal interface between the C-ABI entry points (api.cu) and the two convolution engines.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstring>
+
+#include "../../include/orienmask_b200.h"
+
+namespace om {
+
+// fp16 tcgen05 engine (conv_tc.cu)
+int32_t tc_plan_create(const om_conv_desc& d, void** out);
+int32_t tc_plan_run(const void* plan, cudaStream_t stream);
+void tc_plan_destroy(void* plan);
+
+// fp32 FFMA parity engine (conv_f32.cu)
+int32_t f32_conv_run(const om_conv_desc& d, cudaStream_t stream);
+
+}  // namespace om

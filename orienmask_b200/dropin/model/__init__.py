@@ -1,0 +1,9 @@
+"""Drop-in for the reference's ``model`` package (trainer/builder.py:12, infer.py:13 look classes up by name here)."""
+import os
+import sys
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from orienmask_b200.model import OrienMaskYOLOFPNPlus  # noqa: E402,F401

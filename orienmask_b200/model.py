@@ -1,0 +1,304 @@
+"""``OrienMaskYOLOFPNPlus`` with the reference interface, executed by the sm_100a convolution engine.
+
+Interface mirrored (``/root/reference/model/orienmask_yolo_fpnplus.py:8-37,74-90``): same
+constructor arguments, the same 524 state-dict keys (so ``load_state_dict(strict=True)`` of a
+reference checkpoint works), ``forward(x) -> ((bbox32, orien32), (bbox16, orien16), (bbox8, orien8))``
+with fp32 NCHW tensors.  The modules below only *hold* parameters under the reference's names; the
+arithmetic is a static schedule of C-ABI kernels over a preallocated buffer plan:
+
+* BN folded into fp16 (or fp32, parity mode) weights once per weight version;
+* every ConvBNLeaky = one kernel (bias + LeakyReLU in the epilogue), residual adds fused into the
+  3x3 of each DarkNet block, in place;
+* ``cat([nearest_up(route), x])`` followed by a 1x1 conv is evaluated as
+  ``W_x * x + nearest_up(W_r * route)``: the low-resolution product is a small fp32 "partial" that the
+  high-resolution kernel adds in its epilogue, so neither the up-sampled nor the concatenated tensor
+  ever exists (both are exact re-associations of the reference's sum);
+* inference only (BatchNorm always uses running statistics); CUDA only -- no fallback.
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .arch import conv_specs, STAGE_BLOCKS, STAGE_CHANNELS
+
+
+class _Params(nn.Module):
+    """Parameter holder; never called."""
+
+    def forward(self, *a, **k):
+        raise RuntimeError('parameter holder')
+
+
+def _holder(root, dotted):
+    mod = root
+    for part in dotted.split('.'):
+        if part not in mod._modules:
+            mod.add_module(part, _Params())
+        mod = mod._modules[part]
+    return mod
+
+
+class OrienMaskYOLOFPNPlus(nn.Module):
+    def __init__(self, num_anchors, num_classes, pretrained=None, freeze_backbone=False, backbone_batchnorm_eval=False):
+        super().__init__()
+        self.num_anchors, self.num_classes = num_anchors, num_classes
+        self.precision = os.environ.get('ORIENMASK_B200_PRECISION', 'fp16')     # 'fp16' (tcgen05) | 'fp32' (parity)
+        self._specs = conv_specs(num_anchors, num_classes)
+        for s in self._specs:
+            fan_in = s.cin * s.k * s.k
+            w = torch.empty(s.cout, s.cin, s.k, s.k)
+            nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+            if s.kind == 'cbl':
+                conv = _holder(self, s.prefix + '.conv_block.0')
+                conv.weight = nn.Parameter(w)
+                bn = _holder(self, s.prefix + '.conv_block.1')
+                bn.weight = nn.Parameter(torch.ones(s.cout))
+                bn.bias = nn.Parameter(torch.zeros(s.cout))
+                bn.register_buffer('running_mean', torch.zeros(s.cout))
+                bn.register_buffer('running_var', torch.ones(s.cout))
+                bn.register_buffer('num_batches_tracked', torch.tensor(0, dtype=torch.long))
+            else:
+                conv = _holder(self, s.prefix)
+                conv.weight = nn.Parameter(w)
+                bound = 1.0 / math.sqrt(fan_in)
+                conv.bias = nn.Parameter(torch.empty(s.cout).uniform_(-bound, bound))
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._engines = {}
+        self._weights_version = 0
+        if pretrained is not None:            # backbone checkpoint: take every key that exists with the same shape
+            ckpt = torch.load(pretrained, map_location='cpu')
+            own = self.state_dict()
+            own.update({k: v for k, v in ckpt.items() if k in own and v.shape == own[k].shape})
+            self.load_state_dict(own)
+
+    # -- weight-version tracking: any reload or device/dtype move drops the packed weights ---------
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._invalidate()
+        return r
+
+    def _apply(self, fn, *a, **k):
+        r = super()._apply(fn, *a, **k)
+        self._invalidate()
+        return r
+
+    def _invalidate(self):
+        self._engines = {}
+        self._weights_version += 1
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('orienmask_b200 runs on CUDA (sm_100a) only; got a %s tensor and there is no CPU fallback' % x.device)
+        if x.dim() != 4 or x.size(1) != 3 or x.size(2) % 32 or x.size(3) % 32:
+            raise ValueError('expected [B,3,H,W] with H, W multiples of 32, got %s' % (tuple(x.shape),))
+        key = (int(x.size(0)), int(x.size(2)), int(x.size(3)), self.precision, x.device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _Engine(self, *key[:3], precision=self.precision, device=x.device)
+            self._engines[key] = eng
+        return eng.run(x)
+
+
+class _Engine:
+    """Static buffer plan + launch schedule for one (batch, H, W, precision)."""
+
+    def __init__(self, model, B, H, W, precision, device):
+        if precision not in ('fp16', 'fp32'):
+            raise ValueError("precision must be 'fp16' or 'fp32'")
+        self.lib = _lib.lib()
+        self.B, self.H, self.W, self.device = B, H, W, device
+        self.prec = _lib.PREC_F16 if precision == 'fp16' else _lib.PREC_F32
+        self.adt = torch.float16 if precision == 'fp16' else torch.float32
+        self.nA, self.nC = model.num_anchors, model.num_classes
+        self.sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in model.state_dict().items()
+                   if v.is_floating_point()}
+        self.keep = []            # owns every device tensor the plans point to
+        self.plans = []           # ('stem', args) | ('conv', handle)
+        self.flops = 0
+        with torch.cuda.device(device):
+            self._build()
+        self.sd = None
+
+    # ---- buffers ---------------------------------------------------------------------------------
+    def rows(self, stride):
+        return self.H // stride + 32 // stride
+
+    def act(self, stride, channels, dtype=None):
+        t = torch.zeros(self.B * self.rows(stride), self.W // stride, channels, dtype=dtype or self.adt, device=self.device)
+        self.keep.append(t)
+        return dict(t=t, stride=stride, c=channels)
+
+    # ---- weights ---------------------------------------------------------------------------------
+    def folded(self, prefix, kind):
+        sd = self.sd
+        if kind == 'cbl':
+            w = sd[prefix + '.conv_block.0.weight']
+            g, b = sd[prefix + '.conv_block.1.weight'], sd[prefix + '.conv_block.1.bias']
+            mu, var = sd[prefix + '.conv_block.1.running_mean'], sd[prefix + '.conv_block.1.running_var']
+            scale = g / torch.sqrt(var + 1e-5)
+            return w * scale.view(-1, 1, 1, 1), b - mu * scale
+        return sd[prefix + '.weight'], sd[prefix + '.bias']
+
+    def pack(self, w):
+        """[cout, cin, k, k] fp32 -> engine layout (see om_conv_desc.weights)."""
+        cout, cin, k, _ = w.shape
+        if self.prec == _lib.PREC_F16:
+            cpad = max(32, (cout + 15) // 16 * 16)
+            p = torch.zeros(k * k, cpad, cin, dtype=torch.float16, device=self.device)
+            p[:, :cout] = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).to(torch.float16)
+        else:
+            cpad = (cout + 3) // 4 * 4
+            p = torch.zeros(k * k, cin, cpad, dtype=torch.float32, device=self.device)
+            p[:, :, :cout] = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout)
+        self.keep.append(p)
+        return p
+
+    # ---- op emission -----------------------------------------------------------------------------
+    def conv(self, src, w, bias, dst, k, stride=1, leaky=True, kind=_lib.OUT_ACT, residual=None, upadd=None, nchw=None):
+        d = _lib.ConvDesc()
+        d.precision, d.batch = self.prec, self.B
+        si = src['stride']
+        so = si * stride
+        d.in_h, d.in_w, d.in_rows = self.H // si, self.W // si, self.rows(si)
+        d.out_h, d.out_w, d.out_rows = self.H // so, self.W // so, self.rows(so)
+        d.cin, d.cout = w.shape[1], w.shape[0]
+        d.ksize, d.stride, d.leaky, d.out_kind = k, stride, int(leaky), kind
+        d.input = src['t'].data_ptr()
+        d.weights = self.pack(w).data_ptr()
+        if bias is not None:
+            b = bias.contiguous().clone()
+            self.keep.append(b)
+            d.bias = b.data_ptr()
+        if kind == _lib.OUT_NCHW:
+            d.cout_stride = d.cout
+            d.output = nchw.data_ptr()
+        else:
+            assert dst['stride'] == so and dst['c'] == d.cout
+            d.cout_stride = dst['c']
+            d.output = dst['t'].data_ptr()
+        if residual is not None:
+            d.residual = residual['t'].data_ptr()
+        if upadd is not None:
+            assert upadd['stride'] == 2 * so and upadd['c'] == d.cout
+            d.upadd = upadd['t'].data_ptr()
+            d.up_rows = self.rows(upadd['stride'])
+        handle = _lib.c_vp()
+        _lib.check(self.lib.om_conv_create(d, handle), 'om_conv_create')
+        self.plans.append(('conv', handle))
+        self.flops += 2 * d.batch * d.out_h * d.out_w * d.cout * d.cin * k * k
+
+    def cbl(self, prefix, src, dst, k, stride=1, residual=None):
+        w, b = self.folded(prefix, 'cbl')
+        self.conv(src, w, b, dst, k, stride, True, residual=residual)
+
+    def chain(self, prefix, src, bufs, ks, first_upadd=None, first_cols=None):
+        """conv_bn_leaky sequence <prefix>.0.. ; bufs alternate; optional concat-split on the first conv."""
+        cur = src
+        for i, k in enumerate(ks):
+            w, b = self.folded('%s.%d' % (prefix, i), 'cbl')
+            dst = bufs[i % 2]
+            if i == 0 and first_cols is not None:
+                w = w[:, first_cols[0]:first_cols[1]].contiguous()
+            self.conv(cur, w, b, dst, k, upadd=first_upadd if i == 0 else None)
+            cur = dst
+        return cur
+
+    def partial(self, prefix, cols, src, upadd=None):
+        """fp32 pre-activation partial W[:, cols] * src (+ nearest-up of a coarser partial)."""
+        w, _ = self.folded(prefix, 'cbl')
+        w = w[:, cols[0]:cols[1]].contiguous()
+        dst = self.act(src['stride'], w.shape[0], torch.float32)
+        self.conv(src, w, None, dst, 1, leaky=False, kind=_lib.OUT_PARTIAL, upadd=upadd)
+        return dst
+
+    def head(self, prefix, src, out):
+        w, b = self.folded(prefix, 'conv')
+        self.conv(src, w, b, None, 1, leaky=False, kind=_lib.OUT_NCHW, nchw=out)
+
+    # ---- the schedule (model/orienmask_yolo_fpnplus.py:74-90, model/backbone/darknet.py:47-54) ----
+    def _build(self):
+        B, H, W, dev = self.B, self.H, self.W, self.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        w1, b1 = self.folded('backbone.conv1', 'cbl')
+        self.stem_w = w1.permute(2, 3, 1, 0).reshape(27, 32).contiguous()
+        self.stem_b = b1.contiguous()
+        c1 = self.act(1, 32)
+        self.plans.append(('stem', c1))
+        self.flops += 2 * B * H * W * 32 * 27
+
+        trunk = c1
+        feats = {}
+        for i, (c, n) in enumerate(zip(STAGE_CHANNELS, STAGE_BLOCKS)):
+            stage = 'backbone.conv%d' % (i + 2)
+            st = 2 ** (i + 1)
+            x = self.act(st, 2 * c)
+            y = self.act(st, c)
+            self.cbl(stage + '.0', trunk, x, 3, stride=2)
+            for b in range(1, n + 1):
+                self.cbl('%s.%d.conv.0' % (stage, b), x, y, 1)
+                self.cbl('%s.%d.conv.1' % (stage, b), y, x, 3, residual=x)      # in place: x += leaky(conv(y))
+            trunk = x
+            feats[st] = x
+        x4, x8, x16, x32 = feats[4], feats[8], feats[16], feats[32]
+        ks = (1, 3, 1, 3, 1)
+
+        neck32 = self.chain('neck32', x32, (self.act(32, 512), self.act(32, 1024)), ks)
+        r32 = self.act(32, 256)
+        self.cbl('route32.0', neck32, r32, 1)
+        p16 = self.partial('neck16.0', (0, 256), r32)
+        neck16 = self.chain('neck16', x16, (self.act(16, 256), self.act(16, 512)), ks, first_upadd=p16, first_cols=(256, 768))
+        r16 = self.act(16, 128)
+        self.cbl('route16.0', neck16, r16, 1)
+        p8 = self.partial('neck8.0', (0, 128), r16)
+        neck8 = self.chain('neck8', x8, (self.act(8, 128), self.act(8, 256)), ks, first_upadd=p8, first_cols=(128, 384))
+
+        nb = self.nA * (5 + self.nC)
+        self.out_bbox = []
+        for st, neck, c in ((32, neck32, 512), (16, neck16, 256), (8, neck8, 128)):
+            hb = self.act(st, 2 * c)
+            self.cbl('bbox_head%d.0' % st, neck, hb, 3)
+            out = torch.empty(B, nb, H // st, W // st, **f32)
+            self.head('bbox_head%d.1' % st, hb, out)
+            self.out_bbox.append(out)
+
+        s32, s16, s8, s4 = self.act(32, 64), self.act(16, 64), self.act(8, 64), self.act(4, 64)
+        self.cbl('skip32.0', neck32, s32, 1)
+        self.cbl('skip16.0', neck16, s16, 1)
+        self.cbl('skip8.0', neck8, s8, 1)
+        self.cbl('skip4', x4, s4, 1)
+        q32 = self.partial('neck4.0', (0, 64), s32)
+        q16 = self.partial('neck4.0', (64, 128), s16, upadd=q32)
+        q8 = self.partial('neck4.0', (128, 192), s8, upadd=q16)
+        a4, b4 = self.act(4, 128), self.act(4, 256)
+        neck4 = self.chain('neck4', s4, (a4, b4), ks, first_upadd=q8, first_cols=(192, 256))
+        # orien_head.0-4 alternate 3x3 (128->256) and 1x1 (256->128): neck4 lives in a4, so start on b4
+        o = self.chain('orien_head', neck4, (b4, a4), (3, 1, 3, 1, 3))
+        self.out_orien = torch.empty(B, self.nA * 6, H // 4, W // 4, **f32)
+        self.head('orien_head.5', o, self.out_orien)
+
+    def run(self, x):
+        x = x.contiguous().float()
+        with torch.cuda.device(self.device):
+            stream = _lib.stream_ptr()
+            for kind, arg in self.plans:
+                if kind == 'conv':
+                    _lib.check(self.lib.om_conv_run(arg, stream), 'om_conv_run')
+                else:
+                    _lib.check(self.lib.om_stem_conv(self.prec, _lib.ptr(x), _lib.ptr(self.stem_w), _lib.ptr(self.stem_b),
+                                                     _lib.ptr(arg['t']), self.B, self.H, self.W, self.rows(1), 32, stream),
+                               'om_stem_conv')
+        n2 = self.nA * 2
+        o = self.out_orien
+        return ((self.out_bbox[0], o[:, 0:n2]), (self.out_bbox[1], o[:, n2:2 * n2]), (self.out_bbox[2], o[:, 2 * n2:3 * n2]))
+
+    def __del__(self):
+        try:
+            for kind, arg in self.plans:
+                if kind == 'conv':
+                    self.lib.om_conv_destroy(arg)
+        except Exception:
+            pass

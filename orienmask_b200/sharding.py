@@ -1,0 +1,54 @@
+"""Batch sharding over ranks and the single collective of the inference path.
+
+Images are independent through forward, decode, NMS and mask assembly (BatchNorm is in eval mode,
+the reference loops over images, eval/orienmask_yolo_postprocess.py:75), so a batch is split
+contiguously over the ranks with no data-path collective.  The only exchange is an all-gather of
+the fixed-size detection records ``[B_local, nms_post, 6]`` fp32 (cx, cy, w, h, score, cls) plus
+``[B_local]`` counts -- 76.9 KB per rank at batch 32; masks stay on the GPU that produced them.
+The reference itself has no multi-GPU inference (infer.py:69 asserts n_gpu == 1).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(total, rank, world):
+    """Contiguous split of ``total`` images: rank r gets [lo, hi); earlier ranks take the remainder."""
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(images, rank=None, world=None):
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    lo, hi = shard_bounds(images.shape[0], rank, world)
+    return images[lo:hi]
+
+
+def pack_records(det, cls, count):
+    """[B,K,5] fp32 + [B,K] int64 + [B] int32 -> [B, K*6+1] fp32 rows (count bit-stored as a float value)."""
+    B, K, _ = det.shape
+    rec = torch.cat([det, cls.to(torch.float32).unsqueeze(-1)], dim=-1).reshape(B, K * 6)
+    return torch.cat([rec, count.to(torch.float32).view(B, 1)], dim=1).contiguous()
+
+
+def unpack_records(packed, K):
+    B = packed.shape[0]
+    rec = packed[:, :K * 6].reshape(B, K, 6)
+    return rec[..., :5].contiguous(), rec[..., 5].to(torch.int64), packed[:, K * 6].to(torch.int32)
+
+
+def gather_detections(det, cls, count, group=None):
+    """All-gather the padded detection records of every rank (equal B_local per rank).
+
+    Returns (det [B_total,K,5], cls [B_total,K], count [B_total]) in rank order, on every rank.
+    """
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return det, cls, count
+    K = det.shape[1]
+    packed = pack_records(det, cls, count)
+    world = dist.get_world_size(group)
+    out = torch.empty(world * packed.shape[0], packed.shape[1], dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    return unpack_records(out, K)

@@ -40,3 +40,102 @@ def unpack_masks(gold, prefix, b):
     shape = tuple(int(v) for v in gold['%s_maskshape_%d' % (prefix, b)])
     n = int(np.prod(shape))
     return np.unpackbits(gold['%s_maskbits_%d' % (prefix, b)])[:n].reshape(shape).astype(bool)
+
+
+# ---- helpers for the convolution-engine tests (GPU) ---------------------------------------------
+def to_padded(x, rows, dtype):
+    """NCHW -> padded-row NHWC [B*rows, W, C] with zero rows after each image."""
+    B, C, H, W = x.shape
+    out = torch.zeros(B * rows, W, C, dtype=dtype, device=x.device)
+    out.view(B, rows, W, C)[:, :H] = x.permute(0, 2, 3, 1).to(dtype)
+    return out
+
+
+def from_padded(t, B, H):
+    rows = t.shape[0] // B
+    return t.view(B, rows, t.shape[1], t.shape[2])[:, :H].permute(0, 3, 1, 2).float()
+
+
+def pack_weights(w, precision):
+    from orienmask_b200 import _lib
+    cout, cin, k, _ = w.shape
+    if precision == _lib.PREC_F16:
+        cpad = max(32, (cout + 15) // 16 * 16)
+        p = torch.zeros(k * k, cpad, cin, dtype=torch.float16, device=w.device)
+        p[:, :cout] = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).half()
+    else:
+        cpad = (cout + 3) // 4 * 4
+        p = torch.zeros(k * k, cin, cpad, dtype=torch.float32, device=w.device)
+        p[:, :, :cout] = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout)
+    return p
+
+
+def run_engine_conv(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upadd=None, precision=1, extra_rows=1):
+    """One om_conv_* call on NCHW torch inputs; returns NCHW fp32 (pad rows checked to stay zero)."""
+    from orienmask_b200 import _lib
+    lib = _lib.lib()
+    B, cin, H, W = x.shape
+    cout, _, k, _ = w.shape
+    Ho, Wo = H // stride, W // stride
+    rows_o = Ho + extra_rows
+    rows_i = rows_o * stride
+    adt = torch.float16 if precision == _lib.PREC_F16 else torch.float32
+    xin = to_padded(x, rows_i, adt)
+    wp = pack_weights(w, precision)
+    d = _lib.ConvDesc()
+    d.precision, d.batch = precision, B
+    d.in_h, d.in_w, d.in_rows, d.out_h, d.out_w, d.out_rows = H, W, rows_i, Ho, Wo, rows_o
+    d.cin, d.cout, d.cout_stride, d.ksize, d.stride, d.leaky, d.out_kind = cin, cout, cout, k, stride, int(leaky), kind
+    d.input, d.weights = xin.data_ptr(), wp.data_ptr()
+    keep = [xin, wp]
+    if bias is not None:
+        b = bias.float().contiguous()
+        keep.append(b)
+        d.bias = b.data_ptr()
+    if kind == _lib.OUT_NCHW:
+        out = torch.full((B, cout, Ho, Wo), float('nan'), dtype=torch.float32, device=x.device)
+    elif kind == _lib.OUT_PARTIAL:
+        out = torch.zeros(B * rows_o, Wo, cout, dtype=torch.float32, device=x.device)
+    else:
+        out = torch.zeros(B * rows_o, Wo, cout, dtype=adt, device=x.device)
+    d.output = out.data_ptr()
+    if residual is not None:
+        r = to_padded(residual, rows_o, adt)
+        keep.append(r)
+        d.residual = r.data_ptr()
+    if upadd is not None:
+        up_rows = Ho // 2 + 1
+        u = to_padded(upadd, up_rows, torch.float32)
+        keep.append(u)
+        d.upadd, d.up_rows = u.data_ptr(), up_rows
+    h = _lib.c_vp()
+    _lib.check(lib.om_conv_create(d, h), 'om_conv_create')
+    try:
+        _lib.check(lib.om_conv_run(h, _lib.stream_ptr()), 'om_conv_run')
+        torch.cuda.synchronize()
+    finally:
+        lib.om_conv_destroy(h)
+    if kind == _lib.OUT_NCHW:
+        return out
+    pad = out.view(B, rows_o, Wo, cout)[:, Ho:]
+    assert float(pad.abs().max()) == 0.0, 'padding rows were written'
+    return from_padded(out, B, Ho)
+
+
+def torch_conv_ref(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upadd=None, quantize=False):
+    """fp32 torch reference of the same fused op (optionally on fp16-rounded operands)."""
+    import torch.nn.functional as F
+    if quantize:
+        x, w = x.half().float(), w.half().float()
+        if residual is not None:
+            residual = residual.half().float()
+    y = F.conv2d(x.double(), w.double(), None, stride=stride, padding=w.shape[-1] // 2)
+    if upadd is not None:
+        y = y + F.interpolate(upadd.double(), scale_factor=2, mode='nearest')
+    if bias is not None and kind != 1:
+        y = y + bias.double().view(1, -1, 1, 1)
+    if leaky:
+        y = F.leaky_relu(y, 0.1)
+    if residual is not None:
+        y = y + residual.double()
+    return y.float()

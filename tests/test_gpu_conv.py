@@ -1,0 +1,62 @@
+"""GPU numerics of the convolution engines (C-ABI om_conv_*) against a plain PyTorch fp64 reference."""
+import pytest
+import torch
+
+from tests.common import run_engine_conv, torch_conv_ref
+
+pytestmark = pytest.mark.gpu
+
+F32, F16 = 0, 1
+ACT, PARTIAL, NCHW = 0, 1, 2
+
+# (B, cin, cout, H, W, k, stride, kind, residual, upadd)
+CASES = [
+    (2, 64, 128, 16, 16, 1, 1, ACT, False, False),
+    (2, 64, 128, 17, 34, 3, 1, ACT, False, False),
+    (1, 128, 256, 34, 34, 3, 1, ACT, True, False),
+    (3, 32, 64, 32, 32, 3, 2, ACT, False, False),
+    (2, 64, 32, 16, 16, 1, 1, ACT, False, False),
+    (2, 32, 64, 16, 16, 3, 1, ACT, True, False),
+    (2, 128, 256, 20, 12, 3, 2, ACT, False, False),
+    (2, 512, 1024, 6, 6, 3, 1, ACT, False, False),
+    (2, 256, 255, 8, 8, 1, 1, NCHW, False, False),
+    (1, 256, 18, 24, 24, 1, 1, NCHW, False, False),
+    (2, 64, 128, 12, 12, 1, 1, PARTIAL, False, True),
+    (2, 512, 256, 12, 12, 1, 1, ACT, False, True),
+    (1, 128, 256, 136, 136, 3, 1, ACT, False, False),
+]
+
+
+def _data(case, seed=0):
+    B, cin, cout, H, W, k, stride, kind, use_res, use_up = case
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, cin, H, W, generator=g).cuda()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    b = torch.randn(cout, generator=g).cuda() if kind != PARTIAL else None
+    Ho, Wo = H // stride, W // stride
+    res = torch.randn(B, cout, Ho, Wo, generator=g).cuda() if use_res else None
+    up = torch.randn(B, cout, Ho // 2, Wo // 2, generator=g).cuda() if use_up else None
+    return x, w, b, res, up
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_f32_engine(case):
+    B, cin, cout, H, W, k, stride, kind, _, _ = case
+    x, w, b, res, up = _data(case)
+    leaky = kind == ACT
+    got = run_engine_conv(x, w, b, stride, leaky, kind, res, up, precision=F32)
+    ref = torch_conv_ref(x, w, b, stride, leaky, kind, res, up)
+    assert torch.allclose(got, ref, atol=2e-4, rtol=1e-4), float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_tcgen05_engine(case):
+    B, cin, cout, H, W, k, stride, kind, _, _ = case
+    x, w, b, res, up = _data(case)
+    leaky = kind == ACT
+    got = run_engine_conv(x, w, b, stride, leaky, kind, res, up, precision=F16)
+    # operands rounded to fp16 exactly as the engine stores them; accumulation is fp32 in both
+    ref = torch_conv_ref(x, w, b, stride, leaky, kind, res, up, quantize=True)
+    tol = 2e-3 if kind != ACT else 1e-2           # fp16 output rounding for activation outputs
+    err = float((got - ref).abs().max())
+    assert torch.allclose(got, ref, atol=tol, rtol=4e-3), err

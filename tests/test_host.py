@@ -1,0 +1,107 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, the host mirrors keep the
+reference interface, sharding logic (gloo, world size 2)."""
+import ctypes
+import functools
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from tests.common import ROOT, post_config
+
+
+def test_library_exports_every_declared_symbol():
+    from orienmask_b200 import _lib, build
+    build.build()
+    header = open(os.path.join(ROOT, 'include', 'orienmask_b200.h')).read()
+    declared = set(re.findall(r'\b(om_[a-z0-9_]+)\s*\(', header))
+    declared -= {'om_conv'}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), name
+    assert _lib.lib().om_abi_version() == 1
+
+
+def test_config_errors_are_reported_without_a_gpu():
+    from orienmask_b200 import _lib
+    lib = _lib.lib()
+    cfg = _lib.PostConfig()
+    n = ctypes.c_size_t(0)
+    rc = lib.om_post_workspace_bytes(ctypes.byref(cfg), 1, ctypes.byref(n))
+    assert rc == -1 and b'num_scales' in lib.om_last_error()
+
+
+def test_model_state_dict_layout_and_loud_cpu_failure():
+    import orienmask_b200 as ob
+    from orienmask_b200.arch import state_dict_shapes, macs_per_image
+    from orienmask_b200.synthetic import synthetic_state_dict
+    m = ob.OrienMaskYOLOFPNPlus(num_anchors=3, num_classes=80, pretrained=None, freeze_backbone=False,
+                                backbone_batchnorm_eval=False)
+    sd = m.state_dict()
+    shapes = state_dict_shapes()
+    assert len(sd) == 524 and set(sd) == set(shapes)
+    m.load_state_dict(synthetic_state_dict(0), strict=True)
+    assert abs(macs_per_image(544, 544)[0] - 86.9226e9) < 1e6          # 86.9226 GMAC
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(torch.zeros(1, 3, 64, 64))
+
+
+def test_postprocess_constructor_mirrors_reference():
+    import orienmask_b200 as ob
+    cfg = post_config(544, 544)
+    p = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.45), device=None, **cfg)
+    assert abs(p.nms_thresh - 0.45) < 1e-9 and p.nms_pre == 400 and p.nms_post == 100
+    assert ob.OrienMaskYOLOPostProcess(**cfg).nms_thresh == 0.5
+    with pytest.raises(NotImplementedError):
+        ob.OrienMaskYOLOPostProcess(nms_func=lambda d, c: (d, c, None), **cfg)
+
+
+def test_dropin_packages_resolve_reference_names():
+    """trainer/builder.py:61-77 does getattr(model, 'OrienMaskYOLOFPNPlus'), getattr(eval, 'OrienMaskYOLOPostProcess'),
+    getattr(eval.function, 'batched_nms')."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); import model, eval, eval.function as f; "
+            "print(model.OrienMaskYOLOFPNPlus.__module__, eval.OrienMaskYOLOPostProcess.__module__, f.batched_nms.__module__)"
+            % os.path.join(ROOT, 'orienmask_b200', 'dropin'))
+    out = subprocess.check_output([sys.executable, '-c', code], cwd='/tmp').decode().split()
+    assert out == ['orienmask_b200.model', 'orienmask_b200.postprocess', 'orienmask_b200.function']
+
+
+def test_shard_bounds_cover_batch():
+    from orienmask_b200.sharding import shard_bounds
+    for total in (1, 7, 32, 33):
+        for world in (1, 2, 4, 8):
+            spans = [shard_bounds(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from orienmask_b200.sharding import gather_detections, shard_bounds
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    det = torch.rand(4, 10, 5, generator=g)
+    cls = torch.randint(0, 80, (4, 10), generator=g)
+    cnt = torch.randint(0, 11, (4,), generator=g, dtype=torch.int32)
+    lo, hi = shard_bounds(4, rank, world)
+    d, c, n = gather_detections(det[lo:hi], cls[lo:hi], cnt[lo:hi])
+    q.put((rank, torch.equal(d, det) and torch.equal(c, cls) and torch.equal(n, cnt)))
+    dist.destroy_process_group()
+
+
+def test_gather_detections_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(results) == [(0, True), (1, True)]
