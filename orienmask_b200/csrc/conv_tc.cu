@@ -444,10 +444,13 @@ int32_t tc_plan_create(const om_conv_desc& d, void** out) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     plan->grid = tiles < sms ? tiles : sms;
+    // the attribute is per kernel function, not per launch: always opt in to the full 227 KB
+    constexpr int kMaxSmem = 227 * 1024;
+    if (plan->smem > (size_t)kMaxSmem) { delete plan; return fail(OM_ERR_INVALID, "tile needs %zu bytes of shared memory", plan->smem); }
     cudaError_t e = bk == 64
-        ? cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem)
-        : cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem);
-    if (e != cudaSuccess) { delete plan; return fail(OM_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", plan->smem, cudaGetErrorString(e)); }
+        ? cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
+        : cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) { delete plan; return fail(OM_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); }
     *out = plan;
     return OM_OK;
 }

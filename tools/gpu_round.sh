@@ -1,10 +1,29 @@
 #!/bin/bash
-# Standard GPU visit: parity tests (one process per file), tcgen05 probe, bench.  Logs -> gpurun_out/.
+# Standard GPU visit: parity tests (one process per file), bench, ncu launch list + one full capture.
+# Logs -> gpurun_out/.  Usage: bash tools/gpu_round.sh [tests] [probe] [bench] [ncu] [full]
 mkdir -p gpurun_out
+what="${*:-tests bench ncu}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in post conv forward; do
-  timeout 900 python -m pytest tests/test_gpu_$f.py -q -m gpu -x --timeout 600 > gpurun_out/test_$f.log 2>&1
-  echo "test_gpu_$f exit $?"; tail -5 gpurun_out/test_$f.log
-done
-timeout 900 python tools/tc_probe.py > gpurun_out/tc_probe.log 2>&1; cat gpurun_out/tc_probe.log
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
+if [[ $what == *tests* ]]; then
+  for f in post conv forward; do
+    timeout 900 python -m pytest tests/test_gpu_$f.py -q -m gpu -x --timeout 600 > gpurun_out/test_$f.log 2>&1
+    echo "test_gpu_$f exit $?"; tail -4 gpurun_out/test_$f.log
+  done
+fi
+if [[ $what == *probe* ]]; then
+  timeout 900 python tools/tc_probe.py > gpurun_out/tc_probe.log 2>&1; cat gpurun_out/tc_probe.log
+fi
+if [[ $what == *bench* ]]; then
+  timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
+  timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>> gpurun_out/bench.err; tail -1 gpurun_out/bench_ref.log
+fi
+if [[ $what == *ncu* ]]; then
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+      python tools/profile_step.py --steps 2 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"; tail -2 gpurun_out/ncu_launches.log
+fi
+if [[ $what == *full* ]]; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 182 -c 1 -f -o gpurun_out/prof_conv \
+      python tools/profile_step.py --steps 2 > gpurun_out/ncu_full_conv.log 2>&1; echo "ncu full conv exit $?"
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:mask_kernel -s 1 -c 1 -f -o gpurun_out/prof_mask \
+      python tools/profile_step.py --steps 2 > gpurun_out/ncu_full_mask.log 2>&1; echo "ncu full mask exit $?"
+fi
