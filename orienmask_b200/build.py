@@ -21,6 +21,7 @@ UNITS = [
     ('post.cu', ['-fmad=false']),
     ('conv_f32.cu', []),
     ('conv_tc.cu', []),
+    ('conv_tc2.cu', []),
 ]
 
 

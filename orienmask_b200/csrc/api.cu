@@ -1,5 +1,6 @@
 // C-ABI plumbing: error text, launch accounting, convolution plan objects.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -27,6 +28,7 @@ void count_launch(int n) { g_launches += n; }
 struct om_conv {
     om_conv_desc desc;
     void* tc_plan;
+    int tc_version;      // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (ORIENMASK_B200_CONV=v1, kept for A/B measurements)
 };
 
 extern "C" int32_t om_abi_version(void) { return 1; }
@@ -53,7 +55,9 @@ extern "C" int32_t om_conv_create(const om_conv_desc* d, om_conv** out) {
     c->desc = *d;
     c->tc_plan = nullptr;
     if (d->precision == OM_PREC_F16) {
-        int32_t rc = om::tc_plan_create(*d, &c->tc_plan);
+        const char* sel = getenv("ORIENMASK_B200_CONV");
+        c->tc_version = (sel && sel[0] == 'v' && sel[1] == '1') ? 1 : 2;
+        int32_t rc = c->tc_version == 2 ? om::tc2_plan_create(*d, &c->tc_plan) : om::tc_plan_create(*d, &c->tc_plan);
         if (rc != OM_OK) { delete c; return rc; }
     }
     *out = c;
@@ -62,12 +66,13 @@ extern "C" int32_t om_conv_create(const om_conv_desc* d, om_conv** out) {
 
 extern "C" int32_t om_conv_run(const om_conv* c, void* stream) {
     if (!c) return om::fail(OM_ERR_INVALID, "om_conv_run: null plan");
-    if (c->desc.precision == OM_PREC_F16) return om::tc_plan_run(c->tc_plan, (cudaStream_t)stream);
+    if (c->desc.precision == OM_PREC_F16)
+        return c->tc_version == 2 ? om::tc2_plan_run(c->tc_plan, (cudaStream_t)stream) : om::tc_plan_run(c->tc_plan, (cudaStream_t)stream);
     return om::f32_conv_run(c->desc, (cudaStream_t)stream);
 }
 
 extern "C" void om_conv_destroy(om_conv* c) {
     if (!c) return;
-    if (c->tc_plan) om::tc_plan_destroy(c->tc_plan);
+    if (c->tc_plan) { if (c->tc_version == 2) om::tc2_plan_destroy(c->tc_plan); else om::tc_plan_destroy(c->tc_plan); }
     delete c;
 }

@@ -12,6 +12,11 @@ int32_t tc_plan_create(const om_conv_desc& d, void** out);
 int32_t tc_plan_run(const void* plan, cudaStream_t stream);
 void tc_plan_destroy(void* plan);
 
+// fp16 tcgen05 engine on CTA pairs, cta_group::2 (conv_tc2.cu)
+int32_t tc2_plan_create(const om_conv_desc& d, void** out);
+int32_t tc2_plan_run(const void* plan, cudaStream_t stream);
+void tc2_plan_destroy(void* plan);
+
 // fp32 FFMA parity engine (conv_f32.cu)
 int32_t f32_conv_run(const om_conv_desc& d, cudaStream_t stream);
 

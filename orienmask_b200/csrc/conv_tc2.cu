@@ -1,0 +1,588 @@
+// fp16 implicit-GEMM convolution on CTA pairs: tcgen05.mma.cta_group::2 (UMMA M = 256 over two SMs),
+// TMA-fed operand ring, TMA-store epilogue.
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel + tap, cin] * W[tap, cout, cin]
+//
+// Why pairs: with one CTA per 128 x 256 tile the shared-memory fill (16 KB of activations + 32 KB of
+// weights per 512 tensor-core cycles) is what bounds the 3x3 layers, not the tensor pipe (ncu:
+// profiles/r01_conv_v1_*.txt).  A CTA pair computes two vertically adjacent pixel tiles against the
+// same weight tile; each CTA stages its own activations plus HALF of the weight rows and the
+// cta_group::2 MMA reads both halves, so the fill per tensor-core cycle drops by a third and every
+// weight byte crosses the L2->SM fabric once per 256 pixels instead of once per 128.
+//
+// Roles (7 warps / CTA): warp 0 operand producer (TMA), warp 1 TMEM allocator + MMA issuer (leader
+// CTA only issues), warp 2 residual producer (TMA), warps 3..6 epilogue.  Epilogue: TMEM -> registers
+// -> bias / up-add / LeakyReLU / residual -> 128B-swizzled staging tile -> one TMA store per 64-channel
+// chunk; padding rows of the padded-row NHWC layout are written as zeros so the layout invariant
+// (include/orienmask_b200.h) holds without masking.  Two accumulator stages in TMEM overlap the epilogue
+// of pair i with the main loop of pair i+1.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "conv_plan.h"
+
+namespace {
+
+constexpr int kThreads = 224;            // 7 warps
+constexpr int kEpiWarp0 = 3;
+constexpr int kBlockM = 128;             // pixels per CTA tile (UMMA M = 256 per pair)
+constexpr int kMaxStages = 8;
+constexpr int kStageRows = 128;          // staging tile rows
+constexpr int kStageBytes = kStageRows * 128;
+
+struct Tc2Params {
+    int tiles_x, pairs_y, tiles_n;       // pair grid; linear pair id = (py * tiles_x + tx) * tiles_n + tn
+    int tw, th;                          // pixel tile (tw * th <= 128)
+    int taps, stride;
+    int k_chunks;                        // cin / BK
+    int block_n, half_n;                 // UMMA N and the rows of it each CTA stages
+    int cout_pad;
+    int stages;
+    int tmem_cols;
+    uint32_t idesc;
+    // epilogue
+    int out_h, out_w, out_rows, total_rows;
+    int cout, leaky, out_kind, up_rows, has_res;
+    int chunk_cols;                      // accumulator columns per staged chunk (64 fp16 / 32 fp32 / 32 narrow fp16)
+    int row_bytes;                       // bytes per staged row (128 or 64)
+    int cout_stride;
+    const float* bias;
+    const float* upadd;
+    void* output;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t num_clusters_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+// Operand loads of a CTA pair: data lands in the issuing CTA, completion bytes go to the LEADER's barrier.
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// One 32-byte store per thread: a whole sector, so the L1 -> L2 write traffic is not inflated by partial sectors.
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    const uint32_t z = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z) : "memory");
+}
+// Arrives (once the MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address and byte
+// offsets in 16-byte units, version 1 (Blackwell), layout 2 = SWIZZLE_128B / 4 = SWIZZLE_64B.
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
+    constexpr uint64_t sbo = (8 * BK * 2) >> 4;
+    constexpr uint64_t layout = (BK == 64) ? 2 : 4;
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Byte offset of 16-byte chunk `c` of row `r` in a TMA-swizzled staging tile (128B or 64B rows).
+__device__ __forceinline__ uint32_t swz(int r, int c, int row_bytes) {
+    return row_bytes == 128 ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)) : (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+}
+
+struct PairCoord { int tx, py, tn; };
+__device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
+    PairCoord t;
+    t.tn = pair % p.tiles_n;
+    const int r = pair / p.tiles_n;
+    t.tx = r % p.tiles_x;
+    t.py = r / p.tiles_x;
+    return t;
+}
+
+template <int BK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
+                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_res, const Tc2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int a_bytes = kBlockM * BK * 2;
+    const int b_bytes = p.half_n * BK * 2;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint8_t* res_buf = smem + (size_t)p.stages * stage_bytes;          // [2][kStageBytes] (has_res only)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(res_buf + (p.has_res ? 2 * kStageBytes : 0));
+    uint64_t* full_bar = bars;                         // [stages]   (the leader's copy is the live one)
+    uint64_t* empty_bar = bars + kMaxStages;           // [stages]
+    uint64_t* tmem_full = bars + 2 * kMaxStages;       // [2]
+    uint64_t* tmem_empty = tmem_full + 2;              // [2]        (leader's copy: 8 warp arrivals from both CTAs)
+    uint64_t* res_full = tmem_empty + 2;               // [2]
+    uint64_t* res_empty = res_full + 2;                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);            // [cout_pad]; L1 is carved down to nothing here, so
+                                                                        // per-use global bias loads would each pay an L2 round trip
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int num_pairs = p.tiles_x * p.pairs_y * p.tiles_n;
+    const int k_iters = p.taps * p.k_chunks;
+    const int first_pair = (int)cluster_id_x(), pair_step = (int)num_clusters_x();
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0));
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8);
+            mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < p.cout_pad; i += kThreads)
+        s_bias[i] = (p.bias != nullptr && p.out_kind != OM_OUT_PARTIAL && i < p.cout) ? p.bias[i] : 0.0f;
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();                                    // peer barriers are initialised before any remote signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== operand producer (both CTAs) =====
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t pair_tx_bytes = 2u * (uint32_t)(p.tw * p.th * BK * 2 + b_bytes);
+            for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
+                const PairCoord t = decode_pair(p, pair);
+                const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
+                const int n0 = t.tn * p.block_n + (int)rank * p.half_n;
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    int dx = 0, dy = 0;
+                    const CUtensorMap* ma = &map_a0;
+                    if (p.taps == 9) {
+                        const int r = tap / 3, s = tap - r * 3;
+                        if (p.stride == 1) { dx = s - 1; dy = r - 1; }
+                        else {
+                            dx = (s == 0) ? -1 : 0; dy = (r == 0) ? -1 : 0;
+                            const int sel = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);   // odd row / odd column views
+                            ma = sel == 0 ? &map_a0 : sel == 1 ? &map_a1 : sel == 2 ? &map_a2 : &map_a3;
+                        }
+                    }
+                    for (int kc = 0; kc < p.k_chunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                        if (rank == 0) mbar_expect_tx(&full_bar[stage], pair_tx_bytes);
+                        const uint32_t leader_bar = mapa(smem_u32(&full_bar[stage]), 0);
+                        tma_load_3d_pair(sa, ma, leader_bar, kc * BK, x0 + dx, y0 + dy);
+                        tma_load_2d_pair(sa + a_bytes, &map_b, leader_bar, kc * BK, tap * p.cout_pad + n0);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer (leader CTA) =====
+            int stage = 0; uint32_t phase = 0;
+            int as = 0; uint32_t aphase = 0;
+            for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
+                mbar_wait(&tmem_empty[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
+                for (int kit = 0; kit < k_iters; ++kit) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t adesc = make_kmajor_desc<BK>(sa);
+                    const uint64_t bdesc = make_kmajor_desc<BK>(sa + a_bytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kit | k) != 0);
+                    umma_commit_pair(&empty_bar[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(&tmem_full[as]);
+                as ^= 1; if (as == 0) aphase ^= 1;
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0 && p.has_res) {
+            // ===== residual producer: the 64-channel chunks of this CTA's output tile, in epilogue order =====
+            int rb = 0; uint32_t rphase = 0;
+            const int n_chunks = p.block_n / p.chunk_cols;
+            const uint32_t bytes = (uint32_t)(p.tw * p.th * p.row_bytes);
+            for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
+                const PairCoord t = decode_pair(p, pair);
+                const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
+                for (int j = 0; j < n_chunks; ++j) {
+                    mbar_wait(&res_empty[rb], rphase ^ 1);
+                    mbar_expect_tx(&res_full[rb], bytes);
+                    tma_load_3d(res_buf + rb * kStageBytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0);
+                    rb ^= 1; if (rb == 0) rphase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===== epilogue: 4 warps, TMEM lane quadrant = warp % 4 =====
+        const int quad = warp & 3;
+        const int m = quad * 32 + lane;                     // accumulator row = pixel inside the tile
+        const uint32_t leader_tmem_empty0 = mapa(smem_u32(&tmem_empty[0]), 0);
+        const int n_chunks = p.block_n / p.chunk_cols;
+        const int my = m / p.tw, mx = m - my * p.tw;
+        int as = 0; uint32_t aphase = 0;
+        int rb = 0; uint32_t rphase = 0;
+        for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
+            const PairCoord t = decode_pair(p, pair);
+            const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
+            const int Y = y0 + my, x = x0 + mx;
+            const int img = Y / p.out_rows, y = Y - img * p.out_rows;
+            const bool valid = (m < p.tw * p.th) && (Y < p.total_rows) && (y < p.out_h);
+            const int n0 = t.tn * p.block_n;
+            mbar_wait(&tmem_full[as], aphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
+            const size_t pix = (size_t)Y * p.out_w + x;
+            const float* up = nullptr;
+            if (p.upadd != nullptr && valid)
+                up = p.upadd + ((size_t)(img * p.up_rows + (y >> 1)) * (p.out_w >> 1) + (x >> 1)) * p.cout;
+            for (int j = 0; j < n_chunks; ++j) {
+                if (p.has_res) mbar_wait(&res_full[rb], rphase);
+                for (int c0 = 0; c0 < p.chunk_cols; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + (uint32_t)(j * p.chunk_cols + c0), v);
+                    if (j == n_chunks - 1 && c0 + 32 >= p.chunk_cols) {     // accumulator fully drained -> release it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t)(as * 8));
+                    }
+                    const int cg = n0 + j * p.chunk_cols + c0;       // first global channel of this 32-column group
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                    if (up != nullptr) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 u = __ldg(reinterpret_cast<const float4*>(up + cg + i));
+                            f[i] += u.x; f[i + 1] += u.y; f[i + 2] += u.z; f[i + 3] += u.w;
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 bv = *reinterpret_cast<const float4*>(s_bias + cg + i);     // warp-uniform: smem broadcast
+                        f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+                    }
+                    if (p.leaky) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.0f ? f[i] : 0.1f * f[i];
+                    }
+                    if (p.out_kind == OM_OUT_ACT) {
+                        if (p.has_res) {
+                            const uint8_t* rbuf = res_buf + rb * kStageBytes;
+                            const int cbase = c0 >> 3;               // first 16-byte chunk of this group inside the staged row
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                const uint4 rv = *reinterpret_cast<const uint4*>(rbuf + swz(m, cbase + (i >> 3), p.row_bytes));
+                                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 rf = __half22float2(rh[q]);
+                                    f[i + 2 * q] += rf.x; f[i + 2 * q + 1] += rf.y;
+                                }
+                            }
+                        }
+                        if (valid) {
+                            __half* o = reinterpret_cast<__half*>(p.output) + pix * p.cout_stride + cg;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 16) {       // 2 x 32-byte stores: every store fills whole sectors
+                                uint32_t w[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const __half2 h = __floats2half2_rn(f[i + 2 * q], f[i + 2 * q + 1]);
+                                    w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                                }
+                                st_global_256(o + i, w);
+                            }
+                        }
+                    } else if (p.out_kind == OM_OUT_PARTIAL) {
+                        if (valid) {
+                            float* o = reinterpret_cast<float*>(p.output) + pix * p.cout_stride + cg;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                uint32_t w[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) w[q] = __float_as_uint(f[i + q]);
+                                st_global_256(o + i, w);
+                            }
+                        }
+                    } else if (valid) {   // OM_OUT_NCHW: dense fp32 [B, cout, H, W]; lanes hold consecutive pixels of a row
+                        float* o = reinterpret_cast<float*>(p.output) + ((size_t)img * p.cout * p.out_h + y) * p.out_w + x;
+                        const size_t plane = (size_t)p.out_h * p.out_w;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (cg + i < p.cout) o[(size_t)(cg + i) * plane] = f[i];
+                    }
+                }
+                if (p.has_res) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&res_empty[rb]);
+                    rb ^= 1; if (rb == 0) rphase ^= 1;
+                }
+            }
+            as ^= 1; if (as == 0) aphase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();                                    // nobody leaves while the peer may still touch its smem / TMEM
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int32_t encode(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
+               const cuuint64_t* strides_bytes, const cuuint32_t* box, int inner_bytes) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) return om::fail(OM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return om::fail(OM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return OM_OK;
+}
+
+struct Tc2Plan {
+    CUtensorMap map_a[4];
+    CUtensorMap map_b, map_res;
+    Tc2Params p;
+    int bk;
+    int grid;
+    size_t smem;
+};
+
+// Pixel tile of <= 128 = tw x th with tw | width.  NHWC outputs: the fullest tile, discounting tiles narrower
+// than 8 pixels (their TMA boxes degenerate into many 128..512-byte rows and they share little halo in L2).
+// NCHW heads: the widest row segment among tiles that are at least 90 % full, so that the per-channel fp32
+// stores of a warp form few long runs without idling a large part of the epilogue lanes.
+int pick_tile_w(int w, bool widest) {
+    int best = 1, best_score = -1;
+    for (int tw = 1; tw <= w && tw <= kBlockM; ++tw) {
+        if (w % tw) continue;
+        const int fill = tw * (kBlockM / tw);
+        int score;
+        if (widest) score = (fill * 10 >= kBlockM * 9) ? 1000 + tw : fill;
+        else score = fill * (tw < 8 ? tw : 8);
+        if (score >= best_score) { best_score = score; best = tw; }
+    }
+    return best;
+}
+
+}  // namespace
+
+namespace om {
+
+int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
+    if (d.cin % 32) return fail(OM_ERR_INVALID, "fp16 engine needs cin %% 32 == 0 (got %d)", d.cin);
+    if (d.out_kind != OM_OUT_NCHW && (d.cout % 32 || d.cout_stride % 16 || d.cout_stride < d.cout))
+        return fail(OM_ERR_INVALID, "fp16 engine needs cout %% 32 == 0 and an aligned channel pitch for NHWC outputs");
+    if (d.upadd && (d.out_w % 2 || d.out_kind == OM_OUT_NCHW)) return fail(OM_ERR_INVALID, "upadd needs an even width and an NHWC output");
+    if (d.stride == 2 && (d.in_rows != 2 * d.out_rows || d.in_w != 2 * d.out_w || d.ksize != 3))
+        return fail(OM_ERR_INVALID, "stride-2 layers must be 3x3 with in_rows == 2*out_rows and in_w == 2*out_w");
+    if (d.stride == 1 && (d.in_rows != d.out_rows || d.in_w != d.out_w))
+        return fail(OM_ERR_INVALID, "stride-1 layers need identical input/output geometry");
+    Tc2Plan* plan = new Tc2Plan();
+    memset(plan, 0, sizeof(Tc2Plan));
+    Tc2Params& p = plan->p;
+    const int bk = (d.cin % 64 == 0) ? 64 : 32;
+    plan->bk = bk;
+    int cout_pad = (d.cout + 15) / 16 * 16;
+    if (cout_pad < 32) cout_pad = 32;
+    int bn = cout_pad;
+    if (bn > 256) {
+        bn = 256;
+        while (cout_pad % bn) bn -= 32;
+    }
+    if (bn % 32) { delete plan; return fail(OM_ERR_INVALID, "padded cout %d cannot be split over a CTA pair", cout_pad); }
+    p.block_n = bn; p.half_n = bn / 2; p.cout_pad = cout_pad; p.tiles_n = cout_pad / bn;
+    p.tw = pick_tile_w(d.out_w, d.out_kind == OM_OUT_NCHW); p.th = kBlockM / p.tw;
+    p.tiles_x = d.out_w / p.tw;
+    p.total_rows = d.batch * d.out_rows;
+    const int tiles_y = (p.total_rows + p.th - 1) / p.th;
+    p.pairs_y = (tiles_y + 1) / 2;
+    p.taps = d.ksize * d.ksize; p.stride = d.stride; p.k_chunks = d.cin / bk;
+    p.has_res = d.residual != nullptr;
+    if (d.out_kind == OM_OUT_ACT) { p.chunk_cols = bn >= 64 ? 64 : 32; p.row_bytes = p.chunk_cols * 2; }
+    else { p.chunk_cols = 32; p.row_bytes = 128; }
+    if (bn % p.chunk_cols) { delete plan; return fail(OM_ERR_INVALID, "tile width %d is not a multiple of the staged chunk", bn); }
+    const int stage_bytes = (kBlockM + p.half_n) * bk * 2;
+    const int epi_bytes = p.has_res ? 2 * kStageBytes : 0;
+    constexpr int kMaxSmem = 227 * 1024;
+    const int fixed = 1024 + epi_bytes + (2 * kMaxStages + 8) * 8 + 16 + cout_pad * 4;
+    int stages = (kMaxSmem - fixed) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
+    p.stages = stages;
+    int cols = 32;
+    while (cols < 2 * bn) cols <<= 1;
+    p.tmem_cols = cols;
+    // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b F16, K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 per pair)
+    p.idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((2 * kBlockM) >> 4) << 24);
+    p.out_h = d.out_h; p.out_w = d.out_w; p.out_rows = d.out_rows;
+    p.cout = d.cout; p.leaky = d.leaky; p.out_kind = d.out_kind;
+    p.up_rows = d.up_rows; p.bias = d.bias; p.upadd = d.upadd;
+    p.cout_stride = d.cout_stride; p.output = d.output;
+
+    const size_t esz = 2;
+    int32_t rc = OM_OK;
+    const CUtensorMapDataType f16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    if (d.stride == 1) {
+        cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.batch * d.in_rows};
+        cuuint64_t str[2] = {(cuuint64_t)d.cin * esz, (cuuint64_t)d.in_w * d.cin * esz};
+        cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.tw, (cuuint32_t)p.th};
+        rc = encode(&plan->map_a[0], f16, d.input, 3, dims, str, box, bk * 2);
+        for (int i = 1; i < 4 && rc == OM_OK; ++i) plan->map_a[i] = plan->map_a[0];
+    } else {
+        for (int sel = 0; sel < 4 && rc == OM_OK; ++sel) {          // sel = 2*odd_row + odd_col
+            const int py = sel >> 1, px = sel & 1;
+            cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w / 2, (cuuint64_t)d.batch * d.in_rows / 2};
+            cuuint64_t str[2] = {(cuuint64_t)2 * d.cin * esz, (cuuint64_t)2 * d.in_w * d.cin * esz};
+            cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.tw, (cuuint32_t)p.th};
+            const char* base = reinterpret_cast<const char*>(d.input) + ((size_t)py * d.in_w + px) * d.cin * esz;
+            rc = encode(&plan->map_a[sel], f16, base, 3, dims, str, box, bk * 2);
+        }
+    }
+    if (rc == OM_OK) {
+        cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)p.taps * cout_pad};
+        cuuint64_t str[1] = {(cuuint64_t)d.cin * esz};
+        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.half_n};
+        rc = encode(&plan->map_b, f16, d.weights, 2, dims, str, box, bk * 2);
+    }
+    if (rc == OM_OK && p.has_res) {
+        cuuint64_t dims[3] = {(cuuint64_t)d.cout, (cuuint64_t)d.out_w, (cuuint64_t)d.batch * d.out_rows};
+        cuuint64_t str[2] = {(cuuint64_t)d.cout_stride * esz, (cuuint64_t)d.out_w * d.cout_stride * esz};
+        cuuint32_t box[3] = {(cuuint32_t)p.chunk_cols, (cuuint32_t)p.tw, (cuuint32_t)p.th};
+        rc = encode(&plan->map_res, f16, d.residual, 3, dims, str, box, p.row_bytes);
+    }
+    if (rc == OM_OK && !p.has_res) plan->map_res = plan->map_a[0];
+    if (rc != OM_OK) { delete plan; return rc; }
+
+    plan->smem = (size_t)fixed + (size_t)stages * stage_bytes;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int pairs = p.tiles_x * p.pairs_y * p.tiles_n;
+    const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+    plan->grid = 2 * clusters;
+    cudaError_t e = bk == 64
+        ? cudaFuncSetAttribute(conv_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
+        : cudaFuncSetAttribute(conv_tc2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) { delete plan; return fail(OM_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); }
+    *out = plan;
+    return OM_OK;
+}
+
+int32_t tc2_plan_run(const void* vp, cudaStream_t stream) {
+    const Tc2Plan* plan = reinterpret_cast<const Tc2Plan*>(vp);
+    if (plan->bk == 64)
+        conv_tc2_kernel<64><<<plan->grid, kThreads, plan->smem, stream>>>(plan->map_a[0], plan->map_a[1], plan->map_a[2], plan->map_a[3],
+                                                                          plan->map_b, plan->map_res, plan->p);
+    else
+        conv_tc2_kernel<32><<<plan->grid, kThreads, plan->smem, stream>>>(plan->map_a[0], plan->map_a[1], plan->map_a[2], plan->map_a[3],
+                                                                          plan->map_b, plan->map_res, plan->p);
+    return check_launch("conv_tc2_kernel");
+}
+
+void tc2_plan_destroy(void* vp) { delete reinterpret_cast<Tc2Plan*>(vp); }
+
+}  // namespace om

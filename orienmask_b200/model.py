@@ -119,6 +119,7 @@ class _Engine:
         self.keep = []            # owns every device tensor the plans point to
         self.plans = []           # ('stem', args) | ('conv', handle)
         self.flops = 0
+        self.layers = []          # one entry per launch, in launch order (tools/layer_report.py)
         with torch.cuda.device(device):
             self._build()
         self.sd = None
@@ -158,7 +159,7 @@ class _Engine:
         return p
 
     # ---- op emission -----------------------------------------------------------------------------
-    def conv(self, src, w, bias, dst, k, stride=1, leaky=True, kind=_lib.OUT_ACT, residual=None, upadd=None, nchw=None):
+    def conv(self, src, w, bias, dst, k, stride=1, leaky=True, kind=_lib.OUT_ACT, residual=None, upadd=None, nchw=None, name=None):
         d = _lib.ConvDesc()
         d.precision, d.batch = self.prec, self.B
         si = src['stride']
@@ -189,11 +190,22 @@ class _Engine:
         handle = _lib.c_vp()
         _lib.check(self.lib.om_conv_create(d, handle), 'om_conv_create')
         self.plans.append(('conv', handle))
-        self.flops += 2 * d.batch * d.out_h * d.out_w * d.cout * d.cin * k * k
+        flops = 2 * d.batch * d.out_h * d.out_w * d.cout * d.cin * k * k
+        self.flops += flops
+        esz = 2 if self.prec == _lib.PREC_F16 else 4
+        nbytes = d.batch * d.in_h * d.in_w * d.cin * esz + w.numel() * esz
+        nbytes += d.batch * d.out_h * d.out_w * d.cout * (esz if kind == _lib.OUT_ACT else 4)
+        if residual is not None:
+            nbytes += d.batch * d.out_h * d.out_w * d.cout * esz
+        if upadd is not None:
+            nbytes += d.batch * d.out_h * d.out_w * d.cout        # fp32 quarter-resolution partial
+        self.layers.append(dict(name=name or '?', shape='%dx%d s%d %d->%d @%dx%d%s%s%s' % (
+            k, k, stride, d.cin, d.cout, d.out_h, d.out_w, ' +res' if residual is not None else '',
+            ' +up' if upadd is not None else '', ('', ' partial', ' nchw')[kind]), flops=flops, bytes=nbytes))
 
     def cbl(self, prefix, src, dst, k, stride=1, residual=None):
         w, b = self.folded(prefix, 'cbl')
-        self.conv(src, w, b, dst, k, stride, True, residual=residual)
+        self.conv(src, w, b, dst, k, stride, True, residual=residual, name=prefix)
 
     def chain(self, prefix, src, bufs, ks, first_upadd=None, first_cols=None):
         """conv_bn_leaky sequence <prefix>.0.. ; bufs alternate; optional concat-split on the first conv."""
@@ -203,7 +215,7 @@ class _Engine:
             dst = bufs[i % 2]
             if i == 0 and first_cols is not None:
                 w = w[:, first_cols[0]:first_cols[1]].contiguous()
-            self.conv(cur, w, b, dst, k, upadd=first_upadd if i == 0 else None)
+            self.conv(cur, w, b, dst, k, upadd=first_upadd if i == 0 else None, name='%s.%d' % (prefix, i))
             cur = dst
         return cur
 
@@ -212,12 +224,12 @@ class _Engine:
         w, _ = self.folded(prefix, 'cbl')
         w = w[:, cols[0]:cols[1]].contiguous()
         dst = self.act(src['stride'], w.shape[0], torch.float32)
-        self.conv(src, w, None, dst, 1, leaky=False, kind=_lib.OUT_PARTIAL, upadd=upadd)
+        self.conv(src, w, None, dst, 1, leaky=False, kind=_lib.OUT_PARTIAL, upadd=upadd, name='%s[%d:%d]' % (prefix, cols[0], cols[1]))
         return dst
 
     def head(self, prefix, src, out):
         w, b = self.folded(prefix, 'conv')
-        self.conv(src, w, b, None, 1, leaky=False, kind=_lib.OUT_NCHW, nchw=out)
+        self.conv(src, w, b, None, 1, leaky=False, kind=_lib.OUT_NCHW, nchw=out, name=prefix)
 
     # ---- the schedule (model/orienmask_yolo_fpnplus.py:74-90, model/backbone/darknet.py:47-54) ----
     def _build(self):
@@ -229,6 +241,8 @@ class _Engine:
         c1 = self.act(1, 32)
         self.plans.append(('stem', c1))
         self.flops += 2 * B * H * W * 32 * 27
+        self.layers.append(dict(name='backbone.conv1', shape='3x3 s1 3->32 @%dx%d stem' % (H, W), flops=2 * B * H * W * 32 * 27,
+                                bytes=B * H * W * (3 * 4 + 32 * (2 if self.prec == _lib.PREC_F16 else 4))))
 
         trunk = c1
         feats = {}
@@ -294,6 +308,26 @@ class _Engine:
         n2 = self.nA * 2
         o = self.out_orien
         return ((self.out_bbox[0], o[:, 0:n2]), (self.out_bbox[1], o[:, n2:2 * n2]), (self.out_bbox[2], o[:, 2 * n2:3 * n2]))
+
+    def time_layers(self, x, iters=5):
+        """Per-launch device times (us, mean over `iters` passes) from CUDA events between the launches."""
+        n = len(self.plans)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n + 1)] for _ in range(iters)]
+        x = x.contiguous().float()
+        with torch.cuda.device(self.device):
+            stream = _lib.stream_ptr()
+            for it in range(iters):
+                ev[it][0].record()
+                for i, (kind, arg) in enumerate(self.plans):
+                    if kind == 'conv':
+                        _lib.check(self.lib.om_conv_run(arg, stream), 'om_conv_run')
+                    else:
+                        _lib.check(self.lib.om_stem_conv(self.prec, _lib.ptr(x), _lib.ptr(self.stem_w), _lib.ptr(self.stem_b),
+                                                         _lib.ptr(arg['t']), self.B, self.H, self.W, self.rows(1), 32, stream),
+                                   'om_stem_conv')
+                    ev[it][i + 1].record()
+            torch.cuda.synchronize()
+        return [1e3 * sum(ev[it][i].elapsed_time(ev[it][i + 1]) for it in range(iters)) / iters for i in range(n)]
 
     def __del__(self):
         try:

@@ -17,13 +17,16 @@ if [[ $what == *bench* ]]; then
   timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>> gpurun_out/bench.err; tail -1 gpurun_out/bench_ref.log
 fi
+if [[ $what == *events* ]]; then
+  timeout 600 python tools/profile_step.py --steps 1 --events 10 > gpurun_out/events.log 2>&1; echo "events exit $?"; tail -2 gpurun_out/events.log
+fi
 if [[ $what == *ncu* ]]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-      python tools/profile_step.py --steps 2 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"; tail -2 gpurun_out/ncu_launches.log
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 600 --csv --log-file gpurun_out/launches.csv \
+      python tools/profile_step.py --steps 1 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"; tail -2 gpurun_out/ncu_launches.log
 fi
 if [[ $what == *full* ]]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 182 -c 1 -f -o gpurun_out/prof_conv \
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${CONV_KERNEL:-conv_tc2_kernel} -s ${CONV_SKIP:-84} -c ${CONV_COUNT:-1} -f -o gpurun_out/prof_conv \
       python tools/profile_step.py --steps 2 > gpurun_out/ncu_full_conv.log 2>&1; echo "ncu full conv exit $?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:mask_kernel -s 1 -c 1 -f -o gpurun_out/prof_mask \
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:mask_kernel -c 1 -f -o gpurun_out/prof_mask \
       python tools/profile_step.py --steps 2 > gpurun_out/ncu_full_mask.log 2>&1; echo "ncu full mask exit $?"
 fi

@@ -1,6 +1,7 @@
 """Minimal driver for ncu: `--steps` steps of the bs-32 544x544 hot path (no timing, no CPU baseline)."""
 import argparse
 import functools
+import json
 import os
 import sys
 
@@ -16,15 +17,30 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=2)
 ap.add_argument('--batch', type=int, default=32)
 ap.add_argument('--precision', default='fp16')
+ap.add_argument('--size', type=int, default=544)
+ap.add_argument('--events', type=int, default=0, help='also time every layer with CUDA events over this many passes')
 a = ap.parse_args()
 dev = torch.device('cuda:0')
 model = ob.OrienMaskYOLOFPNPlus(3, 80)
 model.load_state_dict(synthetic_state_dict(0), strict=True)
 model.precision = a.precision
 model = model.to(dev).eval()
-post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5), device=dev, **post_kwargs())
-x = synthetic_images(a.batch, H, W, seed=1).to(dev)
+kw = post_kwargs()
+kw['grid_size'] = [[a.size // s, a.size // s] for s in (32, 16, 8)]
+kw['image_size'] = [a.size, a.size]
+post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5), device=dev, **kw)
+x = synthetic_images(a.batch, a.size, a.size, seed=1).to(dev)
+out = post.apply_padded(model(x))            # un-profiled warm-up: builds the engine (BN folding etc. are torch ops)
+torch.cuda.synchronize()
+eng = next(iter(model._engines.values()))
+os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+json.dump(eng.layers, open(os.path.join(ROOT, 'gpurun_out', 'layers.json'), 'w'))
+if a.events:
+    eng.time_layers(x, 2)
+    json.dump(eng.time_layers(x, a.events), open(os.path.join(ROOT, 'gpurun_out', 'layer_events.json'), 'w'))
+torch.cuda.cudart().cudaProfilerStart()      # ncu --profile-from-start off
 for _ in range(a.steps):
     out = post.apply_padded(model(x))
 torch.cuda.synchronize()
+torch.cuda.cudart().cudaProfilerStop()
 print('instances per image:', out.count.tolist()[:8])
