@@ -22,6 +22,7 @@ UNITS = [
     ('conv_f32.cu', []),
     ('conv_tc.cu', []),
     ('conv_tc2.cu', []),
+    ('conv_stem_tc.cu', []),
 ]
 
 

@@ -8,6 +8,8 @@
 // y = leaky(conv(x, W') + b' [+ upsampled partial]) [+ residual].
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_plan.h"
 
@@ -182,9 +184,12 @@ extern "C" int32_t om_stem_conv(int32_t precision, const float* image, const flo
     const long long total = (long long)batch * h * w;
     const int blocks = (int)((total + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision == OM_PREC_F16)
+    if (precision == OM_PREC_F16) {
+        const char* sel = getenv("ORIENMASK_B200_STEM");
+        if (!(sel && sel[0] == 'f') && h % 4 == 0 && w % 32 == 0)          // default: tensor-core stem (conv_stem_tc.cu)
+            return om::stem_tc_run(image, weights, bias, output, batch, h, w, rows, st);
         stem_kernel<__half, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows);
-    else if (precision == OM_PREC_F32)
+    } else if (precision == OM_PREC_F32)
         stem_kernel<float, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<float*>(output), batch, h, w, rows);
     else
         return om::fail(OM_ERR_INVALID, "om_stem_conv: unknown precision %d", precision);

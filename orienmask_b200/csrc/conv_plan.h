@@ -17,6 +17,10 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out);
 int32_t tc2_plan_run(const void* plan, cudaStream_t stream);
 void tc2_plan_destroy(void* plan);
 
+// tensor-core first layer (conv_stem_tc.cu)
+int32_t stem_tc_run(const float* image, const float* weights, const float* bias, void* output, int batch, int h, int w, int rows,
+                    cudaStream_t stream);
+
 // fp32 FFMA parity engine (conv_f32.cu)
 int32_t f32_conv_run(const om_conv_desc& d, cudaStream_t stream);
 

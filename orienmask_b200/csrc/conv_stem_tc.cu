@@ -1,0 +1,206 @@
+// First layer (3 -> 32, 3x3, stride 1, BN folded, LeakyReLU) on the sm_100a tensor cores, straight from the
+// caller's fp32 NCHW image to the fp16 padded-row NHWC activation the rest of the engine consumes.
+//
+// GEMM view: M = pixels, K = 27 taps*channels (zero-padded to 32), N = 32.  The tensor work is trivial (two
+// K=16 tcgen05 MMAs per 128 pixels); what matters is that the layer moves 12 B in + 64 B out per pixel and
+// nothing else, so the CUDA cores only build the im2col rows: a CTA stages a 3 x 6 x 34 fp32 patch in shared
+// memory (coalesced), each of its 128 threads gathers the 27 taps of one pixel into a 64-byte SWIZZLE_64B
+// K-major row, one elected lane issues the MMAs, and every thread drains its accumulator row from TMEM
+// (bias + LeakyReLU, fp16) with two 32-byte stores.  Several CTAs per SM overlap gather, MMA and stores.
+// The FFMA version of this layer (conv_f32.cu, kept for the fp32 parity engine) needs 864 FMAs per pixel and
+// was the single slowest launch of the forward pass (profiles/r01_layers_events_v2d.md).
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kTileW = 32, kTileH = 4;       // 128 pixels: warp = tile row, lane = column
+constexpr int kPatchW = 36;                  // 34 used columns, padded
+constexpr int kCout = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+// 16-byte chunk c (0..3) of 64-byte row r in a SWIZZLE_64B K-major tile (8-row atoms of 512 B).
+__device__ __forceinline__ uint32_t swz64(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ uint64_t kmajor_desc_64b(uint32_t addr) {
+    return (uint64_t)((addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+
+__global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ img, const float* __restrict__ w27,
+                                                      const float* __restrict__ bias, __half* __restrict__ out,
+                                                      int batch, int h, int wd, int rows) {
+    __shared__ __align__(1024) uint8_t s_a[128 * 64];        // im2col rows, K-major SWIZZLE_64B
+    __shared__ __align__(1024) uint8_t s_b[kCout * 64];      // weights [cout][k], same layout
+    __shared__ float s_patch[3][kTileH + 2][kPatchW];
+    __shared__ float s_bias[kCout];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // weights: w27 is [27][32] (tap-major: (ky*3+kx)*3+ci, then cout); B[n][k] = w27[k][n], k >= 27 -> 0
+    for (int i = tid; i < kCout * 4; i += 128) {
+        const int n = i >> 2, c = i & 3;
+        __half v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = c * 8 + e;
+            v[e] = __float2half(k < 27 ? w27[k * kCout + n] : 0.0f);
+        }
+        *reinterpret_cast<uint4*>(s_b + swz64(n, c)) = *reinterpret_cast<const uint4*>(v);
+    }
+    if (tid < kCout) s_bias[tid] = bias[tid];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&s_tmem)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(kCout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t adesc = kmajor_desc_64b(smem_u32(s_a)), bdesc = kmajor_desc_64b(smem_u32(s_b));
+
+    const int tiles_x = wd / kTileW, tiles_y = h / kTileH;
+    const int tiles_per_image = tiles_x * tiles_y;
+    const long long total = (long long)batch * tiles_per_image;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int n = (int)(tile / tiles_per_image);
+        const int r = (int)(tile - (long long)n * tiles_per_image);
+        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        const int x0 = tx * kTileW, y0 = ty * kTileH;
+        // 1. patch: rows y0-1 .. y0+4, columns x0-1 .. x0+32 of the three planes (zero outside the image)
+        for (int i = tid; i < 3 * (kTileH + 2) * 34; i += 128) {
+            const int ci = i / ((kTileH + 2) * 34);
+            const int rem = i - ci * (kTileH + 2) * 34;
+            const int py = rem / 34, px = rem - py * 34;
+            const int iy = y0 - 1 + py, ix = x0 - 1 + px;
+            float v = 0.0f;
+            if (iy >= 0 && iy < h && ix >= 0 && ix < wd) v = __ldg(img + ((size_t)(n * 3 + ci) * h + iy) * wd + ix);
+            s_patch[ci][py][px] = v;
+        }
+        __syncthreads();
+        // 2. im2col row of pixel (y0 + warp, x0 + lane): k = (ky*3 + kx)*3 + ci
+        {
+            float v[32];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) v[(ky * 3 + kx) * 3 + ci] = s_patch[ci][warp + ky][lane + kx];
+#pragma unroll
+            for (int k = 27; k < 32; ++k) v[k] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 q;
+                __half2* hq = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) hq[e] = __floats2half2_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
+                *reinterpret_cast<uint4*>(s_a + swz64(tid, c)) = q;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        // 3. D[128 x 32] = A[128 x 32] * B^T
+        if (warp == 0) {
+            if (elect_one()) {
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint32_t acc = k;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem), "l"(adesc + (uint64_t)(2 * k)), "l"(bdesc + (uint64_t)(2 * k)), "r"(idesc), "r"(acc) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar)) : "memory");
+            }
+            __syncwarp();
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // 4. epilogue: this thread's pixel, 32 channels
+        uint32_t acc[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
+              "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]), "=r"(acc[15]),
+              "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]), "=r"(acc[20]), "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]),
+              "=r"(acc[24]), "=r"(acc[25]), "=r"(acc[26]), "=r"(acc[27]), "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
+            : "r"(tmem + ((uint32_t)(warp * 32) << 16)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        __half* o = out + ((size_t)(n * rows + y0 + warp) * wd + x0 + lane) * kCout;
+#pragma unroll
+        for (int i = 0; i < 32; i += 16) {
+            uint32_t wv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float a = __uint_as_float(acc[i + 2 * q]) + s_bias[i + 2 * q];
+                float b = __uint_as_float(acc[i + 2 * q + 1]) + s_bias[i + 2 * q + 1];
+                a = a > 0.0f ? a : 0.1f * a;
+                b = b > 0.0f ? b : 0.1f * b;
+                const __half2 hv = __floats2half2_rn(a, b);
+                wv[q] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            st_global_256(o + i, wv);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                   // TMEM rows drained and s_a / s_patch free for the next tile
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+}
+
+}  // namespace
+
+namespace om {
+
+int32_t stem_tc_run(const float* image, const float* weights, const float* bias, void* output, int batch, int h, int w, int rows,
+                    cudaStream_t stream) {
+    if (h % kTileH || w % kTileW) return fail(OM_ERR_INVALID, "tensor-core stem needs h %% 4 == 0 and w %% 32 == 0 (got %dx%d)", h, w);
+    const long long tiles = (long long)batch * (h / kTileH) * (w / kTileW);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (long long)sms * 8;
+    if (grid > tiles) grid = tiles;
+    stem_tc_kernel<<<(int)grid, 128, 0, stream>>>(image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows);
+    return check_launch("stem_tc_kernel");
+}
+
+}  // namespace om

@@ -19,6 +19,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_plan.h"
 
@@ -38,7 +40,11 @@ struct Tc2Params {
     int k_chunks;                        // cin / BK
     int block_n, half_n;                 // UMMA N and the rows of it each CTA stages
     int cout_pad;
-    int stages;
+    int halo;                            // 3x3 stride 1 with tw == 8: one halo box per chunk feeds all nine taps
+    int n_sub;                           // (tap, chunk) blocks per pipeline stage
+    int stages;                          // depth of the block ring
+    int h_stages, h_stage_bytes, h_chunk_bytes;   // halo ring (halo mode): one stage = the halos of all chunks of a tile
+    int a_box_pixels;                    // pixels per activation TMA box
     int tmem_cols;
     uint32_t idesc;
     // epilogue
@@ -61,6 +67,16 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// One lane of a converged warp (always the same one).  The single-thread instructions (TMA, tcgen05.mma/commit,
+// expect_tx) are issued under this predicate while the surrounding loops stay warp-uniform: inside a
+// `lane == 0` branch ptxas cannot keep descriptors/addresses in uniform registers and wraps every
+// UTCHMMA/UTMALDG in an ELECT/R2UR waterfall loop (~20 instructions per MMA), which made the issuing thread --
+// not the tensor pipe -- the bottleneck.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -76,11 +92,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default (.release.cta) semantics: a cluster-scope release would drain every global store in flight first
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+    {
+        uint32_t ok;                                   // fast path: no clock reads when the phase has already completed
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
     const long long t0 = clock64();
     while (true) {
         uint32_t ok;
@@ -136,11 +162,12 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address and byte
 // offsets in 16-byte units, version 1 (Blackwell), layout 2 = SWIZZLE_128B / 4 = SWIZZLE_64B.
+// `sbo_bytes` is the distance between consecutive 8-row groups: 8 rows for a dense tile, one halo row
+// (tw + 2 pixels) when the eight rows of a group are the eight pixels of one tile row inside a halo.
 template <int BK>
-__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
-    constexpr uint64_t sbo = (8 * BK * 2) >> 4;
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
     constexpr uint64_t layout = (BK == 64) ? 2 : 4;
-    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (layout << 61);
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -161,6 +188,8 @@ __device__ __forceinline__ uint32_t swz(int r, int c, int row_bytes) {
     return row_bytes == 128 ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)) : (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
 }
 
+struct AMaps { CUtensorMap m[4]; };       // activation views: [0] everything for stride 1; 2*odd_row + odd_col parity views for stride 2
+
 struct PairCoord { int tx, py, tn; };
 __device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
     PairCoord t;
@@ -173,19 +202,24 @@ __device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
 
 template <int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
-                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_a3,
-                const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_res, const Tc2Params p) {
+conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ CUtensorMap map_res, const Tc2Params p) {
+    const CUtensorMap& map_a0 = maps_a.m[0];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int a_bytes = kBlockM * BK * 2;
-    const int b_bytes = p.half_n * BK * 2;
-    const int stage_bytes = a_bytes + b_bytes;
-    uint8_t* res_buf = smem + (size_t)p.stages * stage_bytes;          // [2][kStageBytes] (has_res only)
+    const int b_sub = p.half_n * BK * 2;                                // one (tap, chunk) block of this CTA's weight rows
+    const int a_sub = p.halo ? 0 : kBlockM * BK * 2;                    // per-tap mode: the matching activation box
+    const int sub_bytes = a_sub + b_sub;
+    const int stage_bytes = p.n_sub * sub_bytes;
+    uint8_t* h_ring = smem;                                             // [h_stages][h_stage_bytes]   (halo mode only)
+    uint8_t* s_ring = smem + (size_t)p.h_stages * p.h_stage_bytes;      // [stages][n_sub][A box | B block]
+    uint8_t* res_buf = s_ring + (size_t)p.stages * stage_bytes;         // [2][kStageBytes] (has_res only)
     uint64_t* bars = reinterpret_cast<uint64_t*>(res_buf + (p.has_res ? 2 * kStageBytes : 0));
-    uint64_t* full_bar = bars;                         // [stages]   (the leader's copy is the live one)
-    uint64_t* empty_bar = bars + kMaxStages;           // [stages]
-    uint64_t* tmem_full = bars + 2 * kMaxStages;       // [2]
+    uint64_t* s_full = bars;                           // [stages]     (the leader's copies of the full barriers are the live ones)
+    uint64_t* s_empty = bars + kMaxStages;             // [stages]
+    uint64_t* h_full = bars + 2 * kMaxStages;          // [h_stages]
+    uint64_t* h_empty = bars + 3 * kMaxStages;         // [h_stages]
+    uint64_t* tmem_full = bars + 4 * kMaxStages;       // [2]
     uint64_t* tmem_empty = tmem_full + 2;              // [2]        (leader's copy: 8 warp arrivals from both CTAs)
     uint64_t* res_full = tmem_empty + 2;               // [2]
     uint64_t* res_empty = res_full + 2;                // [2]
@@ -196,13 +230,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int num_pairs = p.tiles_x * p.pairs_y * p.tiles_n;
-    const int k_iters = p.taps * p.k_chunks;
     const int first_pair = (int)cluster_id_x(), pair_step = (int)num_clusters_x();
+    const int n_groups = p.taps * p.k_chunks / p.n_sub;                 // stages per tile
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
-        for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+        for (int i = 0; i < p.h_stages; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8);
             mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 4);
@@ -221,66 +256,122 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // The K loop of a tile is the sequence of (tap, 64-channel chunk) blocks, tap-major.  A pipeline stage holds
+    // n_sub consecutive blocks behind ONE full/empty barrier pair, so the single MMA-issuing thread pays one wait
+    // and one commit per n_sub * BK/16 MMAs (the issuer, not the tensor pipe, bounds narrow-N layers otherwise).
+    //   per-tap mode: block = activation box {BK, tw, th} shifted by the tap + weight block;
+    //   halo mode (3x3 stride 1, tw = 8): block = weight block only; the activations of the whole tile are ONE
+    //   {BK, tw+2, th+2} halo box per chunk in a second ring, and a tap is a shifted descriptor over it (the
+    //   tensor core applies the 128B/64B swizzle to absolute shared-memory address bits, so a start address
+    //   shifted by whole pixels with a row pitch of tw+2 pixels addresses the TMA-written halo correctly --
+    //   tools/desc_probe.cu, profiles/r01_desc_probe.txt).
     if (warp == 0) {
-        if (lane == 0) {
-            // ===== operand producer (both CTAs) =====
-            int stage = 0; uint32_t phase = 0;
-            const uint32_t pair_tx_bytes = 2u * (uint32_t)(p.tw * p.th * BK * 2 + b_bytes);
+        {
+            // ===== operand producer (both CTAs; whole warp runs the loop, one elected lane issues) =====
+            int st = 0; uint32_t s_phase = 0;
+            int hs = 0; uint32_t h_phase = 0;
+            const uint32_t s_tx = 2u * (uint32_t)p.n_sub * (uint32_t)((p.halo ? 0 : p.a_box_pixels * BK * 2) + b_sub);
+            const uint32_t h_tx = 2u * (uint32_t)p.k_chunks * (uint32_t)(p.a_box_pixels * BK * 2);
             for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
                 const PairCoord t = decode_pair(p, pair);
                 const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
                 const int n0 = t.tn * p.block_n + (int)rank * p.half_n;
-                for (int tap = 0; tap < p.taps; ++tap) {
-                    int dx = 0, dy = 0;
-                    const CUtensorMap* ma = &map_a0;
-                    if (p.taps == 9) {
-                        const int r = tap / 3, s = tap - r * 3;
-                        if (p.stride == 1) { dx = s - 1; dy = r - 1; }
-                        else {
-                            dx = (s == 0) ? -1 : 0; dy = (r == 0) ? -1 : 0;
-                            const int sel = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);   // odd row / odd column views
-                            ma = sel == 0 ? &map_a0 : sel == 1 ? &map_a1 : sel == 2 ? &map_a2 : &map_a3;
+                if (p.halo) {
+                    mbar_wait(&h_empty[hs], h_phase ^ 1);
+                    const uint32_t lb = mapa(smem_u32(&h_full[hs]), 0);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(&h_full[hs], h_tx);
+                        for (int kc = 0; kc < p.k_chunks; ++kc)
+                            tma_load_3d_pair(h_ring + (size_t)hs * p.h_stage_bytes + (size_t)kc * p.h_chunk_bytes, &map_a0, lb, kc * BK, x0 - 1, y0 - 1);
+                    }
+                    __syncwarp();
+                    if (++hs == p.h_stages) { hs = 0; h_phase ^= 1; }
+                }
+                int tap = 0, kc = 0;
+                for (int g = 0; g < n_groups; ++g) {
+                    mbar_wait(&s_empty[st], s_phase ^ 1);
+                    const uint32_t lb = mapa(smem_u32(&s_full[st]), 0);
+                    uint8_t* sb = s_ring + (size_t)st * stage_bytes;
+                    const bool leader_lane = elect_one();
+                    if (leader_lane && rank == 0) mbar_expect_tx(&s_full[st], s_tx);
+                    for (int j = 0; j < p.n_sub; ++j) {
+                        if (!p.halo) {
+                            int dx = 0, dy = 0, sel = 0;
+                            if (p.taps == 9) {
+                                const int r = tap / 3, s = tap - r * 3;
+                                if (p.stride == 1) { dx = s - 1; dy = r - 1; }
+                                else {
+                                    dx = (s == 0) ? -1 : 0; dy = (r == 0) ? -1 : 0;
+                                    sel = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);   // odd row / odd column views
+                                }
+                            }
+                            const CUtensorMap* ma = &maps_a.m[sel];
+                            if (leader_lane) tma_load_3d_pair(sb + (size_t)j * sub_bytes, ma, lb, kc * BK, x0 + dx, y0 + dy);
                         }
+                        if (leader_lane) tma_load_2d_pair(sb + (size_t)j * sub_bytes + a_sub, &map_b, lb, kc * BK, tap * p.cout_pad + n0);
+                        if (++kc == p.k_chunks) { kc = 0; ++tap; }
                     }
-                    for (int kc = 0; kc < p.k_chunks; ++kc) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
-                        uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                        if (rank == 0) mbar_expect_tx(&full_bar[stage], pair_tx_bytes);
-                        const uint32_t leader_bar = mapa(smem_u32(&full_bar[stage]), 0);
-                        tma_load_3d_pair(sa, ma, leader_bar, kc * BK, x0 + dx, y0 + dy);
-                        tma_load_2d_pair(sa + a_bytes, &map_b, leader_bar, kc * BK, tap * p.cout_pad + n0);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                    }
+                    __syncwarp();
+                    if (++st == p.stages) { st = 0; s_phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // ===== MMA issuer (leader CTA) =====
-            int stage = 0; uint32_t phase = 0;
+        if (rank == 0) {
+            // ===== MMA issuer (leader CTA; whole warp runs the loop, one elected lane issues) =====
+            int st = 0; uint32_t s_phase = 0;
+            int hs = 0; uint32_t h_phase = 0;
             int as = 0; uint32_t aphase = 0;
+            const uint32_t pixel_bytes = BK * 2;
+            const uint32_t sbo_b = 8 * pixel_bytes;
+            const uint32_t sbo_a = p.halo ? (uint32_t)(p.tw + 2) * pixel_bytes : 8 * pixel_bytes;
+            const uint32_t s_ring_addr = smem_u32(s_ring), h_ring_addr = smem_u32(h_ring);
             for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
-                tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
-                for (int kit = 0; kit < k_iters; ++kit) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t adesc = make_kmajor_desc<BK>(sa);
-                    const uint64_t bdesc = make_kmajor_desc<BK>(sa + a_bytes);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kit | k) != 0);
-                    umma_commit_pair(&empty_bar[stage]);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                uint32_t h_addr = 0;
+                if (p.halo) {
+                    mbar_wait(&h_full[hs], h_phase);
+                    h_addr = h_ring_addr + (uint32_t)(hs * p.h_stage_bytes);
                 }
-                umma_commit_pair(&tmem_full[as]);
+                tc_fence_after();
+                uint32_t accumulate = 0;
+                int tap = 0, kc = 0;
+                for (int g = 0; g < n_groups; ++g) {
+                    mbar_wait(&s_full[st], s_phase);
+                    tc_fence_after();
+                    const uint32_t sb = s_ring_addr + (uint32_t)(st * stage_bytes);
+                    for (int j = 0; j < p.n_sub; ++j) {
+                        uint32_t a_addr = sb + (uint32_t)(j * sub_bytes);
+                        if (p.halo) {
+                            const int r = tap / 3, s = tap - r * 3;
+                            a_addr = h_addr + (uint32_t)(kc * p.h_chunk_bytes) + (uint32_t)(r * (p.tw + 2) + s) * pixel_bytes;
+                        }
+                        const uint64_t adesc = make_kmajor_desc<BK>(a_addr, sbo_a);
+                        const uint64_t bdesc = make_kmajor_desc<BK>(sb + (uint32_t)(j * sub_bytes + a_sub), sbo_b);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k)
+                                umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (k == 0) ? accumulate : 1u);
+                        }
+                        accumulate = 1;
+                        if (++kc == p.k_chunks) { kc = 0; ++tap; }
+                    }
+                    if (elect_one()) umma_commit_pair(&s_empty[st]);
+                    __syncwarp();
+                    if (++st == p.stages) { st = 0; s_phase ^= 1; }
+                }
+                if (p.halo) {
+                    if (elect_one()) umma_commit_pair(&h_empty[hs]);
+                    if (++hs == p.h_stages) { hs = 0; h_phase ^= 1; }
+                }
+                if (elect_one()) umma_commit_pair(&tmem_full[as]);
+                __syncwarp();
                 as ^= 1; if (as == 0) aphase ^= 1;
             }
         }
     } else if (warp == 2) {
-        if (lane == 0 && p.has_res) {
+        if (p.has_res) {
             // ===== residual producer: the 64-channel chunks of this CTA's output tile, in epilogue order =====
             int rb = 0; uint32_t rphase = 0;
             const int n_chunks = p.block_n / p.chunk_cols;
@@ -290,8 +381,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
                 const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
                 for (int j = 0; j < n_chunks; ++j) {
                     mbar_wait(&res_empty[rb], rphase ^ 1);
-                    mbar_expect_tx(&res_full[rb], bytes);
-                    tma_load_3d(res_buf + rb * kStageBytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0);
+                    if (elect_one()) {
+                        mbar_expect_tx(&res_full[rb], bytes);
+                        tma_load_3d(res_buf + rb * kStageBytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0);
+                    }
+                    __syncwarp();
                     rb ^= 1; if (rb == 0) rphase ^= 1;
                 }
             }
@@ -310,7 +404,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constan
             const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
             const int Y = y0 + my, x = x0 + mx;
             const int img = Y / p.out_rows, y = Y - img * p.out_rows;
-            const bool valid = (m < p.tw * p.th) && (Y < p.total_rows) && (y < p.out_h);
+            const bool valid = (m < p.tw * p.th) && (Y < p.total_rows) && (y < p.out_h) && (x < p.out_w);
             const int n0 = t.tn * p.block_n;
             mbar_wait(&tmem_full[as], aphase);
             tc_fence_after();
@@ -443,7 +537,7 @@ int32_t encode(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int r
 }
 
 struct Tc2Plan {
-    CUtensorMap map_a[4];
+    AMaps maps;
     CUtensorMap map_b, map_res;
     Tc2Params p;
     int bk;
@@ -495,8 +589,11 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     }
     if (bn % 32) { delete plan; return fail(OM_ERR_INVALID, "padded cout %d cannot be split over a CTA pair", cout_pad); }
     p.block_n = bn; p.half_n = bn / 2; p.cout_pad = cout_pad; p.tiles_n = cout_pad / bn;
-    p.tw = pick_tile_w(d.out_w, d.out_kind == OM_OUT_NCHW); p.th = kBlockM / p.tw;
-    p.tiles_x = d.out_w / p.tw;
+    const char* halo_env = getenv("ORIENMASK_B200_HALO");
+    p.halo = d.ksize == 3 && d.stride == 1 && d.out_kind != OM_OUT_NCHW && (d.out_w % 8 == 0 || d.out_w >= 64) &&
+             !(halo_env && halo_env[0] == '0');
+    if (p.halo) { p.tw = 8; p.th = 16; p.tiles_x = (d.out_w + 7) / 8; }
+    else { p.tw = pick_tile_w(d.out_w, d.out_kind == OM_OUT_NCHW); p.th = kBlockM / p.tw; p.tiles_x = d.out_w / p.tw; }
     p.total_rows = d.batch * d.out_rows;
     const int tiles_y = (p.total_rows + p.th - 1) / p.th;
     p.pairs_y = (tiles_y + 1) / 2;
@@ -505,14 +602,36 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     if (d.out_kind == OM_OUT_ACT) { p.chunk_cols = bn >= 64 ? 64 : 32; p.row_bytes = p.chunk_cols * 2; }
     else { p.chunk_cols = 32; p.row_bytes = 128; }
     if (bn % p.chunk_cols) { delete plan; return fail(OM_ERR_INVALID, "tile width %d is not a multiple of the staged chunk", bn); }
-    const int stage_bytes = (kBlockM + p.half_n) * bk * 2;
+    p.a_box_pixels = p.halo ? (p.tw + 2) * (p.th + 2) : p.tw * p.th;
+    p.h_chunk_bytes = p.halo ? ((p.a_box_pixels * bk * 2 + 1023) / 1024) * 1024 : 0;
+    p.h_stage_bytes = p.h_chunk_bytes * p.k_chunks;
+    p.h_stages = p.halo ? 2 : 0;
+    const int sub_bytes = (p.halo ? 0 : kBlockM * bk * 2) + p.half_n * bk * 2;
     const int epi_bytes = p.has_res ? 2 * kStageBytes : 0;
     constexpr int kMaxSmem = 227 * 1024;
-    const int fixed = 1024 + epi_bytes + (2 * kMaxStages + 8) * 8 + 16 + cout_pad * 4;
-    int stages = (kMaxSmem - fixed) / stage_bytes;
-    if (stages > kMaxStages) stages = kMaxStages;
-    if (stages < 2) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
-    p.stages = stages;
+    const int fixed = 1024 + epi_bytes + (4 * kMaxStages + 8) * 8 + 16 + cout_pad * 4;
+    const int ring_budget = kMaxSmem - fixed - p.h_stages * p.h_stage_bytes;
+    if (ring_budget < 2 * sub_bytes) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
+    // blocks per stage: enough MMA cycles behind each barrier round trip (>= ~1024 tensor cycles; one block issues
+    // BK/16 MMAs of N/2 cycles each), while keeping at least three stages in flight
+    {
+        const int total = p.taps * p.k_chunks;
+        const int block_cycles = (bk / 16) * (bn / 2);
+        const char* ns_env = getenv("ORIENMASK_B200_NSUB");
+        int best = 1;
+        for (int n = 1; n <= total; ++n) {
+            if (total % n) continue;
+            const int st = ring_budget / (n * sub_bytes);
+            if (st < 3 && n > 1) break;
+            best = n;
+            if (n * block_cycles >= 1024) break;
+        }
+        if (ns_env && atoi(ns_env) > 0 && total % atoi(ns_env) == 0 && ring_budget / (atoi(ns_env) * sub_bytes) >= 2) best = atoi(ns_env);
+        p.n_sub = best;
+        p.stages = ring_budget / (best * sub_bytes);
+        if (p.stages > kMaxStages) p.stages = kMaxStages;
+        if (p.stages < 2) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
+    }
     int cols = 32;
     while (cols < 2 * bn) cols <<= 1;
     p.tmem_cols = cols;
@@ -529,9 +648,9 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     if (d.stride == 1) {
         cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.batch * d.in_rows};
         cuuint64_t str[2] = {(cuuint64_t)d.cin * esz, (cuuint64_t)d.in_w * d.cin * esz};
-        cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.tw, (cuuint32_t)p.th};
-        rc = encode(&plan->map_a[0], f16, d.input, 3, dims, str, box, bk * 2);
-        for (int i = 1; i < 4 && rc == OM_OK; ++i) plan->map_a[i] = plan->map_a[0];
+        cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(p.halo ? p.tw + 2 : p.tw), (cuuint32_t)(p.halo ? p.th + 2 : p.th)};
+        rc = encode(&plan->maps.m[0], f16, d.input, 3, dims, str, box, bk * 2);
+        for (int i = 1; i < 4 && rc == OM_OK; ++i) plan->maps.m[i] = plan->maps.m[0];
     } else {
         for (int sel = 0; sel < 4 && rc == OM_OK; ++sel) {          // sel = 2*odd_row + odd_col
             const int py = sel >> 1, px = sel & 1;
@@ -539,7 +658,7 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
             cuuint64_t str[2] = {(cuuint64_t)2 * d.cin * esz, (cuuint64_t)2 * d.in_w * d.cin * esz};
             cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.tw, (cuuint32_t)p.th};
             const char* base = reinterpret_cast<const char*>(d.input) + ((size_t)py * d.in_w + px) * d.cin * esz;
-            rc = encode(&plan->map_a[sel], f16, base, 3, dims, str, box, bk * 2);
+            rc = encode(&plan->maps.m[sel], f16, base, 3, dims, str, box, bk * 2);
         }
     }
     if (rc == OM_OK) {
@@ -554,10 +673,10 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
         cuuint32_t box[3] = {(cuuint32_t)p.chunk_cols, (cuuint32_t)p.tw, (cuuint32_t)p.th};
         rc = encode(&plan->map_res, f16, d.residual, 3, dims, str, box, p.row_bytes);
     }
-    if (rc == OM_OK && !p.has_res) plan->map_res = plan->map_a[0];
+    if (rc == OM_OK && !p.has_res) plan->map_res = plan->maps.m[0];
     if (rc != OM_OK) { delete plan; return rc; }
 
-    plan->smem = (size_t)fixed + (size_t)stages * stage_bytes;
+    plan->smem = (size_t)fixed + (size_t)p.h_stages * p.h_stage_bytes + (size_t)p.stages * p.n_sub * sub_bytes;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -575,10 +694,10 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
 int32_t tc2_plan_run(const void* vp, cudaStream_t stream) {
     const Tc2Plan* plan = reinterpret_cast<const Tc2Plan*>(vp);
     if (plan->bk == 64)
-        conv_tc2_kernel<64><<<plan->grid, kThreads, plan->smem, stream>>>(plan->map_a[0], plan->map_a[1], plan->map_a[2], plan->map_a[3],
+        conv_tc2_kernel<64><<<plan->grid, kThreads, plan->smem, stream>>>(plan->maps,
                                                                           plan->map_b, plan->map_res, plan->p);
     else
-        conv_tc2_kernel<32><<<plan->grid, kThreads, plan->smem, stream>>>(plan->map_a[0], plan->map_a[1], plan->map_a[2], plan->map_a[3],
+        conv_tc2_kernel<32><<<plan->grid, kThreads, plan->smem, stream>>>(plan->maps,
                                                                           plan->map_b, plan->map_res, plan->p);
     return check_launch("conv_tc2_kernel");
 }
