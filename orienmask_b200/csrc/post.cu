@@ -8,6 +8,7 @@
 //
 // All kernels are HBM/L2-bound integer+fp32 work: coalesced plane-strided reads of the NCHW heads,
 // 16-byte streaming stores for the masks, warp shuffles/ballots for scans, no tensor cores.
+#include <cmath>
 #include <cstring>
 
 #include "common.cuh"
@@ -35,8 +36,10 @@ struct PostDev {
 
 struct SelState {
     unsigned hist[3][kHistBins];
-    unsigned prefix, k_rem, total, take_all, T, need_eq, eq_taken, n_out;
+    unsigned prefix, k_rem, total, take_all, T, need_eq, eq_taken, n_out, n_list, pad[3];
 };
+
+constexpr int kListBuf = 4096;                 // staged survivors per block before a flush (>= 2 rounds of 256 x 8)
 
 __device__ __forceinline__ float sigmoidf_rn(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -51,47 +54,105 @@ __device__ __forceinline__ void locate_pred(const PostDev& d, int n, int& s, int
     cell = r - a * plane;
 }
 
-// One thread per prediction, 80 plane-strided (coalesced across the warp) class reads each.
-// MODE 0..2: histogram pass of the 11/11/10-bit radix select; MODE 3: collect.
+// Pass 1 (the only pass over the head tensors): one thread per prediction, 80 plane-strided (coalesced across
+// the warp) class reads each.  Every (prediction, class) whose score clears conf_thresh is appended to the
+// image's candidate list (score bits + flat index, unordered) and counted in the level-0 radix histogram; the
+// remaining radix levels and the collection run over that list, not over the heads, so sigmoid/exp are
+// evaluated once per pair.  Logits that cannot clear the threshold even with sigma(obj) = 1 skip the
+// sigmoid entirely (margin 0.01 in logit space >> any rounding of the fp32 sigmoid).
+__global__ void __launch_bounds__(kSelThreads) conf_compact_kernel(PostDev d, SelState* st, unsigned* keys, unsigned* flats,
+                                                                   long long list_cap, float reject_logit) {
+    __shared__ unsigned sh[kHistBins];
+    __shared__ uint2 s_buf[kListBuf];
+    __shared__ unsigned s_cnt, s_base;
+    const int b = blockIdx.y;
+    SelState& S = st[b];
+    for (int i = threadIdx.x; i < kHistBins; i += kSelThreads) sh[i] = 0;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int n = blockIdx.x * kSelThreads + threadIdx.x;
+    const float* pc = nullptr;
+    int plane = 0;
+    float obj = 0.f;
+    bool live = false;
+    if (n < d.n_pred) {
+        int s, a, cell;
+        locate_pred(d, n, s, a, cell, plane);
+        const float* p = d.bbox[s] + (long long)b * d.bstride[s] + (long long)(a * (5 + d.C)) * plane + cell;
+        const float ol = __ldg(p + 4 * plane);
+        if (ol >= reject_logit) {
+            obj = sigmoidf_rn(ol);
+            live = true;
+        }
+        pc = p + 5 * plane;
+    }
+    unsigned* kout = keys + (long long)b * list_cap;
+    unsigned* fout = flats + (long long)b * list_cap;
+    for (int c0 = 0; c0 < d.C; c0 += 8) {
+        if (live) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = (c0 + i < d.C) ? __ldg(pc + (long long)(c0 + i) * plane) : -1e30f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (v[i] < reject_logit) continue;
+                const float conf = sigmoidf_rn(v[i]) * obj;
+                if (conf > d.conf_thresh) {
+                    const unsigned key = __float_as_uint(conf);
+                    atomicAdd(&sh[key >> 21], 1u);
+                    const unsigned slot = atomicAdd(&s_cnt, 1u);
+                    s_buf[slot] = make_uint2(key, (unsigned)(n * d.C + c0 + i));
+                }
+            }
+        }
+        __syncthreads();
+        const unsigned cnt = s_cnt;
+        if (cnt > (unsigned)(kListBuf - kSelThreads * 8) || c0 + 8 >= d.C) {      // block-uniform
+            if (threadIdx.x == 0) s_base = atomicAdd(&S.n_list, cnt);
+            __syncthreads();                              // every thread has read s_cnt by now
+            if (threadIdx.x == 0) s_cnt = 0;
+            const unsigned base = s_base;
+            for (unsigned i = threadIdx.x; i < cnt; i += kSelThreads) {
+                kout[base + i] = s_buf[i].x;
+                fout[base + i] = s_buf[i].y;
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < kHistBins; i += kSelThreads)
+        if (sh[i]) atomicAdd(&S.hist[0][i], sh[i]);
+}
+
+// Radix levels 1 and 2 (MODE 1, 2: histogram of the next 11 / 10 key bits under the current prefix) and the
+// collection (MODE 3) over the candidate list; a fixed number of blocks per image strides over the list.
 template <int MODE>
-__global__ void __launch_bounds__(kSelThreads) select_pass_kernel(PostDev d, SelState* st, uint2* raw) {
+__global__ void __launch_bounds__(kSelThreads) select_list_kernel(PostDev d, SelState* st, const unsigned* keys, const unsigned* flats,
+                                                                  long long list_cap, uint2* raw) {
     __shared__ unsigned sh[kHistBins];
     const int b = blockIdx.y;
     SelState& S = st[b];
-    if (MODE >= 1 && MODE <= 2 && S.take_all) return;
-    const unsigned prefix = (MODE >= 1) ? S.prefix : 0u;
+    if (MODE < 3 && S.take_all) return;
+    const unsigned prefix = S.prefix;
     const unsigned T = S.T, need_eq = S.need_eq, take_all = S.take_all;
+    const unsigned n_list = S.n_list;
     if (MODE < 3) {
         for (int i = threadIdx.x; i < kHistBins; i += kSelThreads) sh[i] = 0;
         __syncthreads();
     }
-    const int n = blockIdx.x * kSelThreads + threadIdx.x;
-    if (n < d.n_pred) {
-        int s, a, cell, plane;
-        locate_pred(d, n, s, a, cell, plane);
-        const float* p = d.bbox[s] + (long long)b * d.bstride[s] + (long long)(a * (5 + d.C)) * plane + cell;
-        const float obj = sigmoidf_rn(__ldg(p + 4 * plane));
-        const float* pc = p + 5 * plane;
-#pragma unroll 8
-        for (int c = 0; c < d.C; ++c) {
-            const float conf = sigmoidf_rn(__ldg(pc + (long long)c * plane)) * obj;
-            if (conf > d.conf_thresh) {
-                const unsigned key = __float_as_uint(conf);
-                if (MODE == 0) {
-                    atomicAdd(&sh[key >> 21], 1u);
-                } else if (MODE == 1) {
-                    if ((key >> 21) == prefix) atomicAdd(&sh[(key >> 10) & 2047u], 1u);
-                } else if (MODE == 2) {
-                    if ((key >> 10) == prefix) atomicAdd(&sh[key & 1023u], 1u);
-                } else {
-                    bool take = take_all || key > T;
-                    if (!take && key == T) take = atomicAdd(&S.eq_taken, 1u) < need_eq;
-                    if (take) {
-                        const unsigned slot = atomicAdd(&S.n_out, 1u);
-                        if (slot < (unsigned)d.nms_pre)
-                            raw[(long long)b * d.nms_pre + slot] = make_uint2(key, (unsigned)(n * d.C + c));
-                    }
-                }
+    const unsigned* kin = keys + (long long)b * list_cap;
+    const unsigned* fin = flats + (long long)b * list_cap;
+    for (unsigned i = blockIdx.x * kSelThreads + threadIdx.x; i < n_list; i += gridDim.x * kSelThreads) {
+        const unsigned key = kin[i];
+        if (MODE == 1) {
+            if ((key >> 21) == prefix) atomicAdd(&sh[(key >> 10) & 2047u], 1u);
+        } else if (MODE == 2) {
+            if ((key >> 10) == prefix) atomicAdd(&sh[key & 1023u], 1u);
+        } else {
+            bool take = take_all || key > T;
+            if (!take && key == T) take = atomicAdd(&S.eq_taken, 1u) < need_eq;
+            if (take) {
+                const unsigned slot = atomicAdd(&S.n_out, 1u);
+                if (slot < (unsigned)d.nms_pre) raw[(long long)b * d.nms_pre + slot] = make_uint2(key, fin[i]);
             }
         }
     }
@@ -260,7 +321,7 @@ __device__ int compact_slots(const unsigned char* flag, int n, int* slot, int* c
 // One CTA per box list.  Warp-cooperative: all warps fill the n x n/32 suppression bit matrix,
 // warp 0 then resolves the greedy chain with the removed-set held one word per lane.
 template <bool BATCHED>
-__global__ void __launch_bounds__(256) nms_kernel(NmsArgs a, PostDev d) {
+__global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
     extern __shared__ unsigned long long smem64[];
     const int b = blockIdx.x;
     const int n = a.counts ? min(a.counts[b], a.cap) : a.n;
@@ -293,24 +354,32 @@ __global__ void __launch_bounds__(256) nms_kernel(NmsArgs a, PostDev d) {
     }
     __syncthreads();
 
-    for (int idx = threadIdx.x; idx < n * nw; idx += blockDim.x) {
-        const int r = idx / nw, wd = idx - r * nw;
-        unsigned bits = 0;
-        if (wd * 32 + 31 > r) {
-            const float ix1 = gx1[r], iy1 = gy1[r], ix2 = gx2[r], iy2 = gy2[r], ia = gar[r];
-            for (int bb = 0; bb < 32; ++bb) {
-                const int j = wd * 32 + bb;
-                if (j > r && j < n) {
+    // suppression bit matrix, upper triangle: one warp per (32-row block, 32-column word); lane = row, so the five
+    // shared-memory reads of box j are warp-wide broadcasts and the word stores hit 32 distinct banks (nw is odd
+    // or the rows differ in r * nw mod 32 -- at worst a 2-way conflict), instead of nw-way conflicts on every read
+    {
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        const int nrb = (n + 31) >> 5;
+        for (int item = warp; item < nrb * nw; item += nwarps) {
+            const int rb = item / nw, wd = item - rb * nw;
+            const int r = rb * 32 + lane;
+            if (r >= n) continue;
+            unsigned bits = 0;
+            if (wd >= rb) {
+                const float ix1 = gx1[r], iy1 = gy1[r], ix2 = gx2[r], iy2 = gy2[r], ia = gar[r];
+                const int jn = max(0, min(32, n - wd * 32));
+                for (int bb = 0; bb < jn; ++bb) {
+                    const int j = wd * 32 + bb;
                     const float xx1 = fmaxf(ix1, gx1[j]), yy1 = fmaxf(iy1, gy1[j]);
                     const float xx2 = fminf(ix2, gx2[j]), yy2 = fminf(iy2, gy2[j]);
                     const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
                     const float inter = w * h;
                     const float ovr = inter / (ia + gar[j] - inter);
-                    if (ovr >= a.thr) bits |= 1u << bb;
+                    if (j > r && ovr >= a.thr) bits |= 1u << bb;
                 }
             }
+            mask[r * nw + wd] = bits;
         }
-        mask[idx] = bits;
     }
     __syncthreads();
 
@@ -456,8 +525,20 @@ __global__ void __launch_bounds__(256) mask_kernel(PostDev d, const int* det_cou
                 }
             }
         }
+        // bounds of the run: fp32 subtraction is monotonic, so fl(min - c) >= t (or fl(max - c) <= -t) for the run
+        // extremes proves |fl(p - c)| >= t for every pixel of the run -- an all-zero store without the 16 tests
+        float pxmin = px[0], pxmax = px[0], pymin = py[0], pymax = py[0];
+#pragma unroll
+        for (int i = 1; i < 16; ++i) {
+            pxmin = fminf(pxmin, px[i]); pxmax = fmaxf(pxmax, px[i]);
+            pymin = fminf(pymin, py[i]); pymax = fmaxf(pymax, py[i]);
+        }
         for (int e = i0; e < i1; ++e) {
             const MaskInst m = inst[e];
+            if (pxmin - m.xc >= m.tw || pxmax - m.xc <= -m.tw || pymin - m.yc >= m.th || pymax - m.yc <= -m.th) {
+                __stcs(reinterpret_cast<uint4*>(mrow + (long long)m.k * img_plane), make_uint4(0u, 0u, 0u, 0u));
+                continue;
+            }
             unsigned w[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -526,12 +607,18 @@ int32_t allow_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+// workspace layout: [batch] SelState | [batch][nms_pre] raw (key, flat) | [batch][cap] keys | [batch][cap] flats,
+// cap = n_pred * num_classes (every pair may clear conf_thresh, e.g. untrained weights)
+static size_t ws_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
 extern "C" int32_t om_post_workspace_bytes(const om_post_config* cfg, int32_t batch, size_t* bytes) {
     PostDev d;
     int32_t rc = make_dev(cfg, d);
     if (rc) return rc;
     if (batch < 1 || !bytes) return om::fail(OM_ERR_INVALID, "bad batch / null output");
-    *bytes = (size_t)batch * sizeof(SelState) + (size_t)batch * cfg->nms_pre * sizeof(uint2);
+    const size_t cap = (size_t)d.n_pred * d.C;
+    *bytes = ws_align((size_t)batch * sizeof(SelState)) + ws_align((size_t)batch * cfg->nms_pre * sizeof(uint2)) +
+             2 * ws_align((size_t)batch * cap * sizeof(unsigned));
     return OM_OK;
 }
 
@@ -548,24 +635,42 @@ extern "C" int32_t om_decode_select(const om_post_config* cfg, const float* cons
         d.bbox[s] = bbox[s]; d.bstride[s] = bbox_batch_stride[s];
     }
     cudaStream_t st = (cudaStream_t)stream;
-    SelState* state = reinterpret_cast<SelState*>(workspace);
-    uint2* raw = reinterpret_cast<uint2*>(state + batch);
+    const long long cap = (long long)d.n_pred * d.C;
+    char* ws = reinterpret_cast<char*>(workspace);
+    SelState* state = reinterpret_cast<SelState*>(ws);
+    ws += ws_align((size_t)batch * sizeof(SelState));
+    uint2* raw = reinterpret_cast<uint2*>(ws);
+    ws += ws_align((size_t)batch * d.nms_pre * sizeof(uint2));
+    unsigned* keys = reinterpret_cast<unsigned*>(ws);
+    ws += ws_align((size_t)batch * cap * sizeof(unsigned));
+    unsigned* flats = reinterpret_cast<unsigned*>(ws);
     OM_CUDA_TRY(cudaMemsetAsync(state, 0, (size_t)batch * sizeof(SelState), st));
+    // sigma(x) <= conf_thresh for x <= logit(conf_thresh): such logits can never yield a candidate
+    const double t = (double)d.conf_thresh;
+    const float reject_logit = t >= 1.0 ? 3.0e38f : (float)(log(t / (1.0 - t)) - 0.01);
     dim3 grid(om::ceil_div(d.n_pred, kSelThreads), batch);
-    select_pass_kernel<0><<<grid, kSelThreads, 0, st>>>(d, state, raw);
-    if ((rc = om::check_launch("select_pass<0>"))) return rc;
+    conf_compact_kernel<<<grid, kSelThreads, 0, st>>>(d, state, keys, flats, cap, reject_logit);
+    if ((rc = om::check_launch("conf_compact"))) return rc;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int per_image = (4 * sms + batch - 1) / batch;
+    if (per_image < 1) per_image = 1;
+    const int max_useful = (int)((cap + kSelThreads - 1) / kSelThreads);
+    if (per_image > max_useful) per_image = max_useful;
+    dim3 lgrid(per_image, batch);
     select_scan_kernel<0><<<batch, 32, 0, st>>>(state, d.nms_pre);
     if ((rc = om::check_launch("select_scan<0>"))) return rc;
-    select_pass_kernel<1><<<grid, kSelThreads, 0, st>>>(d, state, raw);
-    if ((rc = om::check_launch("select_pass<1>"))) return rc;
+    select_list_kernel<1><<<lgrid, kSelThreads, 0, st>>>(d, state, keys, flats, cap, raw);
+    if ((rc = om::check_launch("select_list<1>"))) return rc;
     select_scan_kernel<1><<<batch, 32, 0, st>>>(state, d.nms_pre);
     if ((rc = om::check_launch("select_scan<1>"))) return rc;
-    select_pass_kernel<2><<<grid, kSelThreads, 0, st>>>(d, state, raw);
-    if ((rc = om::check_launch("select_pass<2>"))) return rc;
+    select_list_kernel<2><<<lgrid, kSelThreads, 0, st>>>(d, state, keys, flats, cap, raw);
+    if ((rc = om::check_launch("select_list<2>"))) return rc;
     select_scan_kernel<2><<<batch, 32, 0, st>>>(state, d.nms_pre);
     if ((rc = om::check_launch("select_scan<2>"))) return rc;
-    select_pass_kernel<3><<<grid, kSelThreads, 0, st>>>(d, state, raw);
-    if ((rc = om::check_launch("select_pass<3>"))) return rc;
+    select_list_kernel<3><<<lgrid, kSelThreads, 0, st>>>(d, state, keys, flats, cap, raw);
+    if ((rc = om::check_launch("select_list<3>"))) return rc;
     cand_finalize_kernel<<<batch, 256, (size_t)d.NP * 8, st>>>(d, state, raw, cand_count, cand_det, cand_cls, cand_pred);
     return om::check_launch("cand_finalize");
 }
@@ -585,7 +690,7 @@ extern "C" int32_t om_batched_nms(const om_post_config* cfg, const int32_t* cand
     a.det_anchor = det_anchor; a.det_keep = det_keep;
     const size_t smem = nms_smem_bytes(a.NP, a.cap);
     if ((rc = allow_smem(nms_kernel<true>, smem))) return rc;
-    nms_kernel<true><<<batch, 256, smem, (cudaStream_t)stream>>>(a, d);
+    nms_kernel<true><<<batch, 512, smem, (cudaStream_t)stream>>>(a, d);
     return om::check_launch("nms_kernel<batched>");
 }
 
@@ -604,7 +709,7 @@ extern "C" int32_t om_nms(const float* dets, int32_t n, float threshold, int64_t
     const size_t smem = nms_smem_bytes(a.NP, a.cap);
     int32_t rc;
     if ((rc = allow_smem(nms_kernel<false>, smem))) return rc;
-    nms_kernel<false><<<1, 256, smem, (cudaStream_t)stream>>>(a, d);
+    nms_kernel<false><<<1, 512, smem, (cudaStream_t)stream>>>(a, d);
     return om::check_launch("nms_kernel<single>");
 }
 

@@ -48,7 +48,7 @@ def main():
         rows = [(i, 'conv_', t) for i, t in enumerate(json.load(open(a.csv)))]
     else:
         rows = read_launches(a.csv)
-    conv_names = ('conv_tc', 'stem_kernel', 'conv_f32', 'conv_')
+    conv_names = ('conv_tc', 'stem_kernel', 'stem_tc', 'conv_f32', 'conv_')
     conv = [(i, n, t) for i, n, t in rows if any(c in n for c in conv_names)]
     other = [(i, n, t) for i, n, t in rows if not any(c in n for c in conv_names)]
     per_fwd = len(layers)
