@@ -23,6 +23,12 @@ int32_t fail(int32_t code, const char* fmt, ...) {
 
 void count_launch(int n) { g_launches += n; }
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ORIENMASK_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
 }  // namespace om
 
 struct om_conv {

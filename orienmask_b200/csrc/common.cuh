@@ -22,7 +22,32 @@ inline int32_t check_launch(const char* what) {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Launch with programmatic dependent launch (PDL): the grid may start while its predecessor in the stream drains;
+// the kernel must execute `griddepcontrol.wait` (pdl_wait()) before it touches memory the predecessor reads or
+// writes.  ORIENMASK_B200_PDL=0 turns the attribute off (plain stream order) for A/B measurements.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace om
+
+#ifdef __CUDACC__
+// Device side of PDL: block until every prerequisite grid has completed and its writes are visible, then let the
+// next grid in the stream begin its own prologue.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
 
 #define OM_CUDA_TRY(expr)                                                                  \
     do {                                                                                   \

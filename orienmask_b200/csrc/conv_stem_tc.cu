@@ -57,11 +57,11 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8])
 __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ img, const float* __restrict__ w27,
                                                       const float* __restrict__ bias, __half* __restrict__ out,
                                                       int batch, int h, int wd, int rows) {
-    __shared__ __align__(1024) uint8_t s_a[128 * 64];        // im2col rows, K-major SWIZZLE_64B
+    __shared__ __align__(1024) uint8_t s_a[2][128 * 64];     // im2col rows, K-major SWIZZLE_64B (double-buffered)
     __shared__ __align__(1024) uint8_t s_b[kCout * 64];      // weights [cout][k], same layout
     __shared__ float s_patch[3][kTileH + 2][kPatchW];
     __shared__ float s_bias[kCout];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -78,41 +78,107 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
     }
     if (tid < kCout) s_bias[tid] = bias[tid];
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&s_tmem)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(smem_u32(&s_tmem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
+    pdl_wait();                                        // the previous step's last kernels may still read/write our buffers
     const uint32_t idesc = (1u << 4) | ((uint32_t)(kCout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint64_t adesc = kmajor_desc_64b(smem_u32(s_a)), bdesc = kmajor_desc_64b(smem_u32(s_b));
+    const uint64_t bdesc = kmajor_desc_64b(smem_u32(s_b));
 
     const int tiles_x = wd / kTileW, tiles_y = h / kTileH;
     const int tiles_per_image = tiles_x * tiles_y;
     const long long total = (long long)batch * tiles_per_image;
-    uint32_t phase = 0;
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int n = (int)(tile / tiles_per_image);
-        const int r = (int)(tile - (long long)n * tiles_per_image);
+    uint32_t phase[2] = {0, 0};
+    constexpr int kPatchElems = 3 * (kTileH + 2) * 34;               // 612 = 4.78 per thread
+    constexpr int kPerThread = (kPatchElems + 127) / 128;
+    // patch of a tile: rows y0-1 .. y0+4, columns x0-1 .. x0+32 of the three planes (zero outside the image);
+    // the loads for tile i+1 are issued before tile i is processed, so their latency hides behind its work
+    // per-thread patch slots (tile-independent): plane/row/column inside the patch, offset inside the image, smem index
+    int p_off[kPerThread], p_y[kPerThread], p_x[kPerThread], p_s[kPerThread];
+#pragma unroll
+    for (int q = 0; q < kPerThread; ++q) {
+        const int i = tid + q * 128;
+        const int ci = i / ((kTileH + 2) * 34);
+        const int rem = i - ci * (kTileH + 2) * 34;
+        const int py = rem / 34, px = rem - py * 34;
+        p_y[q] = i < kPatchElems ? py - 1 : -(1 << 20);                 // out-of-range slot -> never valid
+        p_x[q] = px - 1;
+        p_off[q] = (ci * h + py - 1) * wd + px - 1;
+        p_s[q] = (i / 34) * kPatchW + (i % 34);
+    }
+    const int itotal = (int)total;
+    auto fetch = [&](int tile, float (&regs)[kPerThread]) {
+        const int n = tile / tiles_per_image;
+        const int r = tile - n * tiles_per_image;
         const int ty = r / tiles_x, tx = r - ty * tiles_x;
-        const int x0 = tx * kTileW, y0 = ty * kTileH;
-        // 1. patch: rows y0-1 .. y0+4, columns x0-1 .. x0+32 of the three planes (zero outside the image)
-        for (int i = tid; i < 3 * (kTileH + 2) * 34; i += 128) {
-            const int ci = i / ((kTileH + 2) * 34);
-            const int rem = i - ci * (kTileH + 2) * 34;
-            const int py = rem / 34, px = rem - py * 34;
-            const int iy = y0 - 1 + py, ix = x0 - 1 + px;
-            float v = 0.0f;
-            if (iy >= 0 && iy < h && ix >= 0 && ix < wd) v = __ldg(img + ((size_t)(n * 3 + ci) * h + iy) * wd + ix);
-            s_patch[ci][py][px] = v;
+        const int y0 = ty * kTileH, x0 = tx * kTileW;
+        const float* base = img + (size_t)n * 3 * h * wd + (size_t)y0 * wd + x0;
+#pragma unroll
+        for (int q = 0; q < kPerThread; ++q) {
+            const int iy = y0 + p_y[q], ix = x0 + p_x[q];
+            regs[q] = (iy >= 0 && iy < h && ix >= 0 && ix < wd) ? __ldg(base + p_off[q]) : 0.0f;
         }
+    };
+    // epilogue of the tile whose accumulator sits in TMEM stage `buf`: this thread's pixel, 32 channels
+    auto epilogue = [&](int buf, int tile) {
+        const int n = tile / tiles_per_image;
+        const int r = tile - n * tiles_per_image;
+        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        mbar_wait(&s_bar[buf], phase[buf]);
+        phase[buf] ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t acc[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
+              "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]), "=r"(acc[15]),
+              "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]), "=r"(acc[20]), "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]),
+              "=r"(acc[24]), "=r"(acc[25]), "=r"(acc[26]), "=r"(acc[27]), "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
+            : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 32)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        __half* o = out + ((size_t)(n * rows + ty * kTileH + warp) * wd + tx * kTileW + lane) * kCout;
+#pragma unroll
+        for (int i = 0; i < 32; i += 16) {
+            uint32_t wv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float a = __uint_as_float(acc[i + 2 * q]) + s_bias[i + 2 * q];
+                float b = __uint_as_float(acc[i + 2 * q + 1]) + s_bias[i + 2 * q + 1];
+                a = fmaxf(a, 0.1f * a);                        // LeakyReLU(0.1)
+                b = fmaxf(b, 0.1f * b);
+                const __half2 hv = __floats2half2_rn(a, b);
+                wv[q] = *reinterpret_cast<const uint32_t*>(&hv);
+            }
+            st_global_256(o + i, wv);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+
+    float pre[kPerThread];
+    if ((int)blockIdx.x < itotal) fetch((int)blockIdx.x, pre);
+    int buf = 0;
+    int prev = -1;
+    // software pipeline: the MMA of tile i is in flight while the epilogue of tile i-1 runs
+    for (int tile = blockIdx.x; tile < itotal; tile += gridDim.x) {
+        // 1. stage the prefetched patch, start the next tile's loads
+#pragma unroll
+        for (int q = 0; q < kPerThread; ++q)
+            if (tid + q * 128 < kPatchElems) (&s_patch[0][0][0])[p_s[q]] = pre[q];
+        if (tile + (int)gridDim.x < itotal) fetch(tile + (int)gridDim.x, pre);
         __syncthreads();
-        // 2. im2col row of pixel (y0 + warp, x0 + lane): k = (ky*3 + kx)*3 + ci
+        // 2. im2col row of pixel (y0 + warp, x0 + lane): k = (ky*3 + kx)*3 + ci.  s_a[buf] was last read by the MMA of
+        //    tile i-2, whose completion every thread observed in the epilogue of tile i-2.
         {
             float v[32];
 #pragma unroll
@@ -129,61 +195,38 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
                 __half2* hq = reinterpret_cast<__half2*>(&q);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) hq[e] = __floats2half2_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(s_a + swz64(tid, c)) = q;
+                *reinterpret_cast<uint4*>(s_a[buf] + swz64(tid, c)) = q;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
-        __syncthreads();
-        // 3. D[128 x 32] = A[128 x 32] * B^T
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();                                   // also: TMEM stage `buf` was drained by every thread (epilogue i-2)
+        // 3. D[128 x 32] = A[128 x 32] * B^T into TMEM stage `buf`
         if (warp == 0) {
             if (elect_one()) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t adesc = kmajor_desc_64b(smem_u32(s_a[buf]));
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const uint32_t acc = k;
                     asm volatile(
                         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem), "l"(adesc + (uint64_t)(2 * k)), "l"(bdesc + (uint64_t)(2 * k)), "r"(idesc), "r"(acc) : "memory");
+                        ::"r"(tmem + (uint32_t)(buf * 32)), "l"(adesc + (uint64_t)(2 * k)), "l"(bdesc + (uint64_t)(2 * k)), "r"(idesc), "r"(acc) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar)) : "memory");
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[buf])) : "memory");
             }
             __syncwarp();
         }
-        mbar_wait(&s_bar, phase);
-        phase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // 4. epilogue: this thread's pixel, 32 channels
-        uint32_t acc[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(acc[0]), "=r"(acc[1]), "=r"(acc[2]), "=r"(acc[3]), "=r"(acc[4]), "=r"(acc[5]), "=r"(acc[6]), "=r"(acc[7]),
-              "=r"(acc[8]), "=r"(acc[9]), "=r"(acc[10]), "=r"(acc[11]), "=r"(acc[12]), "=r"(acc[13]), "=r"(acc[14]), "=r"(acc[15]),
-              "=r"(acc[16]), "=r"(acc[17]), "=r"(acc[18]), "=r"(acc[19]), "=r"(acc[20]), "=r"(acc[21]), "=r"(acc[22]), "=r"(acc[23]),
-              "=r"(acc[24]), "=r"(acc[25]), "=r"(acc[26]), "=r"(acc[27]), "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
-            : "r"(tmem + ((uint32_t)(warp * 32) << 16)));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        __half* o = out + ((size_t)(n * rows + y0 + warp) * wd + x0 + lane) * kCout;
-#pragma unroll
-        for (int i = 0; i < 32; i += 16) {
-            uint32_t wv[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float a = __uint_as_float(acc[i + 2 * q]) + s_bias[i + 2 * q];
-                float b = __uint_as_float(acc[i + 2 * q + 1]) + s_bias[i + 2 * q + 1];
-                a = a > 0.0f ? a : 0.1f * a;
-                b = b > 0.0f ? b : 0.1f * b;
-                const __half2 hv = __floats2half2_rn(a, b);
-                wv[q] = *reinterpret_cast<const uint32_t*>(&hv);
-            }
-            st_global_256(o + i, wv);
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                                   // TMEM rows drained and s_a / s_patch free for the next tile
+        // 4. epilogue of the previous tile while this tile's MMA runs
+        if (prev >= 0) epilogue(buf ^ 1, prev);
+        prev = tile;
+        buf ^= 1;
     }
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+    if (prev >= 0) epilogue(buf ^ 1, prev);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
 }
 
 }  // namespace
@@ -197,9 +240,9 @@ int32_t stem_tc_run(const float* image, const float* weights, const float* bias,
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long grid = (long long)sms * 8;
+    long long grid = (long long)sms * 5;               // one resident wave (96 registers x 128 threads -> 5 CTAs per SM)
     if (grid > tiles) grid = tiles;
-    stem_tc_kernel<<<(int)grid, 128, 0, stream>>>(image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows);
+    OM_CUDA_TRY(launch_pdl(stem_tc_kernel, dim3((unsigned)grid), dim3(128), 0, stream, image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows));
     return check_launch("stem_tc_kernel");
 }
 

@@ -26,7 +26,7 @@
 
 namespace {
 
-constexpr int kThreads = 224;            // 7 warps
+constexpr int kThreads = 352;            // 11 warps: producer, MMA, addend producer, 2 x 4 epilogue
 constexpr int kEpiWarp0 = 3;
 constexpr int kBlockM = 128;             // pixels per CTA tile (UMMA M = 256 per pair)
 constexpr int kMaxStages = 8;
@@ -49,7 +49,10 @@ struct Tc2Params {
     uint32_t idesc;
     // epilogue
     int out_h, out_w, out_rows, total_rows;
-    int cout, leaky, out_kind, up_rows, has_res;
+    int cout, leaky, out_kind, up_rows;
+    int has_res;                         // epilogue addend staged by TMA: 0 none, 1 residual (fp16, same resolution, after the
+                                         // activation), 2 up-add (fp32 half-resolution partial sum, before bias and activation)
+    int up_bw, up_bh;                    // up-add box: tw/2 + 1 by th/2 + 1 source pixels (covers odd tile origins)
     int chunk_cols;                      // accumulator columns per staged chunk (64 fp16 / 32 fp32 / 32 narrow fp16)
     int row_bytes;                       // bytes per staged row (128 or 64)
     int cout_stride;
@@ -220,7 +223,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     uint64_t* h_full = bars + 2 * kMaxStages;          // [h_stages]
     uint64_t* h_empty = bars + 3 * kMaxStages;         // [h_stages]
     uint64_t* tmem_full = bars + 4 * kMaxStages;       // [2]
-    uint64_t* tmem_empty = tmem_full + 2;              // [2]        (leader's copy: 8 warp arrivals from both CTAs)
+    uint64_t* tmem_empty = tmem_full + 2;              // [2]        (leader's copy: 16 warp arrivals from both CTAs)
     uint64_t* res_full = tmem_empty + 2;               // [2]
     uint64_t* res_empty = res_full + 2;                // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
@@ -239,7 +242,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
         for (int i = 0; i < p.stages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         for (int i = 0; i < p.h_stages; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8);
+            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 16);
             mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -255,6 +258,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     cluster_sync();                                    // peer barriers are initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                        // everything above overlapped the previous layer's tail
 
     // The K loop of a tile is the sequence of (tap, 64-channel chunk) blocks, tap-major.  A pipeline stage holds
     // n_sub consecutive blocks behind ONE full/empty barrier pair, so the single MMA-issuing thread pays one wait
@@ -375,10 +379,11 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             // ===== residual producer: the 64-channel chunks of this CTA's output tile, in epilogue order =====
             int rb = 0; uint32_t rphase = 0;
             const int n_chunks = p.block_n / p.chunk_cols;
-            const uint32_t bytes = (uint32_t)(p.tw * p.th * p.row_bytes);
+            const uint32_t bytes = p.has_res == 1 ? (uint32_t)(p.tw * p.th * p.row_bytes) : (uint32_t)(p.up_bw * p.up_bh * 128);
             for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
                 const PairCoord t = decode_pair(p, pair);
-                const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
+                int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
+                if (p.has_res == 2) { x0 >>= 1; y0 >>= 1; }          // half-resolution source of the nearest x2 up-sampling
                 for (int j = 0; j < n_chunks; ++j) {
                     mbar_wait(&res_empty[rb], rphase ^ 1);
                     if (elect_one()) {
@@ -391,14 +396,19 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             }
         }
     } else {
-        // ===== epilogue: 4 warps, TMEM lane quadrant = warp % 4 =====
+        // ===== epilogue: 2 groups of 4 warps (TMEM lane quadrant = warp % 4).  The 32/64-column chunks of the
+        // accumulator alternate between the two groups (chunk g of this CTA's chunk sequence -> group g & 1, which
+        // is also the addend staging buffer it reads), so two chunks are always in flight: the narrow-K layers are
+        // bounded by how fast the epilogue drains TMEM and stores, not by the tensor pipe. =====
         const int quad = warp & 3;
+        const int half = (warp - kEpiWarp0) >> 2;
         const int m = quad * 32 + lane;                     // accumulator row = pixel inside the tile
         const uint32_t leader_tmem_empty0 = mapa(smem_u32(&tmem_empty[0]), 0);
         const int n_chunks = p.block_n / p.chunk_cols;
         const int my = m / p.tw, mx = m - my * p.tw;
         int as = 0; uint32_t aphase = 0;
-        int rb = 0; uint32_t rphase = 0;
+        const int rb = half; uint32_t rphase = 0;           // this group's staging buffer and its phase
+        int g0 = 0;                                          // chunk sequence number of the tile's first chunk (mod 2)
         for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
             const PairCoord t = decode_pair(p, pair);
             const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
@@ -411,14 +421,21 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
             const size_t pix = (size_t)Y * p.out_w + x;
             const float* up = nullptr;
-            if (p.upadd != nullptr && valid)
+            if (p.upadd != nullptr && p.has_res != 2 && valid)     // fallback: geometry the TMA box cannot express
                 up = p.upadd + ((size_t)(img * p.up_rows + (y >> 1)) * (p.out_w >> 1) + (x >> 1)) * p.cout;
-            for (int j = 0; j < n_chunks; ++j) {
+            const int up_row = ((Y >> 1) - (y0 >> 1)) * p.up_bw + ((x >> 1) - (x0 >> 1));   // source pixel inside the staged box
+            const int j_first = (g0 ^ half) & 1;             // this group's chunks: j_first, j_first + 2, ...
+            if (j_first >= n_chunks) {                        // nothing for this group in this tile: release at once
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t)(as * 8));
+            }
+            for (int j = j_first; j < n_chunks; j += 2) {
                 if (p.has_res) mbar_wait(&res_full[rb], rphase);
                 for (int c0 = 0; c0 < p.chunk_cols; c0 += 32) {
                     uint32_t v[32];
                     tmem_ld32(taddr + (uint32_t)(j * p.chunk_cols + c0), v);
-                    if (j == n_chunks - 1 && c0 + 32 >= p.chunk_cols) {     // accumulator fully drained -> release it
+                    if (j + 2 >= n_chunks && c0 + 32 >= p.chunk_cols) {     // this group's part of the accumulator is drained
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t)(as * 8));
@@ -427,7 +444,16 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    if (up != nullptr) {
+                    if (p.has_res == 2) {
+                        const uint8_t* ubuf = res_buf + rb * kStageBytes;
+                        if (m < p.tw * p.th) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                const float4 u = *reinterpret_cast<const float4*>(ubuf + swz(up_row, i >> 2, 128));
+                                f[i] += u.x; f[i + 1] += u.y; f[i + 2] += u.z; f[i + 3] += u.w;
+                            }
+                        }
+                    } else if (up != nullptr) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 u = __ldg(reinterpret_cast<const float4*>(up + cg + i));
@@ -444,7 +470,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                         for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.0f ? f[i] : 0.1f * f[i];
                     }
                     if (p.out_kind == OM_OUT_ACT) {
-                        if (p.has_res) {
+                        if (p.has_res == 1) {
                             const uint8_t* rbuf = res_buf + rb * kStageBytes;
                             const int cbase = c0 >> 3;               // first 16-byte chunk of this group inside the staged row
 #pragma unroll
@@ -493,9 +519,10 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 if (p.has_res) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&res_empty[rb]);
-                    rb ^= 1; if (rb == 0) rphase ^= 1;
+                    rphase ^= 1;
                 }
             }
+            g0 = (g0 + n_chunks) & 1;
             as ^= 1; if (as == 0) aphase ^= 1;
         }
     }
@@ -598,8 +625,11 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     const int tiles_y = (p.total_rows + p.th - 1) / p.th;
     p.pairs_y = (tiles_y + 1) / 2;
     p.taps = d.ksize * d.ksize; p.stride = d.stride; p.k_chunks = d.cin / bk;
-    p.has_res = d.residual != nullptr;
-    if (d.out_kind == OM_OUT_ACT) { p.chunk_cols = bn >= 64 ? 64 : 32; p.row_bytes = p.chunk_cols * 2; }
+    p.has_res = d.residual != nullptr ? 1 : 0;
+    p.up_bw = p.tw / 2 + 1; p.up_bh = p.th / 2 + 1;
+    if (d.upadd != nullptr && !p.has_res && d.up_rows * 2 == d.out_rows && d.cout % 32 == 0 && p.up_bw * p.up_bh <= kStageRows)
+        p.has_res = 2;
+    if (d.out_kind == OM_OUT_ACT && p.has_res != 2) { p.chunk_cols = bn >= (p.has_res ? 64 : 128) ? 64 : 32; p.row_bytes = p.chunk_cols * 2; }
     else { p.chunk_cols = 32; p.row_bytes = 128; }
     if (bn % p.chunk_cols) { delete plan; return fail(OM_ERR_INVALID, "tile width %d is not a multiple of the staged chunk", bn); }
     p.a_box_pixels = p.halo ? (p.tw + 2) * (p.th + 2) : p.tw * p.th;
@@ -667,7 +697,13 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.half_n};
         rc = encode(&plan->map_b, f16, d.weights, 2, dims, str, box, bk * 2);
     }
-    if (rc == OM_OK && p.has_res) {
+    if (rc == OM_OK && p.has_res == 2) {
+        cuuint64_t dims[3] = {(cuuint64_t)d.cout, (cuuint64_t)d.out_w / 2, (cuuint64_t)d.batch * d.up_rows};
+        cuuint64_t str[2] = {(cuuint64_t)d.cout * 4, (cuuint64_t)(d.out_w / 2) * d.cout * 4};
+        cuuint32_t box[3] = {32u, (cuuint32_t)p.up_bw, (cuuint32_t)p.up_bh};
+        rc = encode(&plan->map_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.upadd, 3, dims, str, box, 128);
+    }
+    if (rc == OM_OK && p.has_res == 1) {
         cuuint64_t dims[3] = {(cuuint64_t)d.cout, (cuuint64_t)d.out_w, (cuuint64_t)d.batch * d.out_rows};
         cuuint64_t str[2] = {(cuuint64_t)d.cout_stride * esz, (cuuint64_t)d.out_w * d.cout_stride * esz};
         cuuint32_t box[3] = {(cuuint32_t)p.chunk_cols, (cuuint32_t)p.tw, (cuuint32_t)p.th};
@@ -694,11 +730,9 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
 int32_t tc2_plan_run(const void* vp, cudaStream_t stream) {
     const Tc2Plan* plan = reinterpret_cast<const Tc2Plan*>(vp);
     if (plan->bk == 64)
-        conv_tc2_kernel<64><<<plan->grid, kThreads, plan->smem, stream>>>(plan->maps,
-                                                                          plan->map_b, plan->map_res, plan->p);
+        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<64>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, plan->p));
     else
-        conv_tc2_kernel<32><<<plan->grid, kThreads, plan->smem, stream>>>(plan->maps,
-                                                                          plan->map_b, plan->map_res, plan->p);
+        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<32>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, plan->p));
     return check_launch("conv_tc2_kernel");
 }
 

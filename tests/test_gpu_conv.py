@@ -64,3 +64,15 @@ def test_tcgen05_engine(case):
     tol = 2e-3 if kind != ACT else 1e-2           # fp16 output rounding for activation outputs
     err = float((got - ref).abs().max())
     assert torch.allclose(got, ref, atol=tol, rtol=4e-3), err
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c[9]] + [(2, 128, 128, 24, 16, 1, 1, ACT, False, True), (1, 64, 256, 14, 34, 1, 1, PARTIAL, False, True)])
+def test_tcgen05_engine_upadd_staged_by_tma(case):
+    """rows_per_image(out) == 2 * rows_per_image(partial): the up-add source tile is staged by TMA (model geometry)."""
+    B, cin, cout, H, W, k, stride, kind, _, _ = case
+    x, w, b, res, up = _data(case, seed=3)
+    leaky = kind == ACT
+    got = run_engine_conv(x, w, b, stride, leaky, kind, res, up, precision=F16, extra_rows=2)
+    ref = torch_conv_ref(x, w, b, stride, leaky, kind, res, up, quantize=True)
+    tol = 2e-3 if kind != ACT else 1e-2
+    assert torch.allclose(got, ref, atol=tol, rtol=4e-3), float((got - ref).abs().max())

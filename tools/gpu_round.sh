@@ -30,3 +30,10 @@ if [[ $what == *full* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:mask_kernel -c 1 -f -o gpurun_out/prof_mask \
       python tools/profile_step.py --steps 2 > gpurun_out/ncu_full_mask.log 2>&1; echo "ncu full mask exit $?"
 fi
+if [[ $what == *abtest* ]]; then
+  # A/B of an environment switch: AB_VAR=name AB_VALUES="0 1"
+  for v in ${AB_VALUES:-0 1}; do
+    env ${AB_VAR:-ORIENMASK_B200_PDL}=$v timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_$v.log 2>&1
+    echo "${AB_VAR:-ORIENMASK_B200_PDL}=$v: $(python -c "import json,sys; d=json.loads(open('gpurun_out/bench_ab_$v.log').read().strip().splitlines()[-1]); print(round(d['value'],1), 'img/s', round(d['ms_per_step'],3), 'ms', d['roofline']['kernel'][-40:])" 2>&1 | tail -1)"
+  done
+fi
