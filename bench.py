@@ -49,6 +49,17 @@ def measured_peaks():
     return dict(tflops=1400.0, hbm=6650.0, source='fallback of B200_PROFILING.md (1.4 PFLOP/s sustained, 6.65 TB/s)')
 
 
+def measured_traffic():
+    """DRAM bytes (read + write) of the conv-engine launches of one bs-32 step from the committed ncu pass
+    (tools/traffic_report.py -> profiles/r01_traffic.json); None when no capture is committed."""
+    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
+    try:
+        f = json.load(open(path))['conv_engine']
+        return {'bytes': f['dram_read'] + f['dram_write'], 'launches': f['launches']}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -255,6 +266,7 @@ def main():
         peaks = measured_peaks()
         value = world * B * args.steps / (total_ms * 1e-3)
         achieved = B * GFLOP_PER_IMAGE / fwd_ms          # GFLOP / ms == TFLOP/s
+        traffic = measured_traffic() if B == BATCH else None
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -270,9 +282,12 @@ def main():
             'gpu_launches': launches,
             'clocks': clocks,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                         'frac': achieved / peaks['tflops'], 'traffic': None,
-                         'kernel': 'conv engine (conv_tc_kernel launches + stem) = the model forward, %.3f ms of %.3f ms per step'
-                                   % (fwd_ms, total_ms / args.steps),
+                         'frac': achieved / peaks['tflops'], 'traffic': traffic['bytes'] if traffic else None,
+                         'traffic_note': ('ncu dram__bytes_read+write summed over the %d conv-engine launches of one step '
+                                          '(profiles/r01_traffic.json); algorithmic HBM bytes of the same launches: see profiles/r01_layers_*.md'
+                                          % traffic['launches']) if traffic else None,
+                         'kernel': 'conv engine = the model forward: 94 conv_tc2_kernel launches (tcgen05 cta_group::2) + stem_tc_kernel, '
+                                   '%.3f ms of %.3f ms per step' % (fwd_ms, total_ms / args.steps),
                          'algorithmic': '%.3f GFLOP/image x %d images per forward' % (GFLOP_PER_IMAGE, B),
                          'peak_source': peaks['source']},
         }

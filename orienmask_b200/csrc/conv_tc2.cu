@@ -26,12 +26,14 @@
 
 namespace {
 
-constexpr int kThreads = 352;            // 11 warps: producer, MMA, addend producer, 2 x 4 epilogue
+constexpr int kEpiGroups = 4;             // epilogue groups of 4 warps (power of two)
+constexpr int kThreads = (3 + 4 * kEpiGroups) * 32;   // producer, MMA, addend producer, kEpiGroups x 4 epilogue warps
 constexpr int kEpiWarp0 = 3;
 constexpr int kBlockM = 128;             // pixels per CTA tile (UMMA M = 256 per pair)
 constexpr int kMaxStages = 8;
 constexpr int kStageRows = 128;          // staging tile rows
 constexpr int kStageBytes = kStageRows * 128;
+constexpr int kMaxResBufs = 2 * kEpiGroups;   // addend staging buffers: one lane per epilogue group, up to 2 deep
 
 struct Tc2Params {
     int tiles_x, pairs_y, tiles_n;       // pair grid; linear pair id = (py * tiles_x + tx) * tiles_n + tn
@@ -41,17 +43,21 @@ struct Tc2Params {
     int block_n, half_n;                 // UMMA N and the rows of it each CTA stages
     int cout_pad;
     int halo;                            // 3x3 stride 1 with tw == 8: one halo box per chunk feeds all nine taps
+    int b_resident;                      // halo mode, all weights of the layer fit: loaded once, no block ring at all
     int n_sub;                           // (tap, chunk) blocks per pipeline stage
     int stages;                          // depth of the block ring
     int h_stages, h_stage_bytes, h_chunk_bytes;   // halo ring (halo mode): one stage = the halos of all chunks of a tile
     int a_box_pixels;                    // pixels per activation TMA box
     int tmem_cols;
+    int acc_stages;                      // accumulator stages in TMEM (2..4): narrow tiles let the MMA run further ahead of the epilogue
     uint32_t idesc;
     // epilogue
     int out_h, out_w, out_rows, total_rows;
     int cout, leaky, out_kind, up_rows;
     int has_res;                         // epilogue addend staged by TMA: 0 none, 1 residual (fp16, same resolution, after the
                                          // activation), 2 up-add (fp32 half-resolution partial sum, before bias and activation)
+    int res_depth;                       // addend staging slots per epilogue group (1..2)
+    int res_buf_bytes;                   // one staged 32-column chunk: 128 rows x 64 B (fp16 residual) or x 128 B (fp32 up-add)
     int up_bw, up_bh;                    // up-add box: tw/2 + 1 by th/2 + 1 source pixels (covers odd tile origins)
     int chunk_cols;                      // accumulator columns per staged chunk (64 fp16 / 32 fp32 / 32 narrow fp16)
     int row_bytes;                       // bytes per staged row (128 or 64)
@@ -203,6 +209,154 @@ __device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
     return t;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue.  kEpiGroups groups of 4 warps (TMEM lane quadrant = warp % 4); the 32-column chunks of the accumulators
+// are dealt round-robin to the groups over this CTA's whole chunk sequence (chunk g -> group g % kEpiGroups, which is
+// also the addend staging lane it reads), so kEpiGroups chunks are in flight.  The memory-bound layers are bounded
+// by how fast TMEM is drained, transformed and stored: with one warp per scheduler the dependent-issue latency of
+// the ~250 instructions per 32 columns was the limit (ncu: epilogue warps busy, tensor pipe 18 % active), hence
+// four warps per scheduler and one specialised instance per (output kind, addend kind).
+//   KIND: 0 fp16 NHWC activation, 1 fp32 NHWC (partial sums), 2 fp32 NCHW (heads)
+//   ADD : 0 none, 1 residual (fp16 chunk staged by TMA, added after the activation), 2 up-add (fp32 half-resolution
+//         chunk staged by TMA, added before bias and activation)
+// ---------------------------------------------------------------------------------------------------------------
+struct EpiCtx {
+    uint32_t tmem_base, leader_tmem_empty0, rank;
+    uint64_t* tmem_full; uint64_t* res_full; uint64_t* res_empty;
+    const uint8_t* res_buf; const float* s_bias;
+    int warp, lane, first_pair, pair_step, num_pairs;
+};
+
+template <int KIND, int ADD>
+__device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& c) {
+    const int quad = c.warp & 3;
+    const int grp = (c.warp - kEpiWarp0) >> 2;
+    const int m = quad * 32 + c.lane;                   // accumulator row = pixel inside the tile
+    const int n_chunks = p.block_n / p.chunk_cols;
+    const int my = m / p.tw, mx = m - my * p.tw;
+    const bool in_tile = m < p.tw * p.th;
+    int as = 0; uint32_t aphase = 0;
+    int rslot = 0; uint32_t rphase = 0;                 // this group's addend slot and its phase
+    int g0 = 0;                                          // sequence number (mod kEpiGroups) of the tile's first chunk
+    for (int pair = c.first_pair; pair < c.num_pairs; pair += c.pair_step) {
+        const PairCoord t = decode_pair(p, pair);
+        const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)c.rank) * p.th;
+        const int Y = y0 + my, x = x0 + mx;
+        const int img = Y / p.out_rows, y = Y - img * p.out_rows;
+        const bool valid = in_tile && (Y < p.total_rows) && (y < p.out_h) && (x < p.out_w);
+        const int n0 = t.tn * p.block_n;
+        mbar_wait(&c.tmem_full[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = c.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
+        const size_t pix = (size_t)Y * p.out_w + x;
+        const float* up = nullptr;                       // fallback up-add straight from global (geometry TMA cannot box)
+        if (ADD == 0 && KIND != 2 && p.upadd != nullptr && valid)
+            up = p.upadd + ((size_t)(img * p.up_rows + (y >> 1)) * (p.out_w >> 1) + (x >> 1)) * p.cout;
+        const int up_row = ((Y >> 1) - (y0 >> 1)) * p.up_bw + ((x >> 1) - (x0 >> 1));   // source pixel inside the staged box
+        const int j_first = (grp - g0) & (kEpiGroups - 1);
+        if (j_first >= n_chunks) {                        // nothing for this group in this tile: release at once
+            tc_fence_before();
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive_cluster(c.leader_tmem_empty0 + (uint32_t)(as * 8));
+        }
+        for (int j = j_first; j < n_chunks; j += kEpiGroups) {
+            const int rb = grp + kEpiGroups * rslot;
+            if (ADD != 0) mbar_wait(&c.res_full[rb], rphase);
+            for (int c0 = 0; c0 < p.chunk_cols; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)(j * p.chunk_cols + c0), v);
+                if (j + kEpiGroups >= n_chunks && c0 + 32 >= p.chunk_cols) {   // this group's part of the accumulator is drained
+                    tc_fence_before();
+                    __syncwarp();
+                    if (c.lane == 0) mbar_arrive_cluster(c.leader_tmem_empty0 + (uint32_t)(as * 8));
+                }
+                const int cg = n0 + j * p.chunk_cols + c0;    // first global channel of these 32 columns
+                float f[32];
+    #pragma unroll
+                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                if (ADD == 2) {
+                    const uint8_t* ubuf = c.res_buf + rb * p.res_buf_bytes;
+                    if (in_tile) {
+    #pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 u = *reinterpret_cast<const float4*>(ubuf + swz(up_row, i >> 2, 128));
+                            f[i] += u.x; f[i + 1] += u.y; f[i + 2] += u.z; f[i + 3] += u.w;
+                        }
+                    }
+                } else if (up != nullptr) {
+    #pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 u = __ldg(reinterpret_cast<const float4*>(up + cg + i));
+                        f[i] += u.x; f[i + 1] += u.y; f[i + 2] += u.z; f[i + 3] += u.w;
+                    }
+                }
+    #pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 bv = *reinterpret_cast<const float4*>(c.s_bias + cg + i);     // warp-uniform: smem broadcast
+                    f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+                }
+                if (p.leaky) {
+    #pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.1f * f[i]);           // LeakyReLU(0.1)
+                }
+                if (KIND == 0) {
+                    if (ADD == 1) {
+                        const uint8_t* rbuf = c.res_buf + rb * p.res_buf_bytes;
+    #pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            const uint4 rv = *reinterpret_cast<const uint4*>(rbuf + swz(m, (c0 >> 3) + (i >> 3), p.row_bytes));
+                            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+    #pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const float2 rf = __half22float2(rh[q]);
+                                f[i + 2 * q] += rf.x; f[i + 2 * q + 1] += rf.y;
+                            }
+                        }
+                    }
+                    if (valid) {
+                        __half* o = reinterpret_cast<__half*>(p.output) + pix * p.cout_stride + cg;
+    #pragma unroll
+                        for (int i = 0; i < 32; i += 16) {       // 2 x 32-byte stores: every store fills whole sectors
+                            uint32_t w[8];
+    #pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const __half2 h = __floats2half2_rn(f[i + 2 * q], f[i + 2 * q + 1]);
+                                w[q] = *reinterpret_cast<const uint32_t*>(&h);
+                            }
+                            st_global_256(o + i, w);
+                        }
+                    }
+                } else if (KIND == 1) {
+                    if (valid) {
+                        float* o = reinterpret_cast<float*>(p.output) + pix * p.cout_stride + cg;
+    #pragma unroll
+                        for (int i = 0; i < 32; i += 8) {
+                            uint32_t w[8];
+    #pragma unroll
+                            for (int q = 0; q < 8; ++q) w[q] = __float_as_uint(f[i + q]);
+                            st_global_256(o + i, w);
+                        }
+                    }
+                } else if (valid) {   // fp32 NCHW [B, cout, H, W]; lanes hold consecutive pixels of a row
+                    float* o = reinterpret_cast<float*>(p.output) + ((size_t)img * p.cout * p.out_h + y) * p.out_w + x;
+                    const size_t plane = (size_t)p.out_h * p.out_w;
+    #pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (cg + i < p.cout) o[(size_t)(cg + i) * plane] = f[i];
+                }
+            }
+            if (ADD != 0) {
+                __syncwarp();
+                if (c.lane == 0) mbar_arrive(&c.res_empty[rb]);
+                if (++rslot == p.res_depth) { rslot = 0; rphase ^= 1; }
+            }
+        }
+        g0 = (g0 + n_chunks) & (kEpiGroups - 1);
+        if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+    }
+}
+
+
 template <int BK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CUtensorMap map_b,
@@ -217,16 +371,16 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     uint8_t* h_ring = smem;                                             // [h_stages][h_stage_bytes]   (halo mode only)
     uint8_t* s_ring = smem + (size_t)p.h_stages * p.h_stage_bytes;      // [stages][n_sub][A box | B block]
     uint8_t* res_buf = s_ring + (size_t)p.stages * stage_bytes;         // [2][kStageBytes] (has_res only)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(res_buf + (p.has_res ? 2 * kStageBytes : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(res_buf + (p.has_res ? kEpiGroups * p.res_depth * p.res_buf_bytes : 0));
     uint64_t* s_full = bars;                           // [stages]     (the leader's copies of the full barriers are the live ones)
     uint64_t* s_empty = bars + kMaxStages;             // [stages]
     uint64_t* h_full = bars + 2 * kMaxStages;          // [h_stages]
     uint64_t* h_empty = bars + 3 * kMaxStages;         // [h_stages]
-    uint64_t* tmem_full = bars + 4 * kMaxStages;       // [2]
-    uint64_t* tmem_empty = tmem_full + 2;              // [2]        (leader's copy: 16 warp arrivals from both CTAs)
-    uint64_t* res_full = tmem_empty + 2;               // [2]
-    uint64_t* res_empty = res_full + 2;                // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
+    uint64_t* tmem_full = bars + 4 * kMaxStages;       // [4]
+    uint64_t* tmem_empty = tmem_full + 4;              // [4]        (leader's copy: 16 warp arrivals from both CTAs)
+    uint64_t* res_full = tmem_empty + 4;               // [kMaxResBufs]  buffer = group + 2 * slot
+    uint64_t* res_empty = res_full + kMaxResBufs;      // [kMaxResBufs]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + kMaxResBufs);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);            // [cout_pad]; L1 is carved down to nothing here, so
                                                                         // per-use global bias loads would each pay an L2 round trip
 
@@ -234,17 +388,17 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     const uint32_t rank = cluster_rank();
     const int num_pairs = p.tiles_x * p.pairs_y * p.tiles_n;
     const int first_pair = (int)cluster_id_x(), pair_step = (int)num_clusters_x();
-    const int n_groups = p.taps * p.k_chunks / p.n_sub;                 // stages per tile
+    const int n_groups = p.b_resident ? 0 : p.taps * p.k_chunks / p.n_sub;   // stages per tile
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
         for (int i = 0; i < p.stages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
         for (int i = 0; i < p.h_stages; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 16);
-            mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 4);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8 * kEpiGroups);
         }
+        for (int i = 0; i < kMaxResBufs; ++i) { mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -276,6 +430,17 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             int hs = 0; uint32_t h_phase = 0;
             const uint32_t s_tx = 2u * (uint32_t)p.n_sub * (uint32_t)((p.halo ? 0 : p.a_box_pixels * BK * 2) + b_sub);
             const uint32_t h_tx = 2u * (uint32_t)p.k_chunks * (uint32_t)(p.a_box_pixels * BK * 2);
+            if (p.b_resident) {                               // the whole weight tensor (this CTA's half of the rows), once
+                const uint32_t lb = mapa(smem_u32(&s_full[0]), 0);
+                if (elect_one()) {
+                    if (rank == 0) mbar_expect_tx(&s_full[0], 2u * (uint32_t)(p.taps * p.k_chunks * b_sub));
+                    for (int tap = 0; tap < p.taps; ++tap)
+                        for (int kc = 0; kc < p.k_chunks; ++kc)
+                            tma_load_2d_pair(s_ring + (size_t)(tap * p.k_chunks + kc) * b_sub, &map_b, lb, kc * BK,
+                                             tap * p.cout_pad + (int)rank * p.half_n);
+                }
+                __syncwarp();
+            }
             for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
                 const PairCoord t = decode_pair(p, pair);
                 const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
@@ -323,47 +488,72 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     } else if (warp == 1) {
         if (rank == 0) {
             // ===== MMA issuer (leader CTA; whole warp runs the loop, one elected lane issues) =====
+            // The loop body is descriptor arithmetic only (64-bit adds of 16-byte units on precomputed bases): with
+            // ~50 integer instructions per (tap, chunk) block the single issuing thread, at one dependent instruction
+            // every few cycles, was slower than the MMAs of a narrow tile (N = 64: 32 cycles per MMA).
             int st = 0; uint32_t s_phase = 0;
             int hs = 0; uint32_t h_phase = 0;
             int as = 0; uint32_t aphase = 0;
-            const uint32_t pixel_bytes = BK * 2;
-            const uint32_t sbo_b = 8 * pixel_bytes;
-            const uint32_t sbo_a = p.halo ? (uint32_t)(p.tw + 2) * pixel_bytes : 8 * pixel_bytes;
+            constexpr uint32_t pixel_bytes = BK * 2;
+            constexpr uint64_t kLayout = (BK == 64) ? 2 : 4;
+            const uint64_t hi_b = ((uint64_t)((8 * pixel_bytes) >> 4) << 32) | (1ull << 16) | (1ull << 46) | (kLayout << 61);
+            const uint64_t hi_a = p.halo ? (((uint64_t)(((uint32_t)(p.tw + 2) * pixel_bytes) >> 4) << 32) | (1ull << 16) | (1ull << 46) | (kLayout << 61)) : hi_b;
             const uint32_t s_ring_addr = smem_u32(s_ring), h_ring_addr = smem_u32(h_ring);
+            const uint32_t sub16 = (uint32_t)sub_bytes >> 4, asub16 = (uint32_t)a_sub >> 4, bsub16 = (uint32_t)b_sub >> 4;
+            const uint32_t hchunk16 = (uint32_t)p.h_chunk_bytes >> 4;
+            constexpr uint32_t px16 = pixel_bytes >> 4;            // one pixel of a halo row in descriptor units
+            if (p.b_resident) mbar_wait(&s_full[0], 0);
             for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
-                uint32_t h_addr = 0;
+                uint64_t ad_tile = 0;
                 if (p.halo) {
                     mbar_wait(&h_full[hs], h_phase);
-                    h_addr = h_ring_addr + (uint32_t)(hs * p.h_stage_bytes);
+                    ad_tile = hi_a | (uint64_t)(((h_ring_addr + (uint32_t)(hs * p.h_stage_bytes)) & 0x3FFFF) >> 4);
                 }
                 tc_fence_after();
-                uint32_t accumulate = 0;
-                int tap = 0, kc = 0;
-                for (int g = 0; g < n_groups; ++g) {
-                    mbar_wait(&s_full[st], s_phase);
-                    tc_fence_after();
-                    const uint32_t sb = s_ring_addr + (uint32_t)(st * stage_bytes);
-                    for (int j = 0; j < p.n_sub; ++j) {
-                        uint32_t a_addr = sb + (uint32_t)(j * sub_bytes);
-                        if (p.halo) {
-                            const int r = tap / 3, s = tap - r * 3;
-                            a_addr = h_addr + (uint32_t)(kc * p.h_chunk_bytes) + (uint32_t)(r * (p.tw + 2) + s) * pixel_bytes;
-                        }
-                        const uint64_t adesc = make_kmajor_desc<BK>(a_addr, sbo_a);
-                        const uint64_t bdesc = make_kmajor_desc<BK>(sb + (uint32_t)(j * sub_bytes + a_sub), sbo_b);
-                        if (elect_one()) {
+                if (p.b_resident) {                       // halo + resident weights: no ring, constant offsets
+                    if (elect_one()) {
+                        uint64_t bd = hi_b | (uint64_t)((s_ring_addr & 0x3FFFF) >> 4);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; ++k)
-                                umma_f16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (k == 0) ? accumulate : 1u);
+                        for (int tap = 0; tap < 9; ++tap) {
+                            uint64_t ad = ad_tile + (uint64_t)(((tap / 3) * 10 + (tap % 3)) * px16);   // tw + 2 == 10
+                            for (int kc = 0; kc < p.k_chunks; ++kc) {
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_f16_pair(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), p.idesc, (tap | kc | k) != 0 ? 1u : 0u);
+                                ad += hchunk16; bd += bsub16;
+                            }
                         }
-                        accumulate = 1;
-                        if (++kc == p.k_chunks) { kc = 0; ++tap; }
                     }
-                    if (elect_one()) umma_commit_pair(&s_empty[st]);
                     __syncwarp();
-                    if (++st == p.stages) { st = 0; s_phase ^= 1; }
+                } else {
+                    uint32_t accumulate = 0;
+                    uint32_t tap_off16 = 0; int tap_s = 0, kc = 0;   // halo: descriptor offset of the current tap, its column, chunk
+                    for (int g = 0; g < n_groups; ++g) {
+                        mbar_wait(&s_full[st], s_phase);
+                        tc_fence_after();
+                        const uint32_t sb16 = ((s_ring_addr + (uint32_t)(st * stage_bytes)) & 0x3FFFF) >> 4;
+                        uint64_t bd = hi_b | (uint64_t)(sb16 + asub16);
+                        uint64_t ad_ring = hi_a | (uint64_t)sb16;
+                        for (int j = 0; j < p.n_sub; ++j) {
+                            const uint64_t ad = p.halo ? ad_tile + (uint64_t)(tap_off16 + (uint32_t)kc * hchunk16) : ad_ring;
+                            if (elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_f16_pair(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), p.idesc, (k == 0) ? accumulate : 1u);
+                            }
+                            accumulate = 1;
+                            bd += sub16; ad_ring += sub16;
+                            if (++kc == p.k_chunks) {       // next tap: +1 pixel, or to the start of the next halo row (+10 - 2)
+                                kc = 0;
+                                if (++tap_s == 3) { tap_s = 0; tap_off16 += 8 * px16; } else tap_off16 += px16;
+                            }
+                        }
+                        if (elect_one()) umma_commit_pair(&s_empty[st]);
+                        __syncwarp();
+                        if (++st == p.stages) { st = 0; s_phase ^= 1; }
+                    }
                 }
                 if (p.halo) {
                     if (elect_one()) umma_commit_pair(&h_empty[hs]);
@@ -371,13 +561,16 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 }
                 if (elect_one()) umma_commit_pair(&tmem_full[as]);
                 __syncwarp();
-                as ^= 1; if (as == 0) aphase ^= 1;
+                if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
         }
     } else if (warp == 2) {
         if (p.has_res) {
             // ===== residual producer: the 64-channel chunks of this CTA's output tile, in epilogue order =====
-            int rb = 0; uint32_t rphase = 0;
+            // chunk g of this CTA's chunk sequence goes to epilogue group g & 1; that group's k-th chunk (k = g >> 1)
+            // uses its slot k % res_depth, so the loads run res_depth chunks ahead of each group (the DRAM latency of
+            // the addend was the top stall of the memory-bound residual layers with a single slot)
+            int grp = 0, slot[kEpiGroups] = {}; uint32_t sphase[kEpiGroups] = {};
             const int n_chunks = p.block_n / p.chunk_cols;
             const uint32_t bytes = p.has_res == 1 ? (uint32_t)(p.tw * p.th * p.row_bytes) : (uint32_t)(p.up_bw * p.up_bh * 128);
             for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
@@ -385,146 +578,29 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
                 if (p.has_res == 2) { x0 >>= 1; y0 >>= 1; }          // half-resolution source of the nearest x2 up-sampling
                 for (int j = 0; j < n_chunks; ++j) {
-                    mbar_wait(&res_empty[rb], rphase ^ 1);
+                    const int rb = grp + kEpiGroups * slot[grp];
+                    mbar_wait(&res_empty[rb], sphase[grp] ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&res_full[rb], bytes);
-                        tma_load_3d(res_buf + rb * kStageBytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0);
+                        tma_load_3d(res_buf + rb * p.res_buf_bytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0);
                     }
                     __syncwarp();
-                    rb ^= 1; if (rb == 0) rphase ^= 1;
+                    if (++slot[grp] == p.res_depth) { slot[grp] = 0; sphase[grp] ^= 1; }
+                    grp = (grp + 1) & (kEpiGroups - 1);
                 }
             }
         }
     } else {
-        // ===== epilogue: 2 groups of 4 warps (TMEM lane quadrant = warp % 4).  The 32/64-column chunks of the
-        // accumulator alternate between the two groups (chunk g of this CTA's chunk sequence -> group g & 1, which
-        // is also the addend staging buffer it reads), so two chunks are always in flight: the narrow-K layers are
-        // bounded by how fast the epilogue drains TMEM and stores, not by the tensor pipe. =====
-        const int quad = warp & 3;
-        const int half = (warp - kEpiWarp0) >> 2;
-        const int m = quad * 32 + lane;                     // accumulator row = pixel inside the tile
-        const uint32_t leader_tmem_empty0 = mapa(smem_u32(&tmem_empty[0]), 0);
-        const int n_chunks = p.block_n / p.chunk_cols;
-        const int my = m / p.tw, mx = m - my * p.tw;
-        int as = 0; uint32_t aphase = 0;
-        const int rb = half; uint32_t rphase = 0;           // this group's staging buffer and its phase
-        int g0 = 0;                                          // chunk sequence number of the tile's first chunk (mod 2)
-        for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
-            const PairCoord t = decode_pair(p, pair);
-            const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
-            const int Y = y0 + my, x = x0 + mx;
-            const int img = Y / p.out_rows, y = Y - img * p.out_rows;
-            const bool valid = (m < p.tw * p.th) && (Y < p.total_rows) && (y < p.out_h) && (x < p.out_w);
-            const int n0 = t.tn * p.block_n;
-            mbar_wait(&tmem_full[as], aphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
-            const size_t pix = (size_t)Y * p.out_w + x;
-            const float* up = nullptr;
-            if (p.upadd != nullptr && p.has_res != 2 && valid)     // fallback: geometry the TMA box cannot express
-                up = p.upadd + ((size_t)(img * p.up_rows + (y >> 1)) * (p.out_w >> 1) + (x >> 1)) * p.cout;
-            const int up_row = ((Y >> 1) - (y0 >> 1)) * p.up_bw + ((x >> 1) - (x0 >> 1));   // source pixel inside the staged box
-            const int j_first = (g0 ^ half) & 1;             // this group's chunks: j_first, j_first + 2, ...
-            if (j_first >= n_chunks) {                        // nothing for this group in this tile: release at once
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t)(as * 8));
-            }
-            for (int j = j_first; j < n_chunks; j += 2) {
-                if (p.has_res) mbar_wait(&res_full[rb], rphase);
-                for (int c0 = 0; c0 < p.chunk_cols; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + (uint32_t)(j * p.chunk_cols + c0), v);
-                    if (j + 2 >= n_chunks && c0 + 32 >= p.chunk_cols) {     // this group's part of the accumulator is drained
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + (uint32_t)(as * 8));
-                    }
-                    const int cg = n0 + j * p.chunk_cols + c0;       // first global channel of this 32-column group
-                    float f[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-                    if (p.has_res == 2) {
-                        const uint8_t* ubuf = res_buf + rb * kStageBytes;
-                        if (m < p.tw * p.th) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                const float4 u = *reinterpret_cast<const float4*>(ubuf + swz(up_row, i >> 2, 128));
-                                f[i] += u.x; f[i + 1] += u.y; f[i + 2] += u.z; f[i + 3] += u.w;
-                            }
-                        }
-                    } else if (up != nullptr) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 u = __ldg(reinterpret_cast<const float4*>(up + cg + i));
-                            f[i] += u.x; f[i + 1] += u.y; f[i + 2] += u.z; f[i + 3] += u.w;
-                        }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        const float4 bv = *reinterpret_cast<const float4*>(s_bias + cg + i);     // warp-uniform: smem broadcast
-                        f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-                    }
-                    if (p.leaky) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = f[i] > 0.0f ? f[i] : 0.1f * f[i];
-                    }
-                    if (p.out_kind == OM_OUT_ACT) {
-                        if (p.has_res == 1) {
-                            const uint8_t* rbuf = res_buf + rb * kStageBytes;
-                            const int cbase = c0 >> 3;               // first 16-byte chunk of this group inside the staged row
-#pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                const uint4 rv = *reinterpret_cast<const uint4*>(rbuf + swz(m, cbase + (i >> 3), p.row_bytes));
-                                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const float2 rf = __half22float2(rh[q]);
-                                    f[i + 2 * q] += rf.x; f[i + 2 * q + 1] += rf.y;
-                                }
-                            }
-                        }
-                        if (valid) {
-                            __half* o = reinterpret_cast<__half*>(p.output) + pix * p.cout_stride + cg;
-#pragma unroll
-                            for (int i = 0; i < 32; i += 16) {       // 2 x 32-byte stores: every store fills whole sectors
-                                uint32_t w[8];
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const __half2 h = __floats2half2_rn(f[i + 2 * q], f[i + 2 * q + 1]);
-                                    w[q] = *reinterpret_cast<const uint32_t*>(&h);
-                                }
-                                st_global_256(o + i, w);
-                            }
-                        }
-                    } else if (p.out_kind == OM_OUT_PARTIAL) {
-                        if (valid) {
-                            float* o = reinterpret_cast<float*>(p.output) + pix * p.cout_stride + cg;
-#pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                uint32_t w[8];
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) w[q] = __float_as_uint(f[i + q]);
-                                st_global_256(o + i, w);
-                            }
-                        }
-                    } else if (valid) {   // OM_OUT_NCHW: dense fp32 [B, cout, H, W]; lanes hold consecutive pixels of a row
-                        float* o = reinterpret_cast<float*>(p.output) + ((size_t)img * p.cout * p.out_h + y) * p.out_w + x;
-                        const size_t plane = (size_t)p.out_h * p.out_w;
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (cg + i < p.cout) o[(size_t)(cg + i) * plane] = f[i];
-                    }
-                }
-                if (p.has_res) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&res_empty[rb]);
-                    rphase ^= 1;
-                }
-            }
-            g0 = (g0 + n_chunks) & 1;
-            as ^= 1; if (as == 0) aphase ^= 1;
-        }
+        EpiCtx c;
+        c.tmem_base = tmem_base; c.leader_tmem_empty0 = mapa(smem_u32(&tmem_empty[0]), 0); c.rank = rank;
+        c.tmem_full = tmem_full; c.res_full = res_full; c.res_empty = res_empty;
+        c.res_buf = res_buf; c.s_bias = s_bias;
+        c.warp = warp; c.lane = lane; c.first_pair = first_pair; c.pair_step = pair_step; c.num_pairs = num_pairs;
+        if (p.out_kind == OM_OUT_NCHW) epilogue_loop<2, 0>(p, c);
+        else if (p.out_kind == OM_OUT_PARTIAL) { if (p.has_res == 2) epilogue_loop<1, 2>(p, c); else epilogue_loop<1, 0>(p, c); }
+        else if (p.has_res == 1) epilogue_loop<0, 1>(p, c);
+        else if (p.has_res == 2) epilogue_loop<0, 2>(p, c);
+        else epilogue_loop<0, 0>(p, c);
     }
 
     tc_fence_before();
@@ -629,17 +705,37 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     p.up_bw = p.tw / 2 + 1; p.up_bh = p.th / 2 + 1;
     if (d.upadd != nullptr && !p.has_res && d.up_rows * 2 == d.out_rows && d.cout % 32 == 0 && p.up_bw * p.up_bh <= kStageRows)
         p.has_res = 2;
-    if (d.out_kind == OM_OUT_ACT && p.has_res != 2) { p.chunk_cols = bn >= (p.has_res ? 64 : 128) ? 64 : 32; p.row_bytes = p.chunk_cols * 2; }
-    else { p.chunk_cols = 32; p.row_bytes = 128; }
-    if (bn % p.chunk_cols) { delete plan; return fail(OM_ERR_INVALID, "tile width %d is not a multiple of the staged chunk", bn); }
+    // staged chunk: fp16 residual 64 columns = 128-byte rows (64-byte TMA rows measured slower), everything else 32 columns
+    // (only for the memory-bound small-K layers: the tensor-bound ones would rather keep the shared memory for operand stages)
+    const int tile_cycles_est = p.taps * p.k_chunks * (bk / 16) * (bn / 2);
+    p.chunk_cols = (p.has_res == 1 && bn >= 64 && tile_cycles_est < 8192) ? 64 : 32; p.row_bytes = p.has_res == 1 ? p.chunk_cols * 2 : 128;
+    p.res_buf_bytes = kStageRows * p.row_bytes;
     p.a_box_pixels = p.halo ? (p.tw + 2) * (p.th + 2) : p.tw * p.th;
     p.h_chunk_bytes = p.halo ? ((p.a_box_pixels * bk * 2 + 1023) / 1024) * 1024 : 0;
     p.h_stage_bytes = p.h_chunk_bytes * p.k_chunks;
     p.h_stages = p.halo ? 2 : 0;
+    if (p.halo && getenv("ORIENMASK_B200_HSTAGES")) p.h_stages = atoi(getenv("ORIENMASK_B200_HSTAGES"));
     const int sub_bytes = (p.halo ? 0 : kBlockM * bk * 2) + p.half_n * bk * 2;
-    const int epi_bytes = p.has_res ? 2 * kStageBytes : 0;
+    // addend prefetch depth: memory-bound tiles (few tensor cycles per tile) need the addend several chunks ahead
+    {
+        const int tile_cycles = p.taps * p.k_chunks * (bk / 16) * (bn / 2);
+        p.res_depth = !p.has_res ? 1 : (tile_cycles < 8192 && p.res_buf_bytes <= 8192) ? 2 : 1;   // kEpiGroups chunks are in flight anyway
+        const char* rd_env = getenv("ORIENMASK_B200_RESDEPTH");
+        if (p.has_res && rd_env && atoi(rd_env) >= 1 && atoi(rd_env) <= 2) p.res_depth = atoi(rd_env);
+    }
+    const int epi_bytes = p.has_res ? kEpiGroups * p.res_depth * p.res_buf_bytes : 0;
     constexpr int kMaxSmem = 227 * 1024;
-    const int fixed = 1024 + epi_bytes + (4 * kMaxStages + 8) * 8 + 16 + cout_pad * 4;
+    const int fixed = 1024 + epi_bytes + (4 * kMaxStages + 8 + 2 * kMaxResBufs) * 8 + 16 + cout_pad * 4;
+    {
+        const int total_b = p.taps * p.k_chunks * p.half_n * bk * 2;
+        const char* br_env = getenv("ORIENMASK_B200_BRES");
+        p.b_resident = p.halo && p.tiles_n == 1 && total_b <= 96 * 1024 && !(br_env && br_env[0] == '0');
+        if (p.b_resident) {
+            int hs = (kMaxSmem - fixed - total_b) / p.h_stage_bytes;
+            p.h_stages = hs > 4 ? 4 : hs;
+            if (p.h_stages < 2) p.b_resident = 0, p.h_stages = 2;
+        }
+    }
     const int ring_budget = kMaxSmem - fixed - p.h_stages * p.h_stage_bytes;
     if (ring_budget < 2 * sub_bytes) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
     // blocks per stage: enough MMA cycles behind each barrier round trip (>= ~1024 tensor cycles; one block issues
@@ -661,9 +757,11 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
         p.stages = ring_budget / (best * sub_bytes);
         if (p.stages > kMaxStages) p.stages = kMaxStages;
         if (p.stages < 2) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
+        if (p.b_resident) { p.n_sub = total; p.stages = 1; }          // the "ring" is the resident weight tensor
     }
+    p.acc_stages = 512 / bn >= 4 ? 4 : 512 / bn;
     int cols = 32;
-    while (cols < 2 * bn) cols <<= 1;
+    while (cols < p.acc_stages * bn) cols <<= 1;
     p.tmem_cols = cols;
     // cute::UMMA::InstrDescriptor: c_format F32 (bit 4), a/b F16, K-major, N>>3 at bit 17, M>>4 at bit 24 (M = 256 per pair)
     p.idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((2 * kBlockM) >> 4) << 24);

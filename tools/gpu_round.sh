@@ -24,6 +24,11 @@ if [[ $what == *ncu* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 600 --csv --log-file gpurun_out/launches.csv \
       python tools/profile_step.py --steps 1 > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"; tail -2 gpurun_out/ncu_launches.log
 fi
+if [[ $what == *traffic* ]]; then
+  # DRAM bytes of every launch of one step (one pass, 3 metrics) -> tools/traffic_report.py -> profiles/
+  timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --profile-from-start off -c 600 --csv \
+      --log-file gpurun_out/traffic.csv python tools/profile_step.py --steps 1 > gpurun_out/ncu_traffic.log 2>&1; echo "ncu traffic exit $?"
+fi
 if [[ $what == *full* ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:${CONV_KERNEL:-conv_tc2_kernel} -s ${CONV_SKIP:-84} -c ${CONV_COUNT:-1} -f -o gpurun_out/prof_conv \
       python tools/profile_step.py --steps 2 > gpurun_out/ncu_full_conv.log 2>&1; echo "ncu full conv exit $?"
