@@ -171,6 +171,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG', 'WARN')        # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     B = args.batch
     model = ob.OrienMaskYOLOFPNPlus(3, 80)

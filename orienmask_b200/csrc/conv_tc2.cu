@@ -1,21 +1,20 @@
-// fp16 implicit-GEMM convolution on CTA pairs: tcgen05.mma.cta_group::2 (UMMA M = 256 over two SMs),
-// TMA-fed operand ring, TMA-store epilogue.
+// fp16 implicit-GEMM convolution on CTA pairs: tcgen05.mma.cta_group::2 (UMMA M = 256 over two SMs), operands
+// staged by TMA into swizzled shared memory, accumulators in TMEM, persistent warp-specialised CTAs.
 //
 //   D[pixel, cout] = sum_{tap, cin} A[pixel + tap, cin] * W[tap, cout, cin]
 //
-// Why pairs: with one CTA per 128 x 256 tile the shared-memory fill (16 KB of activations + 32 KB of
-// weights per 512 tensor-core cycles) is what bounds the 3x3 layers, not the tensor pipe (ncu:
-// profiles/r01_conv_v1_*.txt).  A CTA pair computes two vertically adjacent pixel tiles against the
-// same weight tile; each CTA stages its own activations plus HALF of the weight rows and the
-// cta_group::2 MMA reads both halves, so the fill per tensor-core cycle drops by a third and every
-// weight byte crosses the L2->SM fabric once per 256 pixels instead of once per 128.
+// Why pairs: with one CTA per 128 x 256 tile the shared-memory fill (16 KB of activations + 32 KB of weights per 512
+// tensor-core cycles) bounds the 3x3 layers, not the tensor pipe (profiles/r01_ncu_conv_v1.txt).  A CTA pair
+// computes two vertically adjacent pixel tiles against the same weight tile; each CTA stages its own activations
+// plus HALF of the weight rows and the cta_group::2 MMA reads both halves.
 //
-// Roles (7 warps / CTA): warp 0 operand producer (TMA), warp 1 TMEM allocator + MMA issuer (leader
-// CTA only issues), warp 2 residual producer (TMA), warps 3..6 epilogue.  Epilogue: TMEM -> registers
-// -> bias / up-add / LeakyReLU / residual -> 128B-swizzled staging tile -> one TMA store per 64-channel
-// chunk; padding rows of the padded-row NHWC layout are written as zeros so the layout invariant
-// (include/orienmask_b200.h) holds without masking.  Two accumulator stages in TMEM overlap the epilogue
-// of pair i with the main loop of pair i+1.
+// Roles (19 warps / CTA): warp 0 operand producer (TMA), warp 1 TMEM allocator + MMA issuer (only the leader CTA
+// issues), warp 2 addend producer (TMA: residual or up-add chunks), warps 3..18 epilogue in four groups of four.
+// Operand staging has three shapes (see the comment at the role dispatch): per-tap boxes, one halo box per chunk that
+// feeds all nine taps of a 3x3 stride-1 layer, and -- when all weights of a small layer fit -- resident weights.
+// Epilogue: TMEM -> registers -> (+ fp32 up-add) + bias -> LeakyReLU -> (+ fp16 residual) -> 32-byte global stores;
+// up to four accumulator stages in TMEM let the main loop run ahead of it.  Every launch uses programmatic dependent
+// launch: everything before pdl_wait() overlaps the previous layer's tail.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -650,7 +649,7 @@ struct Tc2Plan {
 
 // Pixel tile of <= 128 = tw x th with tw | width.  NHWC outputs: the fullest tile, discounting tiles narrower
 // than 8 pixels (their TMA boxes degenerate into many 128..512-byte rows and they share little halo in L2).
-// NCHW heads: the widest row segment among tiles that are at least 90 % full, so that the per-channel fp32
+// NCHW heads: the widest row segment among tiles that are at least 75 % full, so that the per-channel fp32
 // stores of a warp form few long runs without idling a large part of the epilogue lanes.
 int pick_tile_w(int w, bool widest) {
     int best = 1, best_score = -1;
@@ -658,7 +657,7 @@ int pick_tile_w(int w, bool widest) {
         if (w % tw) continue;
         const int fill = tw * (kBlockM / tw);
         int score;
-        if (widest) score = (fill * 10 >= kBlockM * 9) ? 1000 + tw : fill;
+        if (widest) score = (fill * 4 >= kBlockM * 3) ? 1000 + tw : fill;
         else score = fill * (tw < 8 ? tw : 8);
         if (score >= best_score) { best_score = score; best = tw; }
     }

@@ -491,15 +491,25 @@ __global__ void __launch_bounds__(256) mask_kernel(PostDev d, const int* det_cou
     const long long img_plane = (long long)d.H * d.W;
     unsigned char* mrow = mask + (long long)b * d.nms_post * img_plane + (long long)y * d.W + xb;
 
+    // pixel-centre grids of :41-43 ((x / W) * nW): they depend on the scale only, and the IEEE division is the most
+    // expensive part of a pixel, so they are rebuilt only when the scale changes between consecutive anchors
+    float bxs[16], bys = 0.f;
+    int cur_scale = -1;
     for (int a = 0; a < d.total_anchors; ++a) {
         const int i0 = a_start[a], i1 = a_start[a + 1];
         if (i0 == i1) continue;                                      // block-uniform
         const int s = d.anchor_scale[a];
+        if (s != cur_scale) {                                        // block-uniform
+            cur_scale = s;
+            bys = ((float)y / (float)d.H) * (float)d.gh[s];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bxs[i] = ((float)(xb + i) / (float)d.W) * (float)d.gw[s];
+        }
         const float* op = d.orien[s] + (long long)b * d.ostride[s] + (long long)(2 * d.anchor_slot[a]) * d.h4 * d.w4;
         // grid_anchors (:21-25): (px / W) * nW
         const float gax = (d.aw_px[a] / (float)d.W) * (float)d.gw[s];
         const float gay = (d.ah_px[a] / (float)d.H) * (float)d.gh[s];
-        const float base_y = ((float)y / (float)d.H) * (float)d.gh[s];     // :41-43
+        const float base_y = bys;
         float px[16], py[16];
 #pragma unroll
         for (int comp = 0; comp < 2; ++comp) {
@@ -518,7 +528,7 @@ __global__ void __launch_bounds__(256) mask_kernel(PostDev d, const int* det_cou
                 const float t1 = __fmaf_rn(lx0, v1[j], lx1 * v1[j + 1]);
                 const float up = __fmaf_rn(ly0, t0, ly1 * t1);
                 if (comp == 0) {
-                    const float base_x = ((float)(xb + i) / (float)d.W) * (float)d.gw[s];
+                    const float base_x = bxs[i];
                     px[i] = (up * gax) / 2.0f + base_x;              // :141-144
                 } else {
                     py[i] = (up * gay) / 2.0f + base_y;

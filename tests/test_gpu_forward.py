@@ -103,3 +103,26 @@ def test_end_to_end_fp16_runs_and_reports():
     for r in res:
         assert r['bbox'].shape[0] == r['mask'].shape[0] == r['cls'].shape[0] > 0
         assert r['mask'].shape[1:] == (544, 544)
+
+
+def test_config5_960_forward_and_post():
+    """BASELINE config 5: 960x960 (stride-4 map 240x240, grids 30/60/120).  fp16 engine drift against the oracle
+    forward on one image, and the full path at batch 2 (shapes, dtypes, non-empty results)."""
+    import orienmask_b200 as ob
+    from orienmask_b200.synthetic import synthetic_images, synthetic_state_dict
+    from oracle.forward_oracle import forward_oracle
+    x = synthetic_images(2, 960, 960, seed=3)
+    ref = forward_oracle(synthetic_state_dict(0), x[:1])
+    model = _model('fp16')
+    out = model(x.cuda())
+    assert out[0][0].shape == (2, 255, 30, 30) and out[2][0].shape == (2, 255, 120, 120) and out[0][1].shape == (2, 6, 240, 240)
+    for (gb, go), (rb, ro) in zip(out, ref):
+        for got, want in ((gb[:1], rb), (go[:1], ro)):
+            rel = float((got.float().cpu() - want).norm() / want.norm())
+            assert rel < 0.03, rel
+    post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5),
+                                       device=torch.device('cuda:0'), **post_config(960, 960, 0.005))
+    res = post(out)
+    assert len(res) == 2
+    for r in res:
+        assert r['mask'].shape[1:] == (960, 960) and r['mask'].dtype == torch.bool and r['bbox'].shape[0] > 0
