@@ -159,6 +159,12 @@ typedef struct om_conv_desc {
                                       activation at (y/2, x/2) (nearest x2 up-sampling), or NULL  */
     int32_t up_rows;
     void* output;
+    /* "Parity-split" (space-to-depth) activation layout, used between a layer and a stride-2 consumer that is its only
+     * reader: the four (row parity, column parity) sub-images are stored one after the other, each a dense padded-row
+     * NHWC tensor [B*rows/2, W/2, C]; plane index = 2*(Y&1) + (x&1), Y the row in the [B*rows] space (rows even).
+     * Every tap of the stride-2 convolution is then a dense TMA box instead of a strided gather. */
+    int32_t in_s2d;                /* the input (of a stride-2 layer) is parity-split                  */
+    int32_t out_s2d;               /* write the OM_OUT_ACT output parity-split (no residual in place)  */
 } om_conv_desc;
 
 typedef struct om_conv om_conv;
@@ -172,10 +178,10 @@ void om_conv_destroy(om_conv* conv);
  * First layer (3 -> cout, 3x3, stride 1, BN folded, LeakyReLU) straight from the caller's image.
  *   image    device fp32 NCHW [batch,3,h,w]
  *   weights  device fp32 [27][cout] (tap-major: (ky*3+kx)*3+ci), bias fp32 [cout]; cout == 32
- *   output   padded-row NHWC [batch*rows, w, cout] in `precision`
+ *   output   padded-row NHWC [batch*rows, w, cout] in `precision` (parity-split when out_s2d, see om_conv_desc)
  */
 int32_t om_stem_conv(int32_t precision, const float* image, const float* weights, const float* bias, void* output,
-                     int32_t batch, int32_t h, int32_t w, int32_t rows, int32_t cout, void* stream);
+                     int32_t batch, int32_t h, int32_t w, int32_t rows, int32_t cout, int32_t out_s2d, void* stream);
 
 #ifdef __cplusplus
 }

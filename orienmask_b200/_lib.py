@@ -36,7 +36,7 @@ class ConvDesc(ctypes.Structure):
         ('cin', c_i32), ('cout', c_i32), ('cout_stride', c_i32),
         ('ksize', c_i32), ('stride', c_i32), ('leaky', c_i32), ('out_kind', c_i32),
         ('input', c_vp), ('weights', c_vp), ('bias', c_vp), ('residual', c_vp), ('upadd', c_vp),
-        ('up_rows', c_i32), ('output', c_vp),
+        ('up_rows', c_i32), ('output', c_vp), ('in_s2d', c_i32), ('out_s2d', c_i32),
     ]
 
 
@@ -56,7 +56,7 @@ SIGNATURES = {
     'om_conv_create': (c_i32, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_vp)]),
     'om_conv_run': (c_i32, [c_vp, c_vp]),
     'om_conv_destroy': (None, [c_vp]),
-    'om_stem_conv': (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'om_stem_conv': (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
 }
 
 _lib = None

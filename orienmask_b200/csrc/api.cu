@@ -37,7 +37,7 @@ struct om_conv {
     int tc_version;      // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (ORIENMASK_B200_CONV=v1, kept for A/B measurements)
 };
 
-extern "C" int32_t om_abi_version(void) { return 1; }
+extern "C" int32_t om_abi_version(void) { return 2; }
 extern "C" const char* om_last_error(void) { return om::error_buffer(); }
 extern "C" int64_t om_launch_count(void) { return om::g_launches; }
 extern "C" void om_launch_count_reset(void) { om::g_launches = 0; }
@@ -57,6 +57,10 @@ extern "C" int32_t om_conv_create(const om_conv_desc* d, om_conv** out) {
     if (!d->input || !d->weights || !d->output) return om::fail(OM_ERR_INVALID, "om_conv_create: null tensor pointer");
     if (d->residual && d->out_kind != OM_OUT_ACT) return om::fail(OM_ERR_INVALID, "residual only with activation outputs");
     if (d->upadd && d->up_rows < 1) return om::fail(OM_ERR_INVALID, "upadd needs up_rows");
+    if (d->in_s2d && (d->stride != 2 || d->in_rows % 2 || d->in_w % 2)) return om::fail(OM_ERR_INVALID, "in_s2d needs a stride-2 layer over even rows/width");
+    if (d->out_s2d && (d->out_kind != OM_OUT_ACT || d->out_rows % 2 || d->out_w % 2 || d->cout_stride != d->cout))
+        return om::fail(OM_ERR_INVALID, "out_s2d needs a dense OM_OUT_ACT output over even rows/width");
+    if (d->out_s2d && d->residual == d->output && d->residual) return om::fail(OM_ERR_INVALID, "out_s2d cannot be written in place over the residual");
     om_conv* c = new om_conv();
     c->desc = *d;
     c->tc_plan = nullptr;

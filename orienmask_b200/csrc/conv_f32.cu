@@ -19,7 +19,7 @@ constexpr int BM = 64, BN = 64, BK = 16, APAD = 4;
 
 struct F32Params {
     int batch, in_h, in_w, in_rows, out_h, out_w, out_rows, cin, cout, cout_pad, cout_stride;
-    int ksize, stride, leaky, out_kind, up_rows;
+    int ksize, stride, leaky, out_kind, up_rows, in_s2d, out_s2d;
     const float* in; const float* w; const float* bias; const float* residual; const float* upadd;
     float* out;
 };
@@ -52,7 +52,12 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const F32Params p) {
         const int r = tap / p.ksize, s = tap - r * p.ksize;
         const int iy = aoy * p.stride + r - pad, ix = aox * p.stride + s - pad;
         const bool in_ok = a_ok && iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w;
-        const float* arow = p.in + ((size_t)(an * p.in_rows + iy) * p.in_w + ix) * p.cin + kq * 4;
+        size_t apix = (size_t)(an * p.in_rows + iy) * p.in_w + ix;
+        if (p.in_s2d) {                                    // parity-split input: plane 2*(Y&1)+(x&1), then (Y>>1, x>>1)
+            const int Yi = an * p.in_rows + iy;
+            apix = (size_t)(2 * (Yi & 1) + (ix & 1)) * ((size_t)p.batch * p.in_rows / 2 * (p.in_w / 2)) + (size_t)(Yi >> 1) * (p.in_w / 2) + (ix >> 1);
+        }
+        const float* arow = p.in + apix * p.cin + kq * 4;
         const float* brow = p.w + ((size_t)tap * p.cin + kb) * p.cout_pad + n0 + cq * 4;
         const bool b_ok = n0 + cq * 4 < p.cout_pad;
         for (int c0 = 0; c0 < p.cin; c0 += BK) {
@@ -83,6 +88,11 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const F32Params p) {
         const int rr = m - n * p.out_h * p.out_w;
         const int oy = rr / p.out_w, ox = rr - oy * p.out_w;
         const size_t pix = (size_t)(n * p.out_rows + oy) * p.out_w + ox;
+        size_t opix = pix;
+        if (p.out_s2d) {
+            const int Yo = n * p.out_rows + oy;
+            opix = (size_t)(2 * (Yo & 1) + (ox & 1)) * ((size_t)p.batch * p.out_rows / 2 * (p.out_w / 2)) + (size_t)(Yo >> 1) * (p.out_w / 2) + (ox >> 1);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = n0 + tx * 4 + j;
@@ -95,7 +105,7 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const F32Params p) {
                 p.out[((size_t)(n * p.cout + c) * p.out_h + oy) * p.out_w + ox] = v;
             } else {
                 if (p.residual) v += p.residual[pix * p.cout_stride + c];
-                p.out[pix * p.cout_stride + c] = v;
+                p.out[opix * p.cout_stride + c] = v;
             }
         }
     }
@@ -105,7 +115,7 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const F32Params p) {
 template <typename OutT, int COUT>
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                    const float* __restrict__ bias, OutT* __restrict__ out,
-                                                   int batch, int h, int wd, int rows) {
+                                                   int batch, int h, int wd, int rows, int out_s2d) {
     __shared__ float sw[27 * COUT];
     __shared__ float sb[COUT];
     for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = w[i];
@@ -137,7 +147,12 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ img
     }
 #pragma unroll
     for (int c = 0; c < COUT; ++c) acc[c] = acc[c] > 0.f ? acc[c] : 0.1f * acc[c];
-    OutT* o = out + ((size_t)(n * rows + y) * wd + x) * COUT;
+    size_t opix = (size_t)(n * rows + y) * wd + x;
+    if (out_s2d) {
+        const int Yo = n * rows + y;
+        opix = (size_t)(2 * (Yo & 1) + (x & 1)) * ((size_t)batch * rows / 2 * (wd / 2)) + (size_t)(Yo >> 1) * (wd / 2) + (x >> 1);
+    }
+    OutT* o = out + opix * COUT;
     if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
         for (int c = 0; c < COUT; c += 8) {
@@ -165,6 +180,7 @@ int32_t f32_conv_run(const om_conv_desc& d, cudaStream_t stream) {
     p.out_h = d.out_h; p.out_w = d.out_w; p.out_rows = d.out_rows; p.cin = d.cin; p.cout = d.cout;
     p.cout_pad = (d.cout + 3) / 4 * 4; p.cout_stride = d.cout_stride;
     p.ksize = d.ksize; p.stride = d.stride; p.leaky = d.leaky; p.out_kind = d.out_kind; p.up_rows = d.up_rows;
+    p.in_s2d = d.in_s2d; p.out_s2d = d.out_s2d;
     p.in = reinterpret_cast<const float*>(d.input); p.w = reinterpret_cast<const float*>(d.weights);
     p.bias = d.bias; p.residual = reinterpret_cast<const float*>(d.residual); p.upadd = d.upadd;
     p.out = reinterpret_cast<float*>(d.output);
@@ -177,20 +193,21 @@ int32_t f32_conv_run(const om_conv_desc& d, cudaStream_t stream) {
 }  // namespace om
 
 extern "C" int32_t om_stem_conv(int32_t precision, const float* image, const float* weights, const float* bias, void* output,
-                                int32_t batch, int32_t h, int32_t w, int32_t rows, int32_t cout, void* stream) {
+                                int32_t batch, int32_t h, int32_t w, int32_t rows, int32_t cout, int32_t out_s2d, void* stream) {
     if (!image || !weights || !bias || !output) return om::fail(OM_ERR_INVALID, "om_stem_conv: null argument");
     if (cout != 32) return om::fail(OM_ERR_UNSUPPORTED, "om_stem_conv: cout must be 32 (got %d)", cout);
     if (batch < 1 || h < 1 || w < 1 || rows <= h) return om::fail(OM_ERR_INVALID, "om_stem_conv: bad geometry");
+    if (out_s2d && (rows % 2 || w % 2)) return om::fail(OM_ERR_INVALID, "om_stem_conv: out_s2d needs even rows and width");
     const long long total = (long long)batch * h * w;
     const int blocks = (int)((total + 255) / 256);
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == OM_PREC_F16) {
         const char* sel = getenv("ORIENMASK_B200_STEM");
         if (!(sel && sel[0] == 'f') && h % 4 == 0 && w % 32 == 0)          // default: tensor-core stem (conv_stem_tc.cu)
-            return om::stem_tc_run(image, weights, bias, output, batch, h, w, rows, st);
-        stem_kernel<__half, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows);
+            return om::stem_tc_run(image, weights, bias, output, batch, h, w, rows, out_s2d, st);
+        stem_kernel<__half, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d);
     } else if (precision == OM_PREC_F32)
-        stem_kernel<float, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<float*>(output), batch, h, w, rows);
+        stem_kernel<float, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<float*>(output), batch, h, w, rows, out_s2d);
     else
         return om::fail(OM_ERR_INVALID, "om_stem_conv: unknown precision %d", precision);
     return om::check_launch("stem_kernel");

@@ -19,7 +19,7 @@ void tc2_plan_destroy(void* plan);
 
 // tensor-core first layer (conv_stem_tc.cu)
 int32_t stem_tc_run(const float* image, const float* weights, const float* bias, void* output, int batch, int h, int w, int rows,
-                    cudaStream_t stream);
+                    int out_s2d, cudaStream_t stream);
 
 // fp32 FFMA parity engine (conv_f32.cu)
 int32_t f32_conv_run(const om_conv_desc& d, cudaStream_t stream);

@@ -56,7 +56,7 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8])
 
 __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ img, const float* __restrict__ w27,
                                                       const float* __restrict__ bias, __half* __restrict__ out,
-                                                      int batch, int h, int wd, int rows) {
+                                                      int batch, int h, int wd, int rows, int out_s2d) {
     __shared__ __align__(1024) uint8_t s_a[2][128 * 64];     // im2col rows, K-major SWIZZLE_64B (double-buffered)
     __shared__ __align__(1024) uint8_t s_b[kCout * 64];      // weights [cout][k], same layout
     __shared__ float s_patch[3][kTileH + 2][kPatchW];
@@ -147,7 +147,11 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
               "=r"(acc[24]), "=r"(acc[25]), "=r"(acc[26]), "=r"(acc[27]), "=r"(acc[28]), "=r"(acc[29]), "=r"(acc[30]), "=r"(acc[31])
             : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 32)));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        __half* o = out + ((size_t)(n * rows + ty * kTileH + warp) * wd + tx * kTileW + lane) * kCout;
+        const int Yo = n * rows + ty * kTileH + warp, xo = tx * kTileW + lane;
+        size_t opix = (size_t)Yo * wd + xo;
+        if (out_s2d)                                       // parity-split output for the stride-2 consumer (om_conv_desc)
+            opix = (size_t)(2 * (Yo & 1) + (xo & 1)) * ((size_t)batch * rows / 2 * (wd / 2)) + (size_t)(Yo >> 1) * (wd / 2) + (xo >> 1);
+        __half* o = out + opix * kCout;
 #pragma unroll
         for (int i = 0; i < 32; i += 16) {
             uint32_t wv[8];
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
 namespace om {
 
 int32_t stem_tc_run(const float* image, const float* weights, const float* bias, void* output, int batch, int h, int w, int rows,
-                    cudaStream_t stream) {
+                    int out_s2d, cudaStream_t stream) {
     if (h % kTileH || w % kTileW) return fail(OM_ERR_INVALID, "tensor-core stem needs h %% 4 == 0 and w %% 32 == 0 (got %dx%d)", h, w);
     const long long tiles = (long long)batch * (h / kTileH) * (w / kTileW);
     int dev = 0, sms = 0;
@@ -242,7 +246,7 @@ int32_t stem_tc_run(const float* image, const float* weights, const float* bias,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)sms * 5;               // one resident wave (96 registers x 128 threads -> 5 CTAs per SM)
     if (grid > tiles) grid = tiles;
-    OM_CUDA_TRY(launch_pdl(stem_tc_kernel, dim3((unsigned)grid), dim3(128), 0, stream, image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows));
+    OM_CUDA_TRY(launch_pdl(stem_tc_kernel, dim3((unsigned)grid), dim3(128), 0, stream, image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d));
     return check_launch("stem_tc_kernel");
 }
 

@@ -61,6 +61,8 @@ struct Tc2Params {
     int chunk_cols;                      // accumulator columns per staged chunk (64 fp16 / 32 fp32 / 32 narrow fp16)
     int row_bytes;                       // bytes per staged row (128 or 64)
     int cout_stride;
+    int out_s2d;                         // write the fp16 output parity-split (see om_conv_desc)
+    long long s2d_plane;                 // pixels per parity plane of the output
     const float* bias;
     const float* upadd;
     void* output;
@@ -313,7 +315,9 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
                         }
                     }
                     if (valid) {
-                        __half* o = reinterpret_cast<__half*>(p.output) + pix * p.cout_stride + cg;
+                        size_t opix = pix;
+                        if (p.out_s2d) opix = (size_t)(2 * (Y & 1) + (x & 1)) * (size_t)p.s2d_plane + (size_t)(Y >> 1) * (p.out_w >> 1) + (x >> 1);
+                        __half* o = reinterpret_cast<__half*>(p.output) + opix * p.cout_stride + cg;
     #pragma unroll
                         for (int i = 0; i < 32; i += 16) {       // 2 x 32-byte stores: every store fills whole sectors
                             uint32_t w[8];
@@ -424,19 +428,19 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     //   tools/desc_probe.cu, profiles/r01_desc_probe.txt).
     if (warp == 0) {
         {
-            // ===== operand producer (both CTAs; whole warp runs the loop, one elected lane issues) =====
+            // ===== operand producer (both CTAs).  The whole warp runs the loop; lane j issues the TMA loads of block j of
+            // the stage, so the ~80 instructions of tap decoding / coordinate arithmetic per block run in parallel
+            // across lanes instead of serialising on one thread (which bounded the layers with small boxes). =====
             int st = 0; uint32_t s_phase = 0;
             int hs = 0; uint32_t h_phase = 0;
             const uint32_t s_tx = 2u * (uint32_t)p.n_sub * (uint32_t)((p.halo ? 0 : p.a_box_pixels * BK * 2) + b_sub);
             const uint32_t h_tx = 2u * (uint32_t)p.k_chunks * (uint32_t)(p.a_box_pixels * BK * 2);
             if (p.b_resident) {                               // the whole weight tensor (this CTA's half of the rows), once
                 const uint32_t lb = mapa(smem_u32(&s_full[0]), 0);
-                if (elect_one()) {
-                    if (rank == 0) mbar_expect_tx(&s_full[0], 2u * (uint32_t)(p.taps * p.k_chunks * b_sub));
-                    for (int tap = 0; tap < p.taps; ++tap)
-                        for (int kc = 0; kc < p.k_chunks; ++kc)
-                            tma_load_2d_pair(s_ring + (size_t)(tap * p.k_chunks + kc) * b_sub, &map_b, lb, kc * BK,
-                                             tap * p.cout_pad + (int)rank * p.half_n);
+                if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[0], 2u * (uint32_t)(p.taps * p.k_chunks * b_sub));
+                if (lane < p.taps * p.k_chunks) {
+                    const int tap = lane / p.k_chunks, kc = lane - tap * p.k_chunks;
+                    tma_load_2d_pair(s_ring + (size_t)lane * b_sub, &map_b, lb, kc * BK, tap * p.cout_pad + (int)rank * p.half_n);
                 }
                 __syncwarp();
             }
@@ -447,22 +451,20 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 if (p.halo) {
                     mbar_wait(&h_empty[hs], h_phase ^ 1);
                     const uint32_t lb = mapa(smem_u32(&h_full[hs]), 0);
-                    if (elect_one()) {
-                        if (rank == 0) mbar_expect_tx(&h_full[hs], h_tx);
-                        for (int kc = 0; kc < p.k_chunks; ++kc)
-                            tma_load_3d_pair(h_ring + (size_t)hs * p.h_stage_bytes + (size_t)kc * p.h_chunk_bytes, &map_a0, lb, kc * BK, x0 - 1, y0 - 1);
-                    }
+                    if (lane == 0 && rank == 0) mbar_expect_tx(&h_full[hs], h_tx);
+                    if (lane < p.k_chunks)
+                        tma_load_3d_pair(h_ring + (size_t)hs * p.h_stage_bytes + (size_t)lane * p.h_chunk_bytes, &map_a0, lb, lane * BK, x0 - 1, y0 - 1);
                     __syncwarp();
                     if (++hs == p.h_stages) { hs = 0; h_phase ^= 1; }
                 }
-                int tap = 0, kc = 0;
                 for (int g = 0; g < n_groups; ++g) {
                     mbar_wait(&s_empty[st], s_phase ^ 1);
                     const uint32_t lb = mapa(smem_u32(&s_full[st]), 0);
                     uint8_t* sb = s_ring + (size_t)st * stage_bytes;
-                    const bool leader_lane = elect_one();
-                    if (leader_lane && rank == 0) mbar_expect_tx(&s_full[st], s_tx);
-                    for (int j = 0; j < p.n_sub; ++j) {
+                    if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[st], s_tx);
+                    if (lane < p.n_sub) {
+                        const int i = g * p.n_sub + lane;            // (tap, chunk) block of this lane, tap-major
+                        const int tap = i / p.k_chunks, kc = i - tap * p.k_chunks;
                         if (!p.halo) {
                             int dx = 0, dy = 0, sel = 0;
                             if (p.taps == 9) {
@@ -473,11 +475,9 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                                     sel = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);   // odd row / odd column views
                                 }
                             }
-                            const CUtensorMap* ma = &maps_a.m[sel];
-                            if (leader_lane) tma_load_3d_pair(sb + (size_t)j * sub_bytes, ma, lb, kc * BK, x0 + dx, y0 + dy);
+                            tma_load_3d_pair(sb + (size_t)lane * sub_bytes, &maps_a.m[sel], lb, kc * BK, x0 + dx, y0 + dy);
                         }
-                        if (leader_lane) tma_load_2d_pair(sb + (size_t)j * sub_bytes + a_sub, &map_b, lb, kc * BK, tap * p.cout_pad + n0);
-                        if (++kc == p.k_chunks) { kc = 0; ++tap; }
+                        tma_load_2d_pair(sb + (size_t)lane * sub_bytes + a_sub, &map_b, lb, kc * BK, tap * p.cout_pad + n0);
                     }
                     __syncwarp();
                     if (++st == p.stages) { st = 0; s_phase ^= 1; }
@@ -747,7 +747,7 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
         for (int n = 1; n <= total; ++n) {
             if (total % n) continue;
             const int st = ring_budget / (n * sub_bytes);
-            if (st < 3 && n > 1) break;
+            if (st < 3 && n > 1 && !(n == total && st >= 2)) break;   // a whole tile per stage may run double-buffered
             best = n;
             if (n * block_cycles >= 1024) break;
         }
@@ -768,6 +768,7 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     p.cout = d.cout; p.leaky = d.leaky; p.out_kind = d.out_kind;
     p.up_rows = d.up_rows; p.bias = d.bias; p.upadd = d.upadd;
     p.cout_stride = d.cout_stride; p.output = d.output;
+    p.out_s2d = d.out_s2d; p.s2d_plane = (long long)d.batch * d.out_rows / 2 * (d.out_w / 2);
 
     const size_t esz = 2;
     int32_t rc = OM_OK;
@@ -785,6 +786,10 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
             cuuint64_t str[2] = {(cuuint64_t)2 * d.cin * esz, (cuuint64_t)2 * d.in_w * d.cin * esz};
             cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.tw, (cuuint32_t)p.th};
             const char* base = reinterpret_cast<const char*>(d.input) + ((size_t)py * d.in_w + px) * d.cin * esz;
+            if (d.in_s2d) {                                   // dense parity planes: every tap is a contiguous box
+                str[0] = (cuuint64_t)d.cin * esz; str[1] = (cuuint64_t)(d.in_w / 2) * d.cin * esz;
+                base = reinterpret_cast<const char*>(d.input) + (size_t)sel * ((size_t)d.batch * d.in_rows / 2 * (d.in_w / 2)) * d.cin * esz;
+            }
             rc = encode(&plan->maps.m[sel], f16, base, 3, dims, str, box, bk * 2);
         }
     }

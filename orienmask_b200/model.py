@@ -46,6 +46,8 @@ class OrienMaskYOLOFPNPlus(nn.Module):
         super().__init__()
         self.num_anchors, self.num_classes = num_anchors, num_classes
         self.precision = os.environ.get('ORIENMASK_B200_PRECISION', 'fp16')     # 'fp16' (tcgen05) | 'fp32' (parity)
+        # replay the forward's ~95 launches as one CUDA graph (small-batch latency; outputs are overwritten by the next call)
+        self.use_cuda_graph = os.environ.get('ORIENMASK_B200_GRAPH', '0') == '1'
         self._specs = conv_specs(num_anchors, num_classes)
         for s in self._specs:
             fan_in = s.cin * s.k * s.k
@@ -100,7 +102,7 @@ class OrienMaskYOLOFPNPlus(nn.Module):
         if eng is None:
             eng = _Engine(self, *key[:3], precision=self.precision, device=x.device)
             self._engines[key] = eng
-        return eng.run(x)
+        return eng.run_graph(x) if self.use_cuda_graph else eng.run(x)
 
 
 class _Engine:
@@ -128,10 +130,11 @@ class _Engine:
     def rows(self, stride):
         return self.H // stride + 32 // stride
 
-    def act(self, stride, channels, dtype=None):
+    def act(self, stride, channels, dtype=None, s2d=False):
+        """Padded-row NHWC buffer; s2d=True marks it parity-split (same size: four [B*rows/2, W/2, C] planes)."""
         t = torch.zeros(self.B * self.rows(stride), self.W // stride, channels, dtype=dtype or self.adt, device=self.device)
         self.keep.append(t)
-        return dict(t=t, stride=stride, c=channels)
+        return dict(t=t, stride=stride, c=channels, s2d=s2d)
 
     # ---- weights ---------------------------------------------------------------------------------
     def folded(self, prefix, kind):
@@ -168,6 +171,9 @@ class _Engine:
         d.out_h, d.out_w, d.out_rows = self.H // so, self.W // so, self.rows(so)
         d.cin, d.cout = w.shape[1], w.shape[0]
         d.ksize, d.stride, d.leaky, d.out_kind = k, stride, int(leaky), kind
+        d.in_s2d = int(bool(src.get('s2d')))
+        d.out_s2d = int(bool(dst is not None and dst.get('s2d')))
+        assert not d.in_s2d or stride == 2, 'only a stride-2 layer can read a parity-split buffer'
         d.input = src['t'].data_ptr()
         d.weights = self.pack(w).data_ptr()
         if bias is not None:
@@ -238,7 +244,9 @@ class _Engine:
         w1, b1 = self.folded('backbone.conv1', 'cbl')
         self.stem_w = w1.permute(2, 3, 1, 0).reshape(27, 32).contiguous()
         self.stem_b = b1.contiguous()
-        c1 = self.act(1, 32)
+        # The outputs of the stem and of stage conv2 are read only by the next stage's stride-2 convolution: they are
+        # written parity-split so that each of its taps is a dense TMA box (strided gathers ran at ~18 B/clk/SM).
+        c1 = self.act(1, 32, s2d=True)
         self.plans.append(('stem', c1))
         self.flops += 2 * B * H * W * 32 * 27
         self.layers.append(dict(name='backbone.conv1', shape='3x3 s1 3->32 @%dx%d stem' % (H, W), flops=2 * B * H * W * 32 * 27,
@@ -254,7 +262,12 @@ class _Engine:
             self.cbl(stage + '.0', trunk, x, 3, stride=2)
             for b in range(1, n + 1):
                 self.cbl('%s.%d.conv.0' % (stage, b), x, y, 1)
-                self.cbl('%s.%d.conv.1' % (stage, b), y, x, 3, residual=x)      # in place: x += leaky(conv(y))
+                if i == 0 and b == n:                                            # feeds only conv3.0 (stride 2)
+                    xs = self.act(st, 2 * c, s2d=True)
+                    self.cbl('%s.%d.conv.1' % (stage, b), y, xs, 3, residual=x)
+                    x = xs
+                else:
+                    self.cbl('%s.%d.conv.1' % (stage, b), y, x, 3, residual=x)  # in place: x += leaky(conv(y))
             trunk = x
             feats[st] = x
         x4, x8, x16, x32 = feats[4], feats[8], feats[16], feats[32]
@@ -294,6 +307,25 @@ class _Engine:
         self.out_orien = torch.empty(B, self.nA * 6, H // 4, W // 4, **f32)
         self.head('orien_head.5', o, self.out_orien)
 
+    def run_graph(self, x):
+        """Same as run(), replayed from a CUDA graph captured on first use (input copied into a static buffer)."""
+        if getattr(self, '_graph', None) is None:
+            self._static_x = torch.empty(self.B, 3, self.H, self.W, dtype=torch.float32, device=self.device)
+            self._static_x.copy_(x)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.run(self._static_x)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_out = self.run(self._static_x)
+            self._graph = g
+        self._static_x.copy_(x)
+        self._graph.replay()
+        return self._graph_out
+
     def run(self, x):
         x = x.contiguous().float()
         with torch.cuda.device(self.device):
@@ -303,7 +335,7 @@ class _Engine:
                     _lib.check(self.lib.om_conv_run(arg, stream), 'om_conv_run')
                 else:
                     _lib.check(self.lib.om_stem_conv(self.prec, _lib.ptr(x), _lib.ptr(self.stem_w), _lib.ptr(self.stem_b),
-                                                     _lib.ptr(arg['t']), self.B, self.H, self.W, self.rows(1), 32, stream),
+                                                     _lib.ptr(arg['t']), self.B, self.H, self.W, self.rows(1), 32, int(bool(arg.get('s2d'))), stream),
                                'om_stem_conv')
         n2 = self.nA * 2
         o = self.out_orien
@@ -323,7 +355,7 @@ class _Engine:
                         _lib.check(self.lib.om_conv_run(arg, stream), 'om_conv_run')
                     else:
                         _lib.check(self.lib.om_stem_conv(self.prec, _lib.ptr(x), _lib.ptr(self.stem_w), _lib.ptr(self.stem_b),
-                                                         _lib.ptr(arg['t']), self.B, self.H, self.W, self.rows(1), 32, stream),
+                                                         _lib.ptr(arg['t']), self.B, self.H, self.W, self.rows(1), 32, int(bool(arg.get('s2d'))), stream),
                                    'om_stem_conv')
                     ev[it][i + 1].record()
             torch.cuda.synchronize()

@@ -70,7 +70,23 @@ def pack_weights(w, precision):
     return p
 
 
-def run_engine_conv(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upadd=None, precision=1, extra_rows=1):
+def to_s2d(t):
+    """padded-row NHWC [R, W, C] -> parity-split: plane 2*(row&1)+(col&1), each [R/2, W/2, C] (include/orienmask_b200.h)."""
+    return torch.stack([t[py::2, px::2] for py in (0, 1) for px in (0, 1)]).contiguous().view(t.shape)
+
+
+def from_s2d(t):
+    R, W, C = t.shape
+    planes = t.view(4, R // 2, W // 2, C)
+    out = torch.empty_like(t)
+    for py in (0, 1):
+        for px in (0, 1):
+            out[py::2, px::2] = planes[2 * py + px]
+    return out
+
+
+def run_engine_conv(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upadd=None, precision=1, extra_rows=1,
+                    in_s2d=False, out_s2d=False):
     """One om_conv_* call on NCHW torch inputs; returns NCHW fp32 (pad rows checked to stay zero)."""
     from orienmask_b200 import _lib
     lib = _lib.lib()
@@ -81,12 +97,15 @@ def run_engine_conv(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upa
     rows_i = rows_o * stride
     adt = torch.float16 if precision == _lib.PREC_F16 else torch.float32
     xin = to_padded(x, rows_i, adt)
+    if in_s2d:
+        xin = to_s2d(xin)
     wp = pack_weights(w, precision)
     d = _lib.ConvDesc()
     d.precision, d.batch = precision, B
     d.in_h, d.in_w, d.in_rows, d.out_h, d.out_w, d.out_rows = H, W, rows_i, Ho, Wo, rows_o
     d.cin, d.cout, d.cout_stride, d.ksize, d.stride, d.leaky, d.out_kind = cin, cout, cout, k, stride, int(leaky), kind
     d.input, d.weights = xin.data_ptr(), wp.data_ptr()
+    d.in_s2d, d.out_s2d = int(in_s2d), int(out_s2d)
     keep = [xin, wp]
     if bias is not None:
         b = bias.float().contiguous()
@@ -117,6 +136,8 @@ def run_engine_conv(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upa
         lib.om_conv_destroy(h)
     if kind == _lib.OUT_NCHW:
         return out
+    if out_s2d:
+        out = from_s2d(out)
     pad = out.view(B, rows_o, Wo, cout)[:, Ho:]
     assert float(pad.abs().max()) == 0.0, 'padding rows were written'
     return from_padded(out, B, Ho)

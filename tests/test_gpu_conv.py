@@ -76,3 +76,20 @@ def test_tcgen05_engine_upadd_staged_by_tma(case):
     ref = torch_conv_ref(x, w, b, stride, leaky, kind, res, up, quantize=True)
     tol = 2e-3 if kind != ACT else 1e-2
     assert torch.allclose(got, ref, atol=tol, rtol=4e-3), float((got - ref).abs().max())
+
+
+@pytest.mark.parametrize('precision', [F32, F16])
+def test_parity_split_layouts(precision):
+    """in_s2d (stride-2 layer reading a parity-split input) and out_s2d (layer writing one), both engines."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 32, 32, 48, generator=g).cuda()
+    w = (torch.randn(64, 32, 3, 3, generator=g) / (32 * 9) ** 0.5).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    q = precision == F16
+    tol = dict(atol=1e-2, rtol=4e-3) if q else dict(atol=2e-4, rtol=1e-4)
+    # extra_rows=2 keeps rows_per_image even for both the stride-2 input (2x) and the s2d output
+    got = run_engine_conv(x, w, b, 2, True, ACT, precision=precision, extra_rows=2, in_s2d=True)
+    assert torch.allclose(got, torch_conv_ref(x, w, b, 2, True, ACT, quantize=q), **tol)
+    res = torch.randn(2, 64, 32, 48, generator=g).cuda()
+    got = run_engine_conv(x, w, b, 1, True, ACT, res, precision=precision, extra_rows=2, out_s2d=True)
+    assert torch.allclose(got, torch_conv_ref(x, w, b, 1, True, ACT, res, quantize=q), **tol)
