@@ -47,6 +47,7 @@ struct Tc2Params {
     int stages;                          // depth of the block ring
     int h_stages, h_stage_bytes, h_chunk_bytes;   // halo ring (halo mode): one stage = the halos of all chunks of a tile
     int a_box_pixels;                    // pixels per activation TMA box
+    int a_sub_bytes;                     // bytes reserved per per-tap activation block
     int tmem_cols;
     int acc_stages;                      // accumulator stages in TMEM (2..4): narrow tiles let the MMA run further ahead of the epilogue
     uint32_t idesc;
@@ -368,7 +369,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_sub = p.half_n * BK * 2;                                // one (tap, chunk) block of this CTA's weight rows
-    const int a_sub = p.halo ? 0 : kBlockM * BK * 2;                    // per-tap mode: the matching activation box
+    const int a_sub = p.a_sub_bytes;                                    // per-tap mode: the matching activation box (0 in halo mode)
     const int sub_bytes = a_sub + b_sub;
     const int stage_bytes = p.n_sub * sub_bytes;
     uint8_t* h_ring = smem;                                             // [h_stages][h_stage_bytes]   (halo mode only)
@@ -685,8 +686,11 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     int cout_pad = (d.cout + 15) / 16 * 16;
     if (cout_pad < 32) cout_pad = 32;
     int bn = cout_pad;
-    if (bn > 256) {
-        bn = 256;
+    int bn_cap = 256;
+    if (getenv("ORIENMASK_B200_BN") && d.out_w <= atoi(getenv("ORIENMASK_B200_BN_MAXW") ? getenv("ORIENMASK_B200_BN_MAXW") : "0"))
+        bn_cap = atoi(getenv("ORIENMASK_B200_BN"));        // experiment: narrower N tiles for the layers that quantise badly
+    if (bn > bn_cap) {
+        bn = bn_cap;
         while (cout_pad % bn) bn -= 32;
     }
     if (bn % 32) { delete plan; return fail(OM_ERR_INVALID, "padded cout %d cannot be split over a CTA pair", cout_pad); }
@@ -714,7 +718,10 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     p.h_stage_bytes = p.h_chunk_bytes * p.k_chunks;
     p.h_stages = p.halo ? 2 : 0;
     if (p.halo && getenv("ORIENMASK_B200_HSTAGES")) p.h_stages = atoi(getenv("ORIENMASK_B200_HSTAGES"));
-    const int sub_bytes = (p.halo ? 0 : kBlockM * bk * 2) + p.half_n * bk * 2;
+    // per-tap activation block: the tw*th-row box rounded up to the 1024-byte swizzle period (the MMA reads 128 rows; rows
+    // beyond the box alias the following weight block and only feed accumulator rows the epilogue masks)
+    p.a_sub_bytes = p.halo ? 0 : ((p.tw * p.th * bk * 2 + 1023) / 1024) * 1024;
+    const int sub_bytes = p.a_sub_bytes + p.half_n * bk * 2;
     // addend prefetch depth: memory-bound tiles (few tensor cycles per tile) need the addend several chunks ahead
     {
         const int tile_cycles = p.taps * p.k_chunks * (bk / 16) * (bn / 2);
