@@ -394,15 +394,13 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     const int first_pair = (int)cluster_id_x(), pair_step = (int)num_clusters_x();
     const int n_groups = p.b_resident ? 0 : p.taps * p.k_chunks / p.n_sub;   // stages per tile
 
-    if (warp == 0 && lane == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0));
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
-        for (int i = 0; i < p.stages; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
-        for (int i = 0; i < p.h_stages; ++i) { mbar_init(&h_full[i], 1); mbar_init(&h_empty[i], 1); }
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8 * kEpiGroups);
-        }
-        for (int i = 0; i < kMaxResBufs; ++i) { mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 4); }
+    if (warp == 0) {                                   // one barrier pair per lane: the ~60 inits are not a serial prologue
+        if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0));
+        if (lane == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
+        if (lane < p.stages) { mbar_init(&s_full[lane], 1); mbar_init(&s_empty[lane], 1); }
+        if (lane >= 8 && lane - 8 < p.h_stages) { mbar_init(&h_full[lane - 8], 1); mbar_init(&h_empty[lane - 8], 1); }
+        if (lane >= 16 && lane < 20) { mbar_init(&tmem_full[lane - 16], 1); mbar_init(&tmem_empty[lane - 16], 8 * kEpiGroups); }
+        if (lane >= 20 && lane - 20 < kMaxResBufs) { mbar_init(&res_full[lane - 20], 1); mbar_init(&res_empty[lane - 20], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {

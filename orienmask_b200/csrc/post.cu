@@ -374,6 +374,9 @@ __global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
                     const float xx2 = fminf(ix2, gx2[j]), yy2 = fminf(iy2, gy2[j]);
                     const float w = fmaxf(0.0f, xx2 - xx1), h = fmaxf(0.0f, yy2 - yy1);
                     const float inter = w * h;
+                    // disjoint boxes (almost all pairs once the class offset is applied): inter == 0 gives ovr = 0 or NaN,
+                    // neither of which reaches a positive threshold -- skip the IEEE division
+                    if (inter == 0.0f && a.thr > 0.0f) continue;
                     const float ovr = inter / (ia + gar[j] - inter);
                     if (j > r && ovr >= a.thr) bits |= 1u << bb;
                 }
