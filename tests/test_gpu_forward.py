@@ -126,3 +126,29 @@ def test_config5_960_forward_and_post():
     assert len(res) == 2
     for r in res:
         assert r['mask'].shape[1:] == (960, 960) and r['mask'].dtype == torch.bool and r['bbox'].shape[0] > 0
+
+
+def test_report_forward_drift_544():
+    """Not a gate beyond the existing ones: writes the measured head drift of both engines against the oracle forward
+    (one 544x544 image, synthetic weights) to gpurun_out/drift.json so that DESIGN.md can quote it."""
+    import json
+    import os
+    from orienmask_b200.synthetic import synthetic_images, synthetic_state_dict
+    from oracle.forward_oracle import forward_oracle
+    from tests.common import ROOT
+    x = synthetic_images(1, 544, 544, seed=1)
+    ref = forward_oracle(synthetic_state_dict(0), x)
+    report = {}
+    for prec in ('fp32', 'fp16'):
+        out = _model(prec)(x.cuda())
+        rows = []
+        for (gb, go), (rb, ro) in zip(out, ref):
+            for name, got, want in (('bbox', gb, rb), ('orien', go, ro)):
+                g = got.float().cpu()
+                rows.append({'head': name, 'shape': list(want.shape), 'max_abs': float((g - want).abs().max()),
+                             'rel_l2': float((g - want).norm() / want.norm())})
+        report[prec] = rows
+        worst = max(r['rel_l2'] for r in rows)
+        assert worst < (1e-4 if prec == 'fp32' else 0.03), (prec, worst)
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(report, open(os.path.join(ROOT, 'gpurun_out', 'drift.json'), 'w'), indent=1)
