@@ -86,3 +86,8 @@ extern "C" void om_conv_destroy(om_conv* c) {
     if (c->tc_plan) { if (c->tc_version == 2) om::tc2_plan_destroy(c->tc_plan); else om::tc_plan_destroy(c->tc_plan); }
     delete c;
 }
+
+// Debug only (not part of the ABI in include/orienmask_b200.h): device buffer of >= 16 uint64 that cluster 0 of the next
+// conv_tc2 launches fills with %globaltimer stamps (prologue / first load / first MMA / first epilogue / exit).
+namespace om { int32_t tc2_set_timeline(void* dev_ptr); }
+extern "C" int32_t om_debug_conv_timeline(void* dev_ptr) { return om::tc2_set_timeline(dev_ptr); }

@@ -88,8 +88,12 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// Execution barrier over the CTA pair.  Relaxed arrive: the default release form compiles to MEMBAR.ALL.GPU and makes
+// every thread wait until all of its global stores are visible device-wide (~0.5 us at kernel exit); what the two
+// uses need is weaker -- barrier-init visibility comes from fence.mbarrier_init.release.cluster, and at exit only
+// "the peer no longer touches my shared memory / TMEM" matters.
 __device__ __forceinline__ void cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
@@ -201,6 +205,16 @@ __device__ __forceinline__ uint32_t swz(int r, int c, int row_bytes) {
 
 struct AMaps { CUtensorMap m[4]; };       // activation views: [0] everything for stride 1; 2*odd_row + odd_col parity views for stride 2
 
+// Debug timeline (tools/_bin/tiny_layer.py): when set, cluster 0 records %globaltimer at fixed points of one launch.
+__device__ unsigned long long* g_timeline = nullptr;
+__device__ __forceinline__ void tick(int slot, bool who) {
+    if (g_timeline != nullptr && who && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_timeline[slot] = t;
+    }
+}
+
 struct PairCoord { int tx, py, tn; };
 __device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
     PairCoord t;
@@ -248,6 +262,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
         const bool valid = in_tile && (Y < p.total_rows) && (y < p.out_h) && (x < p.out_w);
         const int n0 = t.tn * p.block_n;
         mbar_wait(&c.tmem_full[as], aphase);
+        if (pair == c.first_pair) { pdl_wait(); tick(6, c.warp == kEpiWarp0 && c.lane == 0); }
         tc_fence_after();
         const uint32_t taddr = c.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
         const size_t pix = (size_t)Y * p.out_w + x;
@@ -358,6 +373,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
         g0 = (g0 + n_chunks) & (kEpiGroups - 1);
         if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
+    tick(7, c.warp == kEpiWarp0 && c.lane == 0);
 }
 
 
@@ -367,6 +383,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 const __grid_constant__ CUtensorMap map_res, const Tc2Params p) {
     const CUtensorMap& map_a0 = maps_a.m[0];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    tick(0, threadIdx.x == 0);
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_sub = p.half_n * BK * 2;                                // one (tap, chunk) block of this CTA's weight rows
     const int a_sub = p.a_sub_bytes;                                    // per-tap mode: the matching activation box (0 in halo mode)
@@ -414,7 +431,10 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     cluster_sync();                                    // peer barriers are initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();                                        // everything above overlapped the previous layer's tail
+    tick(1, threadIdx.x == 0);
+    // pdl_wait() (griddepcontrol.wait) is executed per role, as late as possible: the producer right before its first
+    // activation load (weights are not produced by the previous layer), the addend producer before its first load, the
+    // epilogue warps before their first store.                                        // everything above overlapped the previous layer's tail
 
     // The K loop of a tile is the sequence of (tap, 64-channel chunk) blocks, tap-major.  A pipeline stage holds
     // n_sub consecutive blocks behind ONE full/empty barrier pair, so the single MMA-issuing thread pays one wait
@@ -450,6 +470,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 if (p.halo) {
                     mbar_wait(&h_empty[hs], h_phase ^ 1);
                     const uint32_t lb = mapa(smem_u32(&h_full[hs]), 0);
+                    if (pair == first_pair) { pdl_wait(); tick(2, lane == 0); }
                     if (lane == 0 && rank == 0) mbar_expect_tx(&h_full[hs], h_tx);
                     if (lane < p.k_chunks)
                         tma_load_3d_pair(h_ring + (size_t)hs * p.h_stage_bytes + (size_t)lane * p.h_chunk_bytes, &map_a0, lb, lane * BK, x0 - 1, y0 - 1);
@@ -460,28 +481,29 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     mbar_wait(&s_empty[st], s_phase ^ 1);
                     const uint32_t lb = mapa(smem_u32(&s_full[st]), 0);
                     uint8_t* sb = s_ring + (size_t)st * stage_bytes;
+                    const int i = g * p.n_sub + lane;                // (tap, chunk) block of this lane, tap-major
+                    const int tap = i / p.k_chunks, kc = i - tap * p.k_chunks;
+                    int dx = 0, dy = 0, sel = 0;
+                    if (!p.halo && p.taps == 9) {
+                        const int r = tap / 3, s = tap - r * 3;
+                        if (p.stride == 1) { dx = s - 1; dy = r - 1; }
+                        else {
+                            dx = (s == 0) ? -1 : 0; dy = (r == 0) ? -1 : 0;
+                            sel = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);       // odd row / odd column views
+                        }
+                    }
+                    if (!p.halo && pair == first_pair && g == 0) { pdl_wait(); tick(2, lane == 0); }   // first activation load
                     if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[st], s_tx);
                     if (lane < p.n_sub) {
-                        const int i = g * p.n_sub + lane;            // (tap, chunk) block of this lane, tap-major
-                        const int tap = i / p.k_chunks, kc = i - tap * p.k_chunks;
-                        if (!p.halo) {
-                            int dx = 0, dy = 0, sel = 0;
-                            if (p.taps == 9) {
-                                const int r = tap / 3, s = tap - r * 3;
-                                if (p.stride == 1) { dx = s - 1; dy = r - 1; }
-                                else {
-                                    dx = (s == 0) ? -1 : 0; dy = (r == 0) ? -1 : 0;
-                                    sel = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);   // odd row / odd column views
-                                }
-                            }
-                            tma_load_3d_pair(sb + (size_t)lane * sub_bytes, &maps_a.m[sel], lb, kc * BK, x0 + dx, y0 + dy);
-                        }
+                        if (!p.halo) tma_load_3d_pair(sb + (size_t)lane * sub_bytes, &maps_a.m[sel], lb, kc * BK, x0 + dx, y0 + dy);
                         tma_load_2d_pair(sb + (size_t)lane * sub_bytes + a_sub, &map_b, lb, kc * BK, tap * p.cout_pad + n0);
                     }
                     __syncwarp();
+                    if (pair == first_pair && g == 0) tick(3, lane == 0);
                     if (++st == p.stages) { st = 0; s_phase ^= 1; }
                 }
             }
+            tick(8, lane == 0);
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -530,6 +552,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     uint32_t tap_off16 = 0; int tap_s = 0, kc = 0;   // halo: descriptor offset of the current tap, its column, chunk
                     for (int g = 0; g < n_groups; ++g) {
                         mbar_wait(&s_full[st], s_phase);
+                        if (pair == first_pair && g == 0) tick(4, lane == 0);
                         tc_fence_after();
                         const uint32_t sb16 = ((s_ring_addr + (uint32_t)(st * stage_bytes)) & 0x3FFFF) >> 4;
                         uint64_t bd = hi_b | (uint64_t)(sb16 + asub16);
@@ -559,6 +582,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 }
                 if (elect_one()) umma_commit_pair(&tmem_full[as]);
                 __syncwarp();
+                if (pair == first_pair) tick(5, lane == 0);
                 if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             }
         }
@@ -568,6 +592,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             // chunk g of this CTA's chunk sequence goes to epilogue group g & 1; that group's k-th chunk (k = g >> 1)
             // uses its slot k % res_depth, so the loads run res_depth chunks ahead of each group (the DRAM latency of
             // the addend was the top stall of the memory-bound residual layers with a single slot)
+            pdl_wait();
             int grp = 0, slot[kEpiGroups] = {}; uint32_t sphase[kEpiGroups] = {};
             const int n_chunks = p.block_n / p.chunk_cols;
             const uint32_t bytes = p.has_res == 1 ? (uint32_t)(p.tw * p.th * p.row_bytes) : (uint32_t)(p.up_bw * p.up_bh * 128);
@@ -601,9 +626,11 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
         else epilogue_loop<0, 0>(p, c);
     }
 
+    tick(9, threadIdx.x == 0);
     tc_fence_before();
     __syncthreads();
     cluster_sync();                                    // nobody leaves while the peer may still touch its smem / TMEM
+    tick(10, threadIdx.x == 0);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -844,5 +871,10 @@ int32_t tc2_plan_run(const void* vp, cudaStream_t stream) {
 }
 
 void tc2_plan_destroy(void* vp) { delete reinterpret_cast<Tc2Plan*>(vp); }
+
+int32_t tc2_set_timeline(void* dev_ptr) {
+    OM_CUDA_TRY(cudaMemcpyToSymbol(g_timeline, &dev_ptr, sizeof(void*)));
+    return OM_OK;
+}
 
 }  // namespace om
