@@ -236,8 +236,14 @@ __device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
 //   ADD : 0 none, 1 residual (fp16 chunk staged by TMA, added after the activation), 2 up-add (fp32 half-resolution
 //         chunk staged by TMA, added before bias and activation)
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 struct EpiCtx {
-    uint32_t tmem_base, leader_tmem_empty0, rank;
+    uint32_t tmem_base, leader_tmem_empty0, rank, s_bias_addr;
     uint64_t* tmem_full; uint64_t* res_full; uint64_t* res_empty;
     const uint8_t* res_buf; const float* s_bias;
     int warp, lane, first_pair, pair_step, num_pairs;
@@ -261,8 +267,9 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
         const int img = Y / p.out_rows, y = Y - img * p.out_rows;
         const bool valid = in_tile && (Y < p.total_rows) && (y < p.out_h) && (x < p.out_w);
         const int n0 = t.tn * p.block_n;
+        if (pair == c.first_pair) pdl_wait();          // while the first accumulator is still being produced
         mbar_wait(&c.tmem_full[as], aphase);
-        if (pair == c.first_pair) { pdl_wait(); tick(6, c.warp == kEpiWarp0 && c.lane == 0); }
+        if (pair == c.first_pair) tick(6, c.warp == kEpiWarp0 && c.lane == 0);
         tc_fence_after();
         const uint32_t taddr = c.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
         const size_t pix = (size_t)Y * p.out_w + x;
@@ -309,7 +316,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
                 }
     #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float4 bv = *reinterpret_cast<const float4*>(c.s_bias + cg + i);     // warp-uniform: smem broadcast
+                    const float4 bv = lds_f4(c.s_bias_addr + (uint32_t)(cg + i) * 4u);          // warp-uniform: smem broadcast
                     f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
                 }
                 if (p.leaky) {
@@ -419,15 +426,19 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
         if (lane >= 16 && lane < 20) { mbar_init(&tmem_full[lane - 16], 1); mbar_init(&tmem_empty[lane - 16], 8 * kEpiGroups); }
         if (lane >= 20 && lane - 20 < kMaxResBufs) { mbar_init(&res_full[lane - 20], 1); mbar_init(&res_empty[lane - 20], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        tick(11, lane == 0);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        tick(12, lane == 0);
     }
     for (int i = threadIdx.x; i < p.cout_pad; i += kThreads)
         s_bias[i] = (p.bias != nullptr && p.out_kind != OM_OUT_PARTIAL && i < p.cout) ? p.bias[i] : 0.0f;
+    tick(13, threadIdx.x == 64);
     tc_fence_before();
     __syncthreads();
+    tick(14, threadIdx.x == 0);
     cluster_sync();                                    // peer barriers are initialised before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
@@ -617,7 +628,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
         EpiCtx c;
         c.tmem_base = tmem_base; c.leader_tmem_empty0 = mapa(smem_u32(&tmem_empty[0]), 0); c.rank = rank;
         c.tmem_full = tmem_full; c.res_full = res_full; c.res_empty = res_empty;
-        c.res_buf = res_buf; c.s_bias = s_bias;
+        c.res_buf = res_buf; c.s_bias = s_bias; c.s_bias_addr = smem_u32(s_bias);
         c.warp = warp; c.lane = lane; c.first_pair = first_pair; c.pair_step = pair_step; c.num_pairs = num_pairs;
         if (p.out_kind == OM_OUT_NCHW) epilogue_loop<2, 0>(p, c);
         else if (p.out_kind == OM_OUT_PARTIAL) { if (p.has_res == 2) epilogue_loop<1, 2>(p, c); else epilogue_loop<1, 0>(p, c); }
