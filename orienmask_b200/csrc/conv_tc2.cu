@@ -63,6 +63,13 @@ struct Tc2Params {
     int row_bytes;                       // bytes per staged row (128 or 64)
     int cout_stride;
     int out_s2d;                         // write the fp16 output parity-split (see om_conv_desc)
+    int flat;                            // pixel tile = 128 consecutive REAL output pixels in (image, y, x) order, gathered by an
+                                         // im2col-mode tensor map (no pad rows, no partially filled tiles; see tc2_plan_create)
+    int flat_hw, flat_total, pad;        // out_h * out_w, batch * out_h * out_w, ksize / 2
+    int res_direct;                      // flat mode: the fp16 residual is read by the epilogue threads themselves (prefetched one
+                                         // chunk ahead) -- im2col-mode TMA costs ~6.5 cycles per pixel whatever the row size, and the
+                                         // flat layers are bounded by exactly that rate (profiles/r01_flat_tiles.md)
+    const void* residual;
     long long s2d_plane;                 // pixels per parity plane of the output
     const float* bias;
     const float* upadd;
@@ -151,6 +158,21 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// im2col-mode loads (tensor map from cuTensorMapEncodeIm2col): `pixelsPerColumn` pixels starting at input position (w, h) of
+// image n, shifted by the filter tap (ow, oh), walking x -> y -> image inside the map's bounding box with its traversal
+// stride; positions outside the image read zeros.
+__device__ __forceinline__ void tma_load_im2col_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c, int w, int h, int n,
+                                                     int ow, int oh) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)ow), "h"((uint16_t)oh) : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h, int n) {
+    const uint16_t z = 0;
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %7};"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(z) : "memory");
+}
 // One 32-byte store per thread: a whole sector, so the L1 -> L2 write traffic is not inflated by partial sectors.
 __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -225,6 +247,20 @@ __device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
     return t;
 }
 
+// Flat mode: first output pixel (x, y, image) of pixel tile `tm`; tiles past the end (odd tile count) re-read tile 0 and
+// are masked in the epilogue.
+struct FlatOrigin { int x, y, n; };
+__device__ __forceinline__ FlatOrigin flat_origin(const Tc2Params& p, int tm) {
+    int q0 = tm * kBlockM;
+    if (q0 >= p.flat_total) q0 = 0;
+    FlatOrigin o;
+    o.n = q0 / p.flat_hw;
+    const int rem = q0 - o.n * p.flat_hw;
+    o.y = rem / p.out_w;
+    o.x = rem - o.y * p.out_w;
+    return o;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Epilogue.  kEpiGroups groups of 4 warps (TMEM lane quadrant = warp % 4); the 32-column chunks of the accumulators
 // are dealt round-robin to the groups over this CTA's whole chunk sequence (chunk g -> group g % kEpiGroups, which is
@@ -234,8 +270,15 @@ __device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
 // four warps per scheduler and one specialised instance per (output kind, addend kind).
 //   KIND: 0 fp16 NHWC activation, 1 fp32 NHWC (partial sums), 2 fp32 NCHW (heads)
 //   ADD : 0 none, 1 residual (fp16 chunk staged by TMA, added after the activation), 2 up-add (fp32 half-resolution
-//         chunk staged by TMA, added before bias and activation)
+//         chunk staged by TMA, added before bias and activation), 3 residual read straight from global memory by the
+//         thread that owns the pixel, one 32-column chunk ahead (flat mode)
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldg_res32(uint4 (&r)[4], const __half* src) {      // 32 fp16 = 64 bytes of one pixel
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[i].x), "=r"(r[i].y), "=r"(r[i].z), "=r"(r[i].w) : "l"(src + 8 * i) : "memory");
+}
+
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -249,7 +292,7 @@ struct EpiCtx {
     int warp, lane, first_pair, pair_step, num_pairs;
 };
 
-template <int KIND, int ADD>
+template <int KIND, int ADD, bool FLAT>
 __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& c) {
     const int quad = c.warp & 3;
     const int grp = (c.warp - kEpiWarp0) >> 2;
@@ -262,12 +305,27 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
     int g0 = 0;                                          // sequence number (mod kEpiGroups) of the tile's first chunk
     for (int pair = c.first_pair; pair < c.num_pairs; pair += c.pair_step) {
         const PairCoord t = decode_pair(p, pair);
-        const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)c.rank) * p.th;
-        const int Y = y0 + my, x = x0 + mx;
-        const int img = Y / p.out_rows, y = Y - img * p.out_rows;
-        const bool valid = in_tile && (Y < p.total_rows) && (y < p.out_h) && (x < p.out_w);
+        int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)c.rank) * p.th;
+        int Y = y0 + my, x = x0 + mx;
+        int img = Y / p.out_rows, y = Y - img * p.out_rows;
+        bool valid = in_tile && (Y < p.total_rows) && (y < p.out_h) && (x < p.out_w);
+        if (FLAT) {                                     // accumulator row m = output pixel (2 * py + rank) * 128 + m in (image, y, x) order
+            const int q = (2 * t.py + (int)c.rank) * kBlockM + m;
+            valid = q < p.flat_total;
+            img = q / p.flat_hw;
+            const int rem = q - img * p.flat_hw;
+            y = rem / p.out_w; x = rem - y * p.out_w;
+            Y = img * p.out_rows + y;
+        }
         const int n0 = t.tn * p.block_n;
         if (pair == c.first_pair) pdl_wait();          // while the first accumulator is still being produced
+        const int j_first = (grp - g0) & (kEpiGroups - 1);
+        uint4 rr[4] = {};
+        const __half* rsrc = nullptr;
+        if (ADD == 3) {
+            rsrc = reinterpret_cast<const __half*>(p.residual) + ((size_t)Y * p.out_w + x) * p.cout_stride + n0;
+            if (valid && j_first < n_chunks) ldg_res32(rr, rsrc + j_first * 32);
+        }
         mbar_wait(&c.tmem_full[as], aphase);
         if (pair == c.first_pair) tick(6, c.warp == kEpiWarp0 && c.lane == 0);
         tc_fence_after();
@@ -277,7 +335,6 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
         if (ADD == 0 && KIND != 2 && p.upadd != nullptr && valid)
             up = p.upadd + ((size_t)(img * p.up_rows + (y >> 1)) * (p.out_w >> 1) + (x >> 1)) * p.cout;
         const int up_row = ((Y >> 1) - (y0 >> 1)) * p.up_bw + ((x >> 1) - (x0 >> 1));   // source pixel inside the staged box
-        const int j_first = (grp - g0) & (kEpiGroups - 1);
         if (j_first >= n_chunks) {                        // nothing for this group in this tile: release at once
             tc_fence_before();
             __syncwarp();
@@ -285,7 +342,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
         }
         for (int j = j_first; j < n_chunks; j += kEpiGroups) {
             const int rb = grp + kEpiGroups * rslot;
-            if (ADD != 0) mbar_wait(&c.res_full[rb], rphase);
+            if (ADD == 1 || ADD == 2) mbar_wait(&c.res_full[rb], rphase);
             for (int c0 = 0; c0 < p.chunk_cols; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(j * p.chunk_cols + c0), v);
@@ -337,6 +394,20 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
                             }
                         }
                     }
+                    if (ADD == 3) {
+                        if (valid) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                const __half2* rh = reinterpret_cast<const __half2*>(&rr[i >> 3]);
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const float2 rf = __half22float2(rh[q]);
+                                    f[i + 2 * q] += rf.x; f[i + 2 * q + 1] += rf.y;
+                                }
+                            }
+                            if (j + kEpiGroups < n_chunks) ldg_res32(rr, rsrc + (j + kEpiGroups) * 32);
+                        }
+                    }
                     if (valid) {
                         size_t opix = pix;
                         if (p.out_s2d) opix = (size_t)(2 * (Y & 1) + (x & 1)) * (size_t)p.s2d_plane + (size_t)(Y >> 1) * (p.out_w >> 1) + (x >> 1);
@@ -371,7 +442,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
                         if (cg + i < p.cout) o[(size_t)(cg + i) * plane] = f[i];
                 }
             }
-            if (ADD != 0) {
+            if (ADD == 1 || ADD == 2) {
                 __syncwarp();
                 if (c.lane == 0) mbar_arrive(&c.res_empty[rb]);
                 if (++rslot == p.res_depth) { rslot = 0; rphase ^= 1; }
@@ -478,6 +549,9 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 const PairCoord t = decode_pair(p, pair);
                 const int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
                 const int n0 = t.tn * p.block_n + (int)rank * p.half_n;
+                FlatOrigin fo = {0, 0, 0};
+                if (p.flat) fo = flat_origin(p, 2 * t.py + (int)rank);
+                const int fw = fo.x * p.stride - p.pad, fh = fo.y * p.stride - p.pad;
                 if (p.halo) {
                     mbar_wait(&h_empty[hs], h_phase ^ 1);
                     const uint32_t lb = mapa(smem_u32(&h_full[hs]), 0);
@@ -495,8 +569,10 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     const int i = g * p.n_sub + lane;                // (tap, chunk) block of this lane, tap-major
                     const int tap = i / p.k_chunks, kc = i - tap * p.k_chunks;
                     int dx = 0, dy = 0, sel = 0;
+                    int tap_r = 0, tap_s = 0;
                     if (!p.halo && p.taps == 9) {
                         const int r = tap / 3, s = tap - r * 3;
+                        tap_r = r; tap_s = s;
                         if (p.stride == 1) { dx = s - 1; dy = r - 1; }
                         else {
                             dx = (s == 0) ? -1 : 0; dy = (r == 0) ? -1 : 0;
@@ -506,7 +582,8 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     if (!p.halo && pair == first_pair && g == 0) { pdl_wait(); tick(2, lane == 0); }   // first activation load
                     if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[st], s_tx);
                     if (lane < p.n_sub) {
-                        if (!p.halo) tma_load_3d_pair(sb + (size_t)lane * sub_bytes, &maps_a.m[sel], lb, kc * BK, x0 + dx, y0 + dy);
+                        if (p.flat) tma_load_im2col_pair(sb + (size_t)lane * sub_bytes, &map_a0, lb, kc * BK, fw, fh, fo.n, tap_s, tap_r);
+                        else if (!p.halo) tma_load_3d_pair(sb + (size_t)lane * sub_bytes, &maps_a.m[sel], lb, kc * BK, x0 + dx, y0 + dy);
                         tma_load_2d_pair(sb + (size_t)lane * sub_bytes + a_sub, &map_b, lb, kc * BK, tap * p.cout_pad + n0);
                     }
                     __syncwarp();
@@ -611,12 +688,15 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 const PairCoord t = decode_pair(p, pair);
                 int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)rank) * p.th;
                 if (p.has_res == 2) { x0 >>= 1; y0 >>= 1; }          // half-resolution source of the nearest x2 up-sampling
+                FlatOrigin fo = {0, 0, 0};
+                if (p.flat) fo = flat_origin(p, 2 * t.py + (int)rank);
                 for (int j = 0; j < n_chunks; ++j) {
                     const int rb = grp + kEpiGroups * slot[grp];
                     mbar_wait(&res_empty[rb], sphase[grp] ^ 1);
                     if (elect_one()) {
                         mbar_expect_tx(&res_full[rb], bytes);
-                        tma_load_3d(res_buf + rb * p.res_buf_bytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0);
+                        if (p.flat) tma_load_im2col(res_buf + rb * p.res_buf_bytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, fo.x, fo.y, fo.n);
+                        else tma_load_3d(res_buf + rb * p.res_buf_bytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0);
                     }
                     __syncwarp();
                     if (++slot[grp] == p.res_depth) { slot[grp] = 0; sphase[grp] ^= 1; }
@@ -630,11 +710,16 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
         c.tmem_full = tmem_full; c.res_full = res_full; c.res_empty = res_empty;
         c.res_buf = res_buf; c.s_bias = s_bias; c.s_bias_addr = smem_u32(s_bias);
         c.warp = warp; c.lane = lane; c.first_pair = first_pair; c.pair_step = pair_step; c.num_pairs = num_pairs;
-        if (p.out_kind == OM_OUT_NCHW) epilogue_loop<2, 0>(p, c);
-        else if (p.out_kind == OM_OUT_PARTIAL) { if (p.has_res == 2) epilogue_loop<1, 2>(p, c); else epilogue_loop<1, 0>(p, c); }
-        else if (p.has_res == 1) epilogue_loop<0, 1>(p, c);
-        else if (p.has_res == 2) epilogue_loop<0, 2>(p, c);
-        else epilogue_loop<0, 0>(p, c);
+        if (p.flat) {
+            if (p.out_kind == OM_OUT_PARTIAL) epilogue_loop<1, 0, true>(p, c);
+            else if (p.res_direct) epilogue_loop<0, 3, true>(p, c);
+            else epilogue_loop<0, 0, true>(p, c);
+        }
+        else if (p.out_kind == OM_OUT_NCHW) epilogue_loop<2, 0, false>(p, c);
+        else if (p.out_kind == OM_OUT_PARTIAL) { if (p.has_res == 2) epilogue_loop<1, 2, false>(p, c); else epilogue_loop<1, 0, false>(p, c); }
+        else if (p.has_res == 1) epilogue_loop<0, 1, false>(p, c);
+        else if (p.has_res == 2) epilogue_loop<0, 2, false>(p, c);
+        else epilogue_loop<0, 0, false>(p, c);
     }
 
     tick(9, threadIdx.x == 0);
@@ -672,6 +757,40 @@ int32_t encode(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int r
     CUresult r = fn(map, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return om::fail(OM_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return OM_OK;
+}
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                   const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// NHWC tensor [batch][h (image pitch `rows` rows)][w][c (pixel pitch `c_stride`)] as an im2col map: `channels` channels of 128 output
+// pixels per load; k x k filter with padding k/2 and traversal stride `stride` (bounding-box corners as cuDNN / CUTLASS fprop).
+int32_t encode_im2col(CUtensorMap* map, const void* base, int c, int c_stride, int w, int h, int rows, int batch, int channels, int ksize,
+                      int stride, int inner_bytes) {
+    static EncodeIm2colFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeIm2colFn>(ptr);
+    }
+    if (!fn) return om::fail(OM_ERR_CUDA, "cuTensorMapEncodeIm2col entry point not available");
+    const size_t esz = 2;
+    cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+    cuuint64_t str[3] = {(cuuint64_t)c_stride * esz, (cuuint64_t)w * c_stride * esz, (cuuint64_t)rows * w * c_stride * esz};
+    const int pad = ksize / 2;
+    int lower[2] = {-pad, -pad}, upper[2] = {pad - (ksize - 1), pad - (ksize - 1)};
+    cuuint32_t trav[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    const CUtensorMapSwizzle sw = inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, str, lower, upper, (cuuint32_t)channels,
+                    (cuuint32_t)kBlockM, trav, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return om::fail(OM_ERR_CUDA, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
+    // same fix-up CUTLASS applies (copy_traits_sm90_im2col.hpp) for drivers <= 13.1 on tensors smaller than 128 KB
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    if (drv <= 13010 && (size_t)batch * rows * w * c_stride * esz < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
     return OM_OK;
 }
 
@@ -734,13 +853,31 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     const char* halo_env = getenv("ORIENMASK_B200_HALO");
     p.halo = d.ksize == 3 && d.stride == 1 && d.out_kind != OM_OUT_NCHW && (d.out_w % 8 == 0 || d.out_w >= 64) &&
              !(halo_env && halo_env[0] == '0');
+    // Flat tiles: every layer that is not served by a halo box, a parity-split input or a TMA-staged up-add computes tiles of 128
+    // consecutive real pixels (image, y, x) gathered by im2col-mode TMA: no pad rows and no partially filled tiles, which at
+    // 17x17 / 34x34 is the difference between 3 and 2 (5 and 4) waves of CTA pairs.
+    const char* flat_env = getenv("ORIENMASK_B200_FLAT");
+    p.flat = !p.halo && !d.in_s2d && d.upadd == nullptr && d.out_kind != OM_OUT_NCHW && !d.out_s2d && !(flat_env && flat_env[0] == '0');
+    p.flat_hw = d.out_h * d.out_w; p.flat_total = d.batch * p.flat_hw; p.pad = d.ksize / 2;
+    if (p.flat && !(flat_env && flat_env[0] == '2')) {
+        // ... but im2col-mode loads cost ~6.5 cycles per pixel, which the memory-bound layers with many waves of tiles cannot
+        // afford: keep rectangular boxes when quantisation is not the problem (more than ~10 waves of pairs)
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long flat_pairs = ((p.flat_total + kBlockM - 1) / kBlockM + 1) / 2;
+        if (flat_pairs * (cout_pad / bn) > 10ll * (sms / 2)) p.flat = 0;
+    }
     if (p.halo) { p.tw = 8; p.th = 16; p.tiles_x = (d.out_w + 7) / 8; }
+    else if (p.flat) { p.tw = kBlockM; p.th = 1; p.tiles_x = 1; }
     else { p.tw = pick_tile_w(d.out_w, d.out_kind == OM_OUT_NCHW); p.th = kBlockM / p.tw; p.tiles_x = d.out_w / p.tw; }
     p.total_rows = d.batch * d.out_rows;
-    const int tiles_y = (p.total_rows + p.th - 1) / p.th;
+    const int tiles_y = p.flat ? (p.flat_total + kBlockM - 1) / kBlockM : (p.total_rows + p.th - 1) / p.th;
     p.pairs_y = (tiles_y + 1) / 2;
     p.taps = d.ksize * d.ksize; p.stride = d.stride; p.k_chunks = d.cin / bk;
-    p.has_res = d.residual != nullptr ? 1 : 0;
+    p.res_direct = (d.residual != nullptr && p.flat) ? 1 : 0;
+    p.residual = d.residual;
+    p.has_res = (d.residual != nullptr && !p.flat) ? 1 : 0;
     p.up_bw = p.tw / 2 + 1; p.up_bh = p.th / 2 + 1;
     if (d.upadd != nullptr && !p.has_res && d.up_rows * 2 == d.out_rows && d.cout % 32 == 0 && p.up_bw * p.up_bh <= kStageRows)
         p.has_res = 2;
@@ -816,7 +953,10 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     const size_t esz = 2;
     int32_t rc = OM_OK;
     const CUtensorMapDataType f16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    if (d.stride == 1) {
+    if (p.flat) {
+        rc = encode_im2col(&plan->maps.m[0], d.input, d.cin, d.cin, d.in_w, d.in_h, d.in_rows, d.batch, bk, d.ksize, d.stride, bk * 2);
+        for (int i = 1; i < 4 && rc == OM_OK; ++i) plan->maps.m[i] = plan->maps.m[0];
+    } else if (d.stride == 1) {
         cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.batch * d.in_rows};
         cuuint64_t str[2] = {(cuuint64_t)d.cin * esz, (cuuint64_t)d.in_w * d.cin * esz};
         cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(p.halo ? p.tw + 2 : p.tw), (cuuint32_t)(p.halo ? p.th + 2 : p.th)};
@@ -848,7 +988,9 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
         cuuint32_t box[3] = {32u, (cuuint32_t)p.up_bw, (cuuint32_t)p.up_bh};
         rc = encode(&plan->map_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, d.upadd, 3, dims, str, box, 128);
     }
-    if (rc == OM_OK && p.has_res == 1) {
+    if (rc == OM_OK && p.has_res == 1 && p.flat) {
+        rc = encode_im2col(&plan->map_res, d.residual, d.cout, d.cout_stride, d.out_w, d.out_h, d.out_rows, d.batch, p.chunk_cols, 1, 1, p.row_bytes);
+    } else if (rc == OM_OK && p.has_res == 1) {
         cuuint64_t dims[3] = {(cuuint64_t)d.cout, (cuuint64_t)d.out_w, (cuuint64_t)d.batch * d.out_rows};
         cuuint64_t str[2] = {(cuuint64_t)d.cout_stride * esz, (cuuint64_t)d.out_w * d.cout_stride * esz};
         cuuint32_t box[3] = {(cuuint32_t)p.chunk_cols, (cuuint32_t)p.tw, (cuuint32_t)p.th};

@@ -28,6 +28,13 @@ CASES = [
     (2, 64, 64, 24, 72, 3, 1, ACT, False, False),
     (3, 32, 64, 40, 16, 3, 1, ACT, True, False),          # 64-byte pixels (SWIZZLE_64B halo)
     (2, 256, 128, 17, 17, 1, 1, ACT, False, False),
+    # flat (im2col-gathered) tiles: runs of 128 pixels that cross rows and images, odd tile counts, strided traversal
+    (5, 64, 64, 17, 17, 3, 1, ACT, True, False),
+    (7, 128, 64, 17, 17, 1, 1, ACT, False, False),
+    (4, 64, 128, 34, 34, 3, 2, ACT, False, False),
+    (3, 256, 512, 34, 34, 3, 1, ACT, True, False),
+    (3, 96, 64, 10, 14, 3, 1, ACT, False, False),         # 64-byte pixels (BK = 32), three chunks
+    (2, 64, 128, 34, 34, 1, 1, PARTIAL, False, False),
 ]
 
 
