@@ -140,6 +140,61 @@ def run_reference(args, rank):
                       'e2e': {'value': v, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
+def measure_stages(torch, ob, transform, host_u8, out, dev, iters=10):
+    """The two neighbours of the path, each timed alone with CUDA events against the HBM roofline:
+    pre-process (uint8 HWC -> fp32 NCHW) and detections -> COCO RLE (masks -> run-length strings for 480x640 originals)."""
+    from orienmask_b200.coco_format import encode_masks
+    from orienmask_b200 import _lib
+    hbm = measured_peaks()['hbm']
+    x = host_u8.to(dev)
+    res = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    us = timed(lambda: transform(x))
+    nbytes = x.numel() + x.shape[0] * 3 * H * W * 4
+    res['preprocess'] = {'us': us, 'bytes': nbytes, 'GBps': nbytes / us / 1e3, 'frac_of_hbm': nbytes / us / 1e3 / hbm,
+                         'what': 'uint8 HWC [%d,%d,%d,3] -> fp32 NCHW, one prep_kernel launch' % tuple(x.shape[:3])}
+    dets = out.to_list()
+    counts = [int(d['bbox'].shape[0]) for d in dets]
+    infos = [{'id': i, 'height': 480, 'width': 640, 'collate_pad': [0, 0, 0, 0, H, W]} for i in range(len(dets))]
+    masks = [d['mask'] for d in dets]
+    lib = _lib.lib()
+    lib.om_launch_count_reset()
+    t0 = time.perf_counter()
+    enc = encode_masks(masks, counts, infos)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = int(lib.om_launch_count())
+    # kernel alone: CUDA events around repeated calls of the same launch (through encode_masks' C-ABI call)
+    ev = []
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        encode_masks(masks, counts, infos)
+        e1.record()
+        torch.cuda.synchronize()
+        ev.append(e0.elapsed_time(e1))
+    nbytes = sum(counts) * H * W
+    text = sum(len(e['counts']) for im in enc for e in im)
+    res['coco_format'] = {'ms_host_to_strings': min(ev), 'first_call_ms': wall_ms, 'instances': sum(counts), 'mask_bytes_read': nbytes,
+                          'rle_text_bytes': text, 'GBps_end_to_end': nbytes / min(ev) / 1e6, 'launches': launches,
+                          'what': 'bool masks [K,%d,%d] -> crop/resize to 480x640 -> round -> column-major RLE -> COCO strings on the '
+                                  'device (mask_rle_kernel), strings to host' % (H, W)}
+    return res
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -179,9 +234,12 @@ def main():
     model.precision = args.precision
     model = model.to(dev).eval()
     post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5), device=dev, **post_kwargs())
-    # two distinct resident batches, alternated (per-step activation traffic is >> the 126 MB L2 anyway)
-    host = [synthetic_images(B, H, W, seed=1 + rank * 2 + i).pin_memory() for i in range(2)]
-    resident = [h.to(dev) for h in host]
+    # two distinct resident batches, alternated (per-step activation traffic is >> the 126 MB L2 anyway).  The host side
+    # holds what cv2.imread yields (uint8 HWC, infer.py:147); the device-resident arm holds the transformed model input.
+    transform = ob.FastCOCOTransform([dict(type='Resize', size=(H, W)), dict(type='Normalize', mean=(0, 0, 0), std=(255, 255, 255))])
+    host = [(synthetic_images(B, H, W, seed=1 + rank * 2 + i) * 255).round().clamp(0, 255).to(torch.uint8)
+            .permute(0, 2, 3, 1).contiguous().pin_memory() for i in range(2)]
+    resident = [transform(h.to(dev)) for h in host]
     lib = _lib.lib()
 
     def step(x):
@@ -227,7 +285,7 @@ def main():
 
     # ---- end to end through the public API from pinned host memory -----------------------------
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [torch.empty_like(resident[0]) for _ in range(2)]
+    bufs = [torch.empty_like(host[0], device=dev) for _ in range(2)]
     rec_host = torch.empty(B * world, 100, 5, dtype=torch.float32).pin_memory()
     cnt_host = torch.empty(B * world, dtype=torch.int32).pin_memory()
     ready = [torch.cuda.Event() for _ in range(2)]
@@ -247,8 +305,9 @@ def main():
                     bufs[1 - s].copy_(host[(i + 1) % 2], non_blocking=True)
                     ready[1 - s].record(copy_stream)
             cur.wait_event(ready[s])
-            _, det, cls, cnt = step(bufs[s])
+            x = transform(bufs[s])                    # infer.py:149: permute + resize + normalise (one kernel)
             freed[s].record(cur)
+            _, det, cls, cnt = step(x)
             rec_host.copy_(det, non_blocking=True)
             cnt_host.copy_(cnt, non_blocking=True)
         torch.cuda.synchronize()
@@ -262,6 +321,8 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
+
+    stages = measure_stages(torch, ob, transform, host[0], out, dev) if rank == 0 else None
 
     if rank == 0:
         peaks = measured_peaks()
@@ -278,10 +339,13 @@ def main():
                        'precision': 'fp16 storage / fp32 accumulate convs, fp32 heads + post-process' if args.precision == 'fp16' else 'fp32',
                        'avg_instances_per_image': k_avg},
             'e2e': {'value': world * B * args.steps / e2e_s, 'unit': 'images/sec',
-                    'h2d_bytes_per_step': int(host[0].numel() * 4), 'd2h_bytes_per_step': int(rec_host.numel() * 4 + cnt_host.numel() * 4),
-                    'note': 'pinned fp32 NCHW images -> model() -> postprocess -> detection records + counts to host; copies double-buffered on a side stream'},
+                    'h2d_bytes_per_step': int(host[0].numel() * host[0].element_size()),
+                    'd2h_bytes_per_step': int(rec_host.numel() * 4 + cnt_host.numel() * 4),
+                    'note': 'pinned uint8 HWC images (cv2 layout) -> FastCOCOTransform -> model() -> postprocess -> detection records + '
+                            'counts to host; copies double-buffered on a side stream'},
             'gpu_launches': launches,
             'clocks': clocks,
+            'stages': stages,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
                          'frac': achieved / peaks['tflops'], 'traffic': traffic['bytes'] if traffic else None,
                          'traffic_note': ('ncu dram__bytes_read+write summed over the %d conv-engine launches of one step '

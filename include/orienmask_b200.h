@@ -16,6 +16,8 @@
  *   om_batched_nms         eval/function.py:77-103 (batched_nms) + eval/orienmask_yolo_postprocess.py:146-154
  *   om_mask_assemble       eval/orienmask_yolo_postprocess.py:69-72,99,141-144,156-164 (bilinear x4,
  *                          get_orien_grid, per-instance orientation thresholding)
+ *   om_preprocess          data/transform.py:444-510 (FastCOCOTransform: permute + Resize + Normalize) and infer.py:21-32 (pad)
+ *   om_mask_rle            eval/coco_eval.py:108-127,191-205 (_recover_shape_segm + maskUtils.encode of every instance)
  *   om_stem_conv, om_conv_*  model/base.py:104-137 (ConvBNRelu, BN folded), model/backbone/darknet.py:6-15
  *                          (residual add), model/base.py:95-101 + torch.cat in
  *                          model/orienmask_yolo_fpnplus.py:78-79,85-86 (nearest upsample + concat, done
@@ -182,6 +184,65 @@ void om_conv_destroy(om_conv* conv);
  */
 int32_t om_stem_conv(int32_t precision, const float* image, const float* weights, const float* bias, void* output,
                      int32_t batch, int32_t h, int32_t w, int32_t rows, int32_t cout, int32_t out_s2d, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Pre-process (the caller side of the path: infer.py:147-151)                                   */
+/* ------------------------------------------------------------------------------------------- */
+
+#define OM_SRC_U8 0    /* uint8 HWC (what cv2.imread yields)                                     */
+#define OM_SRC_F32 1   /* float32 HWC (what infer.py:148 hands to the transform)                 */
+
+/* FastCOCOTransform(pipeline=[Resize | ShortEdgeResize, Normalize]) followed by pad(): the resized image
+ * (resize_h x resize_w, bilinear, align_corners=False) is normalised per channel and placed at
+ * (pad_top, pad_left) inside an out_h x out_w canvas filled with pad_value. */
+typedef struct om_prep_config {
+    int32_t src_h, src_w;          /* source image, layout [batch, src_h, src_w, 3]                  */
+    int32_t src_dtype;             /* OM_SRC_*                                                       */
+    int32_t resize_h, resize_w;    /* Resize.size / ShortEdgeResize result (data/transform.py:463-494) */
+    int32_t pad_top, pad_left;     /* infer.py:25 (centred: (new - old) // 2)                        */
+    int32_t out_h, out_w;          /* canvas (multiples of size_divisor)                             */
+    float mean[3], std[3];         /* Normalize (data/transform.py:496-507): (v - mean) / std        */
+    float pad_value;               /* infer.py:21, applied after normalisation                       */
+} om_prep_config;
+
+/*
+ *   src   device, uint8 or fp32 [batch, src_h, src_w, 3]; image b at src + b*src_batch_stride (elements)
+ *   out   device, fp32 NCHW [batch, 3, out_h, out_w], contiguous (the model input)
+ */
+int32_t om_preprocess(const om_prep_config* cfg, const void* src, int64_t src_batch_stride, int32_t batch, float* out,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Detections -> COCO segmentation format (the consumer side of the path: trainer/tester.py:46-50) */
+/* ------------------------------------------------------------------------------------------- */
+
+/* One image of a batch: where its instance masks live and how COCOMetrics._recover_shape_segm
+ * (eval/coco_eval.py:191-205) maps them back to the original image. */
+typedef struct om_rle_image {
+    const uint8_t* mask;           /* device, uint8 0/1 [count, mask_h, mask_w] (the post-process output)       */
+    int32_t count;                 /* instances of this image (<= max_inst)                                   */
+    int32_t mask_h, mask_w;        /* network-input size                                                      */
+    int32_t top, left;             /* first row / column kept after removing `collate_pad` and `pad`          */
+    int32_t crop_h, crop_w;        /* size of the kept window                                                 */
+    int32_t out_h, out_w;          /* sample_info['height'], ['width']: bilinear resize target, then round()  */
+    int32_t hflip, vflip;          /* torch.flip on the cropped mask before the resize                        */
+} om_rle_image;
+
+/*
+ * For every instance k < images[b].count: crop, flip, bilinear-resize (align_corners=False) and round the mask,
+ * run-length encode it in column-major order (pycocotools rleEncode: first count = leading zeros) and compress the
+ * counts into the COCO string (rleToString).  The resized mask is never materialised.
+ *   images      device [batch]
+ *   max_out_h, max_mask_h, max_mask_w   maxima over the batch of out_h, mask_h, mask_w (size the per-CTA tables)
+ * Outputs (device), instance index = b*max_inst + k:
+ *   counts   [batch*max_inst, cap]      uint32 run lengths
+ *   n_counts [batch*max_inst]           int32  number of runs; when > cap nothing else is valid for that instance
+ *                                              and the caller retries with a larger cap
+ *   str      [batch*max_inst, str_cap]  uint8  compressed counts (ASCII, no terminator)
+ *   str_len  [batch*max_inst]           int32  bytes in str, or -1 when cap or str_cap was too small
+ */
+int32_t om_mask_rle(const om_rle_image* images, int32_t batch, int32_t max_inst, int32_t max_out_h, int32_t max_mask_h,
+                    int32_t max_mask_w, int32_t cap, int32_t str_cap, uint32_t* counts, int32_t* n_counts, uint8_t* str, int32_t* str_len, void* stream);
 
 #ifdef __cplusplus
 }

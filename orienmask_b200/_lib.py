@@ -40,6 +40,23 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class PrepConfig(ctypes.Structure):
+    _fields_ = [
+        ('src_h', c_i32), ('src_w', c_i32), ('src_dtype', c_i32), ('resize_h', c_i32), ('resize_w', c_i32),
+        ('pad_top', c_i32), ('pad_left', c_i32), ('out_h', c_i32), ('out_w', c_i32),
+        ('mean', c_f32 * 3), ('std', c_f32 * 3), ('pad_value', c_f32),
+    ]
+
+
+class RleImage(ctypes.Structure):
+    _fields_ = [
+        ('mask', c_vp), ('count', c_i32), ('mask_h', c_i32), ('mask_w', c_i32), ('top', c_i32), ('left', c_i32),
+        ('crop_h', c_i32), ('crop_w', c_i32), ('out_h', c_i32), ('out_w', c_i32), ('hflip', c_i32), ('vflip', c_i32),
+    ]
+
+
+SRC_U8, SRC_F32 = 0, 1
+
 # name -> (restype, argtypes); every symbol declared in include/orienmask_b200.h
 SIGNATURES = {
     'om_abi_version': (c_i32, []),
@@ -56,6 +73,8 @@ SIGNATURES = {
     'om_conv_create': (c_i32, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_vp)]),
     'om_conv_run': (c_i32, [c_vp, c_vp]),
     'om_conv_destroy': (None, [c_vp]),
+    'om_preprocess': (c_i32, [ctypes.POINTER(PrepConfig), c_vp, c_i64, c_i32, c_vp, c_vp]),
+    'om_mask_rle': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'om_stem_conv': (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
 }
 

@@ -19,6 +19,8 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relax
 UNITS = [
     ('api.cu', []),
     ('post.cu', ['-fmad=false']),
+    ('prep.cu', ['-fmad=false']),
+    ('rle.cu', ['-fmad=false']),
     ('conv_f32.cu', []),
     ('conv_tc.cu', []),
     ('conv_tc2.cu', []),

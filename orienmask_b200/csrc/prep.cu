@@ -1,0 +1,127 @@
+// Pre-process: the step right before the model in infer.py.
+//
+//   reference                                                   here
+//   ---------                                                   ----
+//   FastCOCOTransform.__call__   data/transform.py:455-461      HWC -> CHW permute
+//   FastCOCOTransform.Resize     data/transform.py:463-474      F.interpolate(bilinear, align_corners=False)
+//   FastCOCOTransform.Normalize  data/transform.py:496-507      (v - mean) / std, fp32
+//   pad(image, 32, 0)            infer.py:21-32                 centred zero padding to a multiple of 32
+//
+// One pass: every output element is produced from <= 4 source texels, so the kernel reads the (small) HWC source through
+// L1/L2 and writes the fp32 NCHW network input once -- HBM-bound on 12 bytes out + 3 (u8) or 12 (f32) bytes in per pixel,
+// instead of the reference's permute copy + interpolate + two in-place normalisation passes + pad copy.
+//
+// Arithmetic is ATen's upsample_bilinear2d expression with one fixed fp32 rounding sequence (what torch 2.11 CPU computes at
+// 544x544 and what nvcc's default contraction gives the CUDA kernel infer.py runs; oracle/prep_oracle.py explains the pinning): scale = in/out; src = max(fma(scale, d + 0.5, -0.5), 0); i0 = (int)src; i1 = min(i0+1, in-1);
+// l1 = src - i0; l0 = 1 - l1; row = fma(l0x, v[i0], l1x * v[i1]); out = fma(l0y, row0, l1y * row1); (out - mean) / std.
+#include "common.cuh"
+
+namespace {
+
+struct PrepDev {
+    int src_h, src_w, rh, rw, top, left, out_h, out_w;
+    float scale_y, scale_x;
+    float mean[3], stdv[3], pad_value;
+    long long src_batch_stride;     // elements
+};
+
+__device__ __forceinline__ void src_index(float scale, int d, int n_in, int& i0, int& i1, float& l0, float& l1) {
+    float s = __fmaf_rn(scale, __fadd_rn((float)d, 0.5f), -0.5f);
+    s = fmaxf(s, 0.0f);
+    i0 = min((int)s, n_in - 1);
+    i1 = min(i0 + 1, n_in - 1);
+    l1 = __fsub_rn(s, (float)i0);
+    l0 = __fsub_rn(1.0f, l1);
+}
+
+template <typename T> __device__ __forceinline__ float load_px(const T* p) { return (float)__ldg(p); }
+
+// thread = 4 consecutive output pixels of one row, all three channels
+template <typename T>
+__global__ void __launch_bounds__(256) prep_kernel(PrepDev d, const T* __restrict__ src, float* __restrict__ out) {
+    const int quads = (d.out_w + 3) >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (t >= (long long)quads * d.out_h) return;
+    const int oy = (int)(t / quads), ox0 = (int)(t - (long long)oy * quads) * 4;
+    const T* img = src + (long long)b * d.src_batch_stride;
+    float v[3][4];
+    const int y = oy - d.top;
+    const bool row_in = y >= 0 && y < d.rh;
+    int y0 = 0, y1 = 0; float ly0 = 0.f, ly1 = 0.f;
+    if (row_in) src_index(d.scale_y, y, d.src_h, y0, y1, ly0, ly1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int x = ox0 + i - d.left;
+        if (row_in && x >= 0 && x < d.rw) {
+            int x0, x1; float lx0, lx1;
+            src_index(d.scale_x, x, d.src_w, x0, x1, lx0, lx1);
+            // a tap with weight 0 contributes exactly 0 (fma(1, v0, 0 * v1) == v0): skip its loads.  With src == resize
+            // size (the 544x544 workload) every pixel is a single tap, as in ATen's own identity shortcut.
+            const bool two_x = lx1 != 0.0f, two_y = ly1 != 0.0f;
+            const T* p00 = img + ((long long)y0 * d.src_w + x0) * 3;
+            const T* p01 = img + ((long long)y0 * d.src_w + x1) * 3;
+            const T* p10 = img + ((long long)y1 * d.src_w + x0) * 3;
+            const T* p11 = img + ((long long)y1 * d.src_w + x1) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float r0 = load_px(p00 + c);
+                if (two_x) r0 = __fmaf_rn(lx0, r0, __fmul_rn(lx1, load_px(p01 + c)));
+                float val = r0;
+                if (two_y) {
+                    float r1 = load_px(p10 + c);
+                    if (two_x) r1 = __fmaf_rn(lx0, r1, __fmul_rn(lx1, load_px(p11 + c)));
+                    val = __fmaf_rn(ly0, r0, __fmul_rn(ly1, r1));
+                }
+                v[c][i] = __fdiv_rn(__fsub_rn(val, d.mean[c]), d.stdv[c]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c][i] = d.pad_value;
+        }
+    }
+    const long long plane = (long long)d.out_h * d.out_w;
+    float* o = out + (long long)b * 3 * plane + (long long)oy * d.out_w + ox0;
+    if ((d.out_w & 3) == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(o + c * plane) = make_float4(v[c][0], v[c][1], v[c][2], v[c][3]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (ox0 + i < d.out_w) o[c * plane + i] = v[c][i];
+    }
+}
+
+}  // namespace
+
+extern "C" int32_t om_preprocess(const om_prep_config* cfg, const void* src, int64_t src_batch_stride, int32_t batch, float* out,
+                                 void* stream) {
+    if (!cfg || !src || !out || batch < 1) return om::fail(OM_ERR_INVALID, "om_preprocess: null argument or batch < 1");
+    if (cfg->src_dtype != OM_SRC_U8 && cfg->src_dtype != OM_SRC_F32) return om::fail(OM_ERR_INVALID, "om_preprocess: unknown src_dtype %d", cfg->src_dtype);
+    if (cfg->src_h < 1 || cfg->src_w < 1 || cfg->resize_h < 1 || cfg->resize_w < 1)
+        return om::fail(OM_ERR_INVALID, "om_preprocess: non-positive size");
+    if (cfg->pad_top < 0 || cfg->pad_left < 0 || cfg->out_h < cfg->pad_top + cfg->resize_h || cfg->out_w < cfg->pad_left + cfg->resize_w)
+        return om::fail(OM_ERR_INVALID, "om_preprocess: the resized image (%dx%d at %d,%d) does not fit the output %dx%d", cfg->resize_h,
+                        cfg->resize_w, cfg->pad_top, cfg->pad_left, cfg->out_h, cfg->out_w);
+    for (int c = 0; c < 3; ++c)
+        if (cfg->std[c] == 0.0f) return om::fail(OM_ERR_INVALID, "om_preprocess: std[%d] is zero", c);
+    if ((cfg->out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15)) return om::fail(OM_ERR_INVALID, "om_preprocess: output must be 16-byte aligned");
+    if (batch > 65535) return om::fail(OM_ERR_INVALID, "om_preprocess: batch > 65535");
+    PrepDev d;
+    d.src_h = cfg->src_h; d.src_w = cfg->src_w; d.rh = cfg->resize_h; d.rw = cfg->resize_w;
+    d.top = cfg->pad_top; d.left = cfg->pad_left; d.out_h = cfg->out_h; d.out_w = cfg->out_w;
+    d.scale_y = (float)cfg->src_h / (float)cfg->resize_h;          // area_pixel_compute_scale<float>: in / out
+    d.scale_x = (float)cfg->src_w / (float)cfg->resize_w;
+    for (int c = 0; c < 3; ++c) { d.mean[c] = cfg->mean[c]; d.stdv[c] = cfg->std[c]; }
+    d.pad_value = cfg->pad_value;
+    d.src_batch_stride = src_batch_stride;
+    const long long threads = (long long)((cfg->out_w + 3) / 4) * cfg->out_h;
+    dim3 grid((unsigned)((threads + 255) / 256), (unsigned)batch);
+    if (cfg->src_dtype == OM_SRC_U8)
+        prep_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>(d, reinterpret_cast<const unsigned char*>(src), out);
+    else
+        prep_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(d, reinterpret_cast<const float*>(src), out);
+    return om::check_launch("prep_kernel");
+}

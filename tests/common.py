@@ -160,3 +160,34 @@ def torch_conv_ref(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upad
     if residual is not None:
         y = y + residual.double()
     return y.float()
+
+
+# ---- detections -> COCO format fixtures -----------------------------------------------------------
+def blob_masks(k, height, width, seed):
+    """Seeded instance-like masks: unions of a few ellipses and axis-aligned boxes, bool [k, H, W]."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width]
+    out = np.zeros((k, height, width), dtype=bool)
+    for i in range(k):
+        for _ in range(int(rng.integers(1, 4))):
+            cy, cx = rng.uniform(0, height), rng.uniform(0, width)
+            ry, rx = rng.uniform(2, height / 3), rng.uniform(2, width / 3)
+            if rng.random() < 0.5:
+                out[i] |= ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1.0
+            else:
+                out[i] |= (np.abs(yy - cy) < ry) & (np.abs(xx - cx) < rx)
+    out[k - 1] = False                       # an empty mask
+    if k > 1:
+        out[k - 2] = True                    # a full mask (first pixel set: leading zero-length run)
+    return out
+
+
+# name -> (mask H, mask W, sample_info); collate_pad = [left, right, top, down, h, w] (infer.py:28-30),
+# pad = (top, down, left, right, h, w) (data/transform.py Resize/Pad), as eval/coco_eval.py:160-176,192-197 read them
+COCO_INFOS = {
+    'plain': (64, 96, {'id': 1, 'height': 45, 'width': 70}),
+    'collate': (64, 96, {'id': 2, 'height': 100, 'width': 131, 'collate_pad': [15, 16, 8, 8, 64, 96]}),
+    'both': (64, 96, {'id': 3, 'height': 53, 'width': 80, 'collate_pad': [0, 0, 0, 0, 64, 96], 'pad': (4, 6, 10, 0, 64, 96)}),
+    'flips': (64, 96, {'id': 4, 'height': 64, 'width': 96, 'hflip': True, 'vflip': True}),
+    'hflip_up': (32, 32, {'id': 5, 'height': 75, 'width': 50, 'pad': (0, 3, 2, 1, 32, 32), 'hflip': True}),
+}

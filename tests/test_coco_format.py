@@ -1,0 +1,163 @@
+"""Detections -> COCO format: oracle vs the reference's golden outputs and hand-derived RLE known
+answers (CPU); CUDA kernel vs oracle, bit-exact on counts and strings (GPU)."""
+import numpy as np
+import pytest
+import torch
+
+from tests.common import GOLDEN, COCO_INFOS, blob_masks
+from oracle import coco_oracle as co
+
+
+def _gold(name):
+    g = np.load(GOLDEN + '/coco_small.npz')
+    shape = tuple(int(v) for v in g[name + '_shape'])
+    segm = np.unpackbits(g[name + '_segm'])[:int(np.prod(shape))].reshape(shape)
+    return segm, g[name + '_boxes_in'], g[name + '_boxes_out']
+
+
+def _iou(a, b):
+    a, b = a.astype(bool), b.astype(bool)
+    union = (a | b).sum()
+    return 1.0 if union == 0 else float((a & b).sum()) / float(union)
+
+
+# ---- oracle pinned ---------------------------------------------------------------------------------
+def test_rle_known_answers():
+    """Hand-derived from maskApi.c (see oracle/coco_oracle.py header for the loop)."""
+    assert co.rle_encode(np.ones((2, 2), np.uint8)).tolist() == [0, 4]             # first pixel set -> empty run of zeros first
+    assert co.rle_encode(np.zeros((3, 2), np.uint8)).tolist() == [6]
+    m = np.array([[0, 1], [1, 1], [0, 0]], np.uint8)                                # column-major stream: 0 1 0 | 1 1 0
+    assert co.rle_encode(m).tolist() == [1, 1, 1, 2, 1]
+    assert co.rle_to_string([0, 4]) == b'04'                                         # 0 -> '0' (48), 4 -> '4' (52)
+    assert co.rle_to_string([100]) == b'T3'                                          # 100 = 3*32 + 4: (4 | 0x20) + 48 = 'T', 3 + 48 = '3'
+    assert co.rle_to_string([3, 5, 7, 0]) == b'357K'                                 # i = 3: 0 - 5 = -5 -> 27 + 48 = 'K'
+    assert co.rle_to_string([1, 1, 1, 50]) == b'111a1'                               # 50 - 1 = 49 = 1*32 + 17; bit 4 set and x = 1 != -1 -> more
+    assert co.rle_from_string(b'357K').tolist() == [3, 5, 7, 0]
+
+
+def test_rle_round_trips():
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        h, w = (int(v) for v in rng.integers(1, 60, 2))
+        m = (rng.random((h, w)) < rng.random()).astype(np.uint8)
+        counts = co.rle_encode(m)
+        assert int(counts.sum()) == h * w
+        text = co.rle_to_string(counts)
+        assert np.array_equal(co.rle_from_string(text), counts)
+        assert np.array_equal(co.rle_decode(counts, h, w), m)
+
+
+@pytest.mark.parametrize('name', sorted(COCO_INFOS))
+def test_oracle_matches_reference_golden(name):
+    H, W, info = COCO_INFOS[name]
+    segm, boxes_in, boxes_out = _gold(name)
+    masks = blob_masks(6, H, W, seed=len(name))
+    got = co.recover_shape_segm(masks, info)
+    assert got.shape == segm.shape
+    for k in range(got.shape[0]):
+        assert _iou(got[k], segm[k]) >= 0.999                  # north star: mask IoU >= 0.999 (interpolation ties, see oracle header)
+    assert np.abs(co.recover_shape_bbox(boxes_in, info) - boxes_out).max() <= 1e-4     # pixels, fp32 reassociation only
+
+
+def test_oracle_resize_matches_torch_round():
+    masks = blob_masks(5, 544, 544, seed=9)
+    info = {'id': 0, 'height': 480, 'width': 640}
+    ref = torch.nn.functional.interpolate(torch.from_numpy(masks).unsqueeze(0).float(), size=(480, 640), mode='bilinear',
+                                          align_corners=False).squeeze(0).round().to(torch.uint8).numpy()
+    got = co.recover_shape_segm(masks, info)
+    for k in range(5):
+        assert _iou(got[k], ref[k]) >= 0.999
+
+
+def test_host_bbox_format_matches_oracle():
+    import orienmask_b200 as ob
+    cat2label = list(range(1, 81))
+    m = ob.COCOMetrics(None, cat2label, with_mask=False, save_dir='.')
+    infos, dets, dets_np = [], [], []
+    g = torch.Generator().manual_seed(1)
+    for name, (H, W, info) in sorted(COCO_INFOS.items()):
+        bbox = torch.rand(4, 5, generator=g) * 0.5 + 0.2
+        cls = torch.randint(0, 80, (4,), generator=g)
+        infos.append(info)
+        dets.append({'bbox': bbox, 'cls': cls, 'mask': None})
+        dets_np.append({'bbox': bbox.numpy(), 'cls': cls.numpy()})
+    dets.append({'bbox': torch.zeros(0, 5), 'cls': torch.zeros(0, dtype=torch.long), 'mask': None})      # K = 0 is skipped (:133-134)
+    dets_np.append({'bbox': np.zeros((0, 5), np.float32), 'cls': np.zeros(0, np.int64)})
+    infos.append({'id': 99, 'height': 10, 'width': 10})
+    got = m.to_coco_format(infos, dets)['bbox']
+    ref = co.to_bbox_coco_format(infos, dets_np, cat2label)
+    assert len(got) == len(ref) == 20
+    for a, b in zip(got, ref):
+        assert a['image_id'] == b['image_id'] and a['category_id'] == b['category_id'] and a['score'] == b['score']
+        assert np.allclose(a['bbox'], b['bbox'], atol=1e-4)
+
+
+# ---- GPU -------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_kernel_matches_oracle_golden_cases():
+    import orienmask_b200 as ob
+    cat2label = list(range(1, 81))
+    metrics = ob.COCOMetrics(None, cat2label, with_mask=True, save_dir='.')
+    infos, dets, dets_np = [], [], []
+    for name, (H, W, info) in sorted(COCO_INFOS.items()):
+        masks = blob_masks(6, H, W, seed=len(name))
+        g = torch.Generator().manual_seed(7)
+        bbox = torch.rand(6, 5, generator=g)
+        cls = torch.randint(0, 80, (6,), generator=g)
+        infos.append(info)
+        dets.append({'bbox': bbox.cuda(), 'cls': cls.cuda(), 'mask': torch.from_numpy(masks).cuda()})
+        dets_np.append({'bbox': bbox.numpy(), 'cls': cls.numpy(), 'mask': masks})
+    dets.insert(2, {'bbox': torch.zeros(0, 5).cuda(), 'cls': torch.zeros(0, dtype=torch.long).cuda(), 'mask': torch.zeros(0, 64, 96, dtype=torch.bool).cuda()})
+    dets_np.insert(2, {'bbox': np.zeros((0, 5), np.float32), 'cls': np.zeros(0, np.int64), 'mask': np.zeros((0, 64, 96), bool)})
+    infos.insert(2, {'id': 42, 'height': 30, 'width': 40})
+    got = metrics.to_coco_format(infos, dets)
+    ref = co.to_segm_coco_format(infos, dets_np, cat2label)
+    assert len(got['segm']) == len(ref) == 30
+    for a, b in zip(got['segm'], ref):
+        assert a['image_id'] == b['image_id'] and a['category_id'] == b['category_id'] and a['score'] == b['score']
+        assert a['segmentation']['size'] == b['segmentation']['size']
+        assert a['segmentation']['counts'] == b['segmentation']['counts']               # bit-exact strings
+    # and against the reference's own recovered masks (golden), through the decoder
+    i = 0
+    for name, (H, W, info) in sorted(COCO_INFOS.items()):
+        segm, _, _ = _gold(name)
+        rows = [r for r in got['segm'] if r['image_id'] == info['id']]
+        for k, r in enumerate(rows):
+            h, w = r['segmentation']['size']
+            dec = co.rle_decode(co.rle_from_string(r['segmentation']['counts']), h, w)
+            assert _iou(dec, segm[k]) >= 0.999
+        i += 1
+
+
+@pytest.mark.gpu
+def test_kernel_full_size_round_trip_and_overflow_retry():
+    """544x544 masks of the real post-process -> 480x640 originals; a tiny initial cap forces the retry path."""
+    from orienmask_b200.coco_format import encode_masks
+    masks = blob_masks(12, 544, 544, seed=4)
+    noisy = np.random.default_rng(1).random((544, 544)) < 0.5
+    masks[3] = noisy                                                   # tens of thousands of runs
+    info = {'id': 0, 'height': 480, 'width': 640, 'collate_pad': [0, 0, 0, 0, 544, 544]}
+    enc = encode_masks([torch.from_numpy(masks).cuda()], [12], [info], cap=64)[0]
+    ref = co.recover_shape_segm(masks, info)
+    for k in range(12):
+        counts = co.rle_from_string(enc[k]['counts'])
+        assert np.array_equal(counts, co.rle_encode(ref[k]))
+        assert np.array_equal(co.rle_decode(counts, 480, 640), ref[k])                   # encode -> decode round trip
+
+
+@pytest.mark.gpu
+def test_post_process_output_feeds_formatter():
+    """The post-process's own list-of-dicts result (bool mask views into the padded buffer) goes straight in."""
+    import functools
+    import orienmask_b200 as ob
+    from tests.common import synthetic_heads, post_config
+    post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5), device=torch.device('cuda:0'),
+                                       **post_config(64, 96, 0.005))
+    heads = [(b.cuda(), o.cuda()) for b, o in synthetic_heads(2, 64, 96, seed=5)]
+    dets = post(heads)
+    infos = [{'id': 7, 'height': 50, 'width': 75, 'collate_pad': [0, 0, 0, 0, 64, 96]}, {'id': 8, 'height': 64, 'width': 96}]
+    out = ob.COCOMetrics(None, list(range(1, 81)), True, '.').to_coco_format(infos, dets)
+    dets_np = [{k: v.cpu().numpy() for k, v in d.items()} for d in dets]
+    ref = co.to_segm_coco_format(infos, dets_np, list(range(1, 81)))
+    assert [r['segmentation'] for r in out['segm']] == [r['segmentation'] for r in ref]
+    assert len(out['bbox']) == len(out['segm']) == sum(d['bbox'].shape[0] for d in dets)
