@@ -31,7 +31,7 @@ def _crop_window(info, H, W):
     return int(top), int(left), int(h), int(w)
 
 
-def encode_masks(masks, counts, infos, cap=2048):
+def encode_masks(masks, counts, infos, cap=4096):
     """RLE strings of every instance of a batch.
 
     masks   list (per image) of uint8/bool CUDA tensors [>= counts[b], H, W] (contiguous), or None where counts[b] == 0

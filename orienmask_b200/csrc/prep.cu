@@ -40,10 +40,11 @@ template <typename T> __device__ __forceinline__ float load_px(const T* p) { ret
 template <typename T>
 __global__ void __launch_bounds__(256) prep_kernel(PrepDev d, const T* __restrict__ src, float* __restrict__ out) {
     const int quads = (d.out_w + 3) >> 2;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (t >= (long long)quads * d.out_h) return;
-    const int oy = (int)(t / quads), ox0 = (int)(t - (long long)oy * quads) * 4;
+    const int b = blockIdx.z;
+    const int oy = blockIdx.y;                                     // one output row per blockIdx.y: no per-thread division
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= quads) return;
+    const int ox0 = q * 4;
     const T* img = src + (long long)b * d.src_batch_stride;
     float v[3][4];
     const int y = oy - d.top;
@@ -117,11 +118,13 @@ extern "C" int32_t om_preprocess(const om_prep_config* cfg, const void* src, int
     for (int c = 0; c < 3; ++c) { d.mean[c] = cfg->mean[c]; d.stdv[c] = cfg->std[c]; }
     d.pad_value = cfg->pad_value;
     d.src_batch_stride = src_batch_stride;
-    const long long threads = (long long)((cfg->out_w + 3) / 4) * cfg->out_h;
-    dim3 grid((unsigned)((threads + 255) / 256), (unsigned)batch);
+    const int quads = (cfg->out_w + 3) / 4;
+    const int block = quads >= 128 ? 128 : (quads >= 64 ? 64 : 32);
+    if (cfg->out_h > 65535) return om::fail(OM_ERR_INVALID, "om_preprocess: out_h > 65535");
+    dim3 grid((unsigned)((quads + block - 1) / block), (unsigned)cfg->out_h, (unsigned)batch);
     if (cfg->src_dtype == OM_SRC_U8)
-        prep_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>(d, reinterpret_cast<const unsigned char*>(src), out);
+        prep_kernel<unsigned char><<<grid, block, 0, (cudaStream_t)stream>>>(d, reinterpret_cast<const unsigned char*>(src), out);
     else
-        prep_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(d, reinterpret_cast<const float*>(src), out);
+        prep_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(d, reinterpret_cast<const float*>(src), out);
     return om::check_launch("prep_kernel");
 }

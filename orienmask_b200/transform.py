@@ -44,7 +44,28 @@ def pad(image, size_divisor=32, pad_value=0):
     return image, info
 
 
+class _Step:
+    """Parameter holder with the reference's nested-class names, so ``trainer/builder.py:108-115`` (which builds every
+    pipeline item as ``getattr(transform_class, item['type'])(**item)``) works on this class unchanged."""
+
+    def __repr__(self):
+        return '%s(%s)' % (type(self).__name__, ', '.join('%s=%r' % kv for kv in vars(self).items()))
+
+
 class FastCOCOTransform:
+    class Resize(_Step):                               # data/transform.py:463-474
+        def __init__(self, size, interpolation='bilinear', align_corners=False):
+            self.size, self.interpolation, self.align_corners = _pair(size), interpolation, align_corners
+
+    class ShortEdgeResize(_Step):                      # data/transform.py:476-494
+        def __init__(self, short_length, max_size, interpolation='bilinear', align_corners=False):
+            self.short_length, self.max_size = short_length, max_size
+            self.interpolation, self.align_corners = interpolation, align_corners
+
+    class Normalize(_Step):                            # data/transform.py:496-507
+        def __init__(self, mean, std):
+            self.mean, self.std = mean, std
+
     def __init__(self, pipeline, use_cuda=True):
         if not use_cuda:
             raise RuntimeError('orienmask_b200.FastCOCOTransform runs on CUDA only; there is no CPU path')
@@ -81,14 +102,15 @@ class FastCOCOTransform:
         scale = min(short_length / min(h, w), max_size / max(h, w))
         return int(h * scale + 0.5), int(w * scale + 0.5)
 
-    def __call__(self, image):
-        return self._run(image, None, 0.0)[0]
+    def __call__(self, image, out=None):
+        return self._run(image, None, 0.0, out)[0]
 
-    def transform_and_pad(self, image, size_divisor=32, pad_value=0):
-        """``pad(transform(image))`` of infer.py:149-150 in the same single pass; returns (image, pad_info)."""
-        return self._run(image, size_divisor, pad_value)
+    def transform_and_pad(self, image, size_divisor=32, pad_value=0, out=None):
+        """``pad(transform(image))`` of infer.py:149-150 in the same single pass; returns (image, pad_info).
+        ``out``: optional preallocated fp32 [n, 3, H, W] result (a serving loop reuses its input buffer)."""
+        return self._run(image, size_divisor, pad_value, out)
 
-    def _run(self, image, size_divisor, pad_value):
+    def _run(self, image, size_divisor, pad_value, out=None):
         if not isinstance(image, torch.Tensor) or not image.is_cuda:
             raise RuntimeError('orienmask_b200.FastCOCOTransform needs a CUDA tensor, got %s; there is no CPU path'
                                % getattr(image, 'device', type(image)))
@@ -112,7 +134,11 @@ class FastCOCOTransform:
         for c in range(3):
             cfg.mean[c], cfg.std[c] = self.mean[c], self.std[c]
         cfg.pad_value = float(pad_value)
-        out = torch.empty(n, 3, info[4], info[5], dtype=torch.float32, device=image.device)
+        if out is None:
+            out = torch.empty(n, 3, info[4], info[5], dtype=torch.float32, device=image.device)
+        elif (tuple(out.shape) != (n, 3, info[4], info[5]) or out.dtype != torch.float32 or out.device != image.device
+              or not out.is_contiguous()):
+            raise ValueError('out must be a contiguous fp32 [%d, 3, %d, %d] tensor on %s' % (n, info[4], info[5], image.device))
         with torch.cuda.device(image.device):
             _lib.check(_lib.lib().om_preprocess(cfg, _lib.ptr(image), image.stride(0), n, _lib.ptr(out), _lib.stream_ptr()),
                        'om_preprocess')

@@ -64,6 +64,11 @@ def test_host_mirror_geometry_and_errors():
         t(torch.zeros(1, 37, 50, 3))                                            # CPU tensor: no fallback
     with pytest.raises(NotImplementedError):
         ob.FastCOCOTransform([dict(type='Resize', size=8, interpolation='nearest')])
+    # trainer/builder.py:108-115 builds every pipeline item as getattr(transform_class, type)(**kwargs)
+    cfg = [dict(type='Resize', size=(544, 544), interpolation='bilinear', align_corners=False),
+           dict(type='Normalize', mean=(0, 0, 0), std=(255, 255, 255))]                    # config/base.py:158-164
+    built = ob.FastCOCOTransform(pipeline=[getattr(ob.FastCOCOTransform, c.pop('type'))(**c) for c in [dict(i) for i in cfg]], use_cuda=True)
+    assert built.resize == ('fixed', (544, 544)) and built.std == (255.0, 255.0, 255.0)
     x, info = ob.pad(torch.zeros(1, 3, 48, 65))
     assert tuple(x.shape) == (1, 3, 64, 96) and info == [15, 16, 8, 8, 64, 96]
 

@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 what="${*:-tests bench ncu}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 if [[ $what == *tests* ]]; then
-  for f in post conv forward; do
-    timeout 900 python -m pytest tests/test_gpu_$f.py -q -m gpu -x --timeout 600 > gpurun_out/test_$f.log 2>&1
+  for f in post conv forward prep coco_format; do
+    timeout 900 python -m pytest $( [[ $f == prep || $f == coco_format ]] && echo tests/test_$f.py || echo tests/test_gpu_$f.py ) -q -m gpu -x --timeout 600 > gpurun_out/test_$f.log 2>&1
     echo "test_gpu_$f exit $?"; tail -4 gpurun_out/test_$f.log
   done
 fi
@@ -41,4 +41,13 @@ if [[ $what == *abtest* ]]; then
     env ${AB_VAR:-ORIENMASK_B200_PDL}=$v timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ab_$v.log 2>&1
     echo "${AB_VAR:-ORIENMASK_B200_PDL}=$v: $(python -c "import json,sys; d=json.loads(open('gpurun_out/bench_ab_$v.log').read().strip().splitlines()[-1]); print(round(d['value'],1), 'img/s', round(d['ms_per_step'],3), 'ms', d['roofline']['kernel'][-40:])" 2>&1 | tail -1)"
   done
+fi
+if [[ $what == *fullx* ]]; then
+  # extra full captures: a flat-tile (im2col) layer, the RLE kernel, the pre-process kernel
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:conv_tc2_kernel -s 44 -c 1 -f -o gpurun_out/prof_conv_flat \
+      python tools/profile_step.py --steps 2 > gpurun_out/ncu_full_flat.log 2>&1; echo "ncu full flat exit $?"
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:mask_rle_kernel -c 1 -f -o gpurun_out/prof_rle \
+      python tools/profile_step.py --steps 2 > gpurun_out/ncu_full_rle.log 2>&1; echo "ncu full rle exit $?"
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:prep_kernel -c 1 -f -o gpurun_out/prof_prep \
+      python tools/profile_step.py --steps 2 > gpurun_out/ncu_full_prep.log 2>&1; echo "ncu full prep exit $?"
 fi

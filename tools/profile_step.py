@@ -18,6 +18,7 @@ ap.add_argument('--steps', type=int, default=2)
 ap.add_argument('--batch', type=int, default=32)
 ap.add_argument('--precision', default='fp16')
 ap.add_argument('--size', type=int, default=544)
+ap.add_argument('--coco', type=int, default=1, help='also run the detections -> COCO RLE kernel inside the profiled region')
 ap.add_argument('--events', type=int, default=0, help='also time every layer with CUDA events over this many passes')
 a = ap.parse_args()
 dev = torch.device('cuda:0')
@@ -29,8 +30,23 @@ kw = post_kwargs()
 kw['grid_size'] = [[a.size // s, a.size // s] for s in (32, 16, 8)]
 kw['image_size'] = [a.size, a.size]
 post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5), device=dev, **kw)
-x = synthetic_images(a.batch, a.size, a.size, seed=1).to(dev)
-out = post.apply_padded(model(x))            # un-profiled warm-up: builds the engine (BN folding etc. are torch ops)
+# the step as infer.py / test.py run it: uint8 HWC image -> transform -> model -> post-process -> COCO RLE strings
+from orienmask_b200.coco_format import encode_masks  # noqa: E402
+u8 = (synthetic_images(a.batch, a.size, a.size, seed=1) * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().to(dev)
+transform = ob.FastCOCOTransform([dict(type='Resize', size=(a.size, a.size)), dict(type='Normalize', mean=(0, 0, 0), std=(255, 255, 255))])
+infos = [{'id': i, 'height': 480 * a.size // 544, 'width': 640 * a.size // 544, 'collate_pad': [0, 0, 0, 0, a.size, a.size]} for i in range(a.batch)]
+
+
+def full_step():
+    out = post.apply_padded(model(transform(u8)))
+    if a.coco:
+        dets = out.to_list()
+        encode_masks([d['mask'] for d in dets], [int(d['bbox'].shape[0]) for d in dets], infos)
+    return out
+
+
+x = transform(u8)
+out = full_step()            # un-profiled warm-up: builds the engine (BN folding etc. are torch ops)
 torch.cuda.synchronize()
 eng = next(iter(model._engines.values()))
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
@@ -40,7 +56,7 @@ if a.events:
     json.dump(eng.time_layers(x, a.events), open(os.path.join(ROOT, 'gpurun_out', 'layer_events.json'), 'w'))
 torch.cuda.cudart().cudaProfilerStart()      # ncu --profile-from-start off
 for _ in range(a.steps):
-    out = post.apply_padded(model(x))
+    out = full_step()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print('instances per image:', out.count.tolist()[:8])
