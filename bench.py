@@ -178,7 +178,7 @@ def measure_stages(torch, ob, transform, host_u8, out, dev, iters=10):
                          'what': 'uint8 HWC [%d,%d,%d,3] -> fp32 NCHW, one prep_kernel launch' % tuple(x.shape[:3])}
     dets = out.to_list()
     counts = [int(d['bbox'].shape[0]) for d in dets]
-    infos = [{'id': i, 'height': 480, 'width': 640, 'collate_pad': [0, 0, 0, 0, H, W]} for i in range(len(dets))]
+    infos = [{'id': i, 'height': 480 * H // 544, 'width': 640 * W // 544, 'collate_pad': [0, 0, 0, 0, H, W]} for i in range(len(dets))]
     masks = [d['mask'] for d in dets]
     lib = _lib.lib()
     lib.om_launch_count_reset()
@@ -201,7 +201,7 @@ def measure_stages(torch, ob, transform, host_u8, out, dev, iters=10):
     text = sum(len(e['counts']) for im in enc for e in im)
     res['coco_format'] = {'ms_host_to_strings': min(ev), 'first_call_ms': wall_ms, 'instances': sum(counts), 'mask_bytes_read': nbytes,
                           'rle_text_bytes': text, 'GBps_end_to_end': nbytes / min(ev) / 1e6, 'launches': launches,
-                          'what': 'bool masks [K,%d,%d] -> crop/resize to 480x640 -> round -> column-major RLE -> COCO strings on the '
+                          'what': 'bool masks [K,%d,%d] -> crop/resize to the 4:3 original -> round -> column-major RLE -> COCO strings on the '
                                   'device (mask_rle_kernel), strings to host' % (H, W)}
     return res
 
@@ -216,7 +216,14 @@ def main():
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--size', type=int, default=544, help='square input size (960 with --batch 8 = config 5); the headline metric is 544')
     args = ap.parse_args()
+    global H, W, GFLOP_PER_IMAGE
+    if args.size != H:
+        from orienmask_b200.arch import macs_per_image
+        H = W = args.size
+        GFLOP_PER_IMAGE = 2e-9 * macs_per_image(H, W)[0]
+        args.no_cpu_baseline = True
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))
@@ -344,13 +351,13 @@ def main():
             'metric': METRIC, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f16' if args.precision == 'fp16' else 'f32', 'data': 'synthetic',
-            'config': {'workload': 'bs=%d 544x544 per GPU: DarkNet-53+FPNPlus forward + decode + batched NMS + mask assembly' % B,
+            'config': {'workload': 'bs=%d %dx%d per GPU: DarkNet-53+FPNPlus forward + decode + batched NMS + mask assembly' % (B, H, W),
                        'global_batch': B * world, 'parallelism': 'dp%d' % world, 'weights': 'synthetic_state_dict(seed 0)',
                        'l2': 'two alternating resident batches; per-step activation traffic (>10 GB) >> 126 MB L2',
                        'precision': 'fp16 storage / fp32 accumulate convs, fp32 heads + post-process' if args.precision == 'fp16' else 'fp32',
                        'avg_instances_per_image': k_avg},
             'e2e': {'value': world * B * args.steps / e2e_s, 'unit': 'images/sec',
-                    'h2d_bytes_per_step': int(host[0].numel() * host[0].element_size()),
+                    'h2d_bytes_per_step': int(host[0].numel() * host[0].element_size()) * world,
                     'd2h_bytes_per_step': int(rec_host.numel() * 4 + cnt_host.numel() * 4),
                     'note': 'pinned uint8 HWC images (cv2 layout) -> FastCOCOTransform -> model() -> postprocess -> detection records + '
                             'counts to host; copies double-buffered on a side stream'},

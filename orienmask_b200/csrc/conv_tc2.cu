@@ -42,6 +42,11 @@ struct Tc2Params {
     int block_n, half_n;                 // UMMA N and the rows of it each CTA stages
     int cout_pad;
     int halo;                            // 3x3 stride 1 with tw == 8: one halo box per chunk feeds all nine taps
+    int halo_s2;                         // halo mode for a stride-2 3x3 over a parity-split input: one (tw+1) x (th+1) box per parity plane
+                                         // and chunk (4 boxes instead of 9 tap boxes); tap (r, s) reads plane 2*(r!=1) + (s!=1) at offset
+                                         // ((r!=0), (s!=0)) inside the box
+    int halo_pitch;                      // pixels per row of a halo box: tw + 2 (stride 1) or tw + 1 (stride 2)
+    int halo_planes;                     // boxes per chunk: 1 or 4
     int b_resident;                      // halo mode, all weights of the layer fit: loaded once, no block ring at all
     int n_sub;                           // (tap, chunk) blocks per pipeline stage
     int stages;                          // depth of the block ring
@@ -535,7 +540,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             int st = 0; uint32_t s_phase = 0;
             int hs = 0; uint32_t h_phase = 0;
             const uint32_t s_tx = 2u * (uint32_t)p.n_sub * (uint32_t)((p.halo ? 0 : p.a_box_pixels * BK * 2) + b_sub);
-            const uint32_t h_tx = 2u * (uint32_t)p.k_chunks * (uint32_t)(p.a_box_pixels * BK * 2);
+            const uint32_t h_tx = 2u * (uint32_t)(p.k_chunks * p.halo_planes) * (uint32_t)(p.a_box_pixels * BK * 2);
             if (p.b_resident) {                               // the whole weight tensor (this CTA's half of the rows), once
                 const uint32_t lb = mapa(smem_u32(&s_full[0]), 0);
                 if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[0], 2u * (uint32_t)(p.taps * p.k_chunks * b_sub));
@@ -557,8 +562,10 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     const uint32_t lb = mapa(smem_u32(&h_full[hs]), 0);
                     if (pair == first_pair) { pdl_wait(); tick(2, lane == 0); }
                     if (lane == 0 && rank == 0) mbar_expect_tx(&h_full[hs], h_tx);
-                    if (lane < p.k_chunks)
-                        tma_load_3d_pair(h_ring + (size_t)hs * p.h_stage_bytes + (size_t)lane * p.h_chunk_bytes, &map_a0, lb, lane * BK, x0 - 1, y0 - 1);
+                    if (lane < p.k_chunks * p.halo_planes) {       // buffer order: [plane][chunk]; plane coordinates == output coordinates
+                        const int plane = lane / p.k_chunks, kc = lane - plane * p.k_chunks;
+                        tma_load_3d_pair(h_ring + (size_t)hs * p.h_stage_bytes + (size_t)lane * p.h_chunk_bytes, &maps_a.m[plane], lb, kc * BK, x0 - 1, y0 - 1);
+                    }
                     __syncwarp();
                     if (++hs == p.h_stages) { hs = 0; h_phase ^= 1; }
                 }
@@ -605,11 +612,16 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             constexpr uint32_t pixel_bytes = BK * 2;
             constexpr uint64_t kLayout = (BK == 64) ? 2 : 4;
             const uint64_t hi_b = ((uint64_t)((8 * pixel_bytes) >> 4) << 32) | (1ull << 16) | (1ull << 46) | (kLayout << 61);
-            const uint64_t hi_a = p.halo ? (((uint64_t)(((uint32_t)(p.tw + 2) * pixel_bytes) >> 4) << 32) | (1ull << 16) | (1ull << 46) | (kLayout << 61)) : hi_b;
+            const uint64_t hi_a = p.halo ? (((uint64_t)(((uint32_t)p.halo_pitch * pixel_bytes) >> 4) << 32) | (1ull << 16) | (1ull << 46) | (kLayout << 61)) : hi_b;
+            // descriptor offset (16-byte units) of filter tap (r, s) inside the tile's halo stage
+            const uint32_t plane16 = (uint32_t)p.k_chunks * ((uint32_t)p.h_chunk_bytes >> 4);
+            auto tap_off = [&](int r, int s) -> uint32_t {
+                if (p.halo_s2) return (uint32_t)(2 * (r != 1) + (s != 1)) * plane16 + (uint32_t)((r != 0) * p.halo_pitch + (s != 0)) * (pixel_bytes >> 4);
+                return (uint32_t)(r * p.halo_pitch + s) * (pixel_bytes >> 4);
+            };
             const uint32_t s_ring_addr = smem_u32(s_ring), h_ring_addr = smem_u32(h_ring);
             const uint32_t sub16 = (uint32_t)sub_bytes >> 4, asub16 = (uint32_t)a_sub >> 4, bsub16 = (uint32_t)b_sub >> 4;
             const uint32_t hchunk16 = (uint32_t)p.h_chunk_bytes >> 4;
-            constexpr uint32_t px16 = pixel_bytes >> 4;            // one pixel of a halo row in descriptor units
             if (p.b_resident) mbar_wait(&s_full[0], 0);
             for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
                 mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -625,7 +637,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                         uint64_t bd = hi_b | (uint64_t)((s_ring_addr & 0x3FFFF) >> 4);
 #pragma unroll
                         for (int tap = 0; tap < 9; ++tap) {
-                            uint64_t ad = ad_tile + (uint64_t)(((tap / 3) * 10 + (tap % 3)) * px16);   // tw + 2 == 10
+                            uint64_t ad = ad_tile + (uint64_t)tap_off(tap / 3, tap % 3);
                             for (int kc = 0; kc < p.k_chunks; ++kc) {
 #pragma unroll
                                 for (int k = 0; k < BK / 16; ++k)
@@ -637,7 +649,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     __syncwarp();
                 } else {
                     uint32_t accumulate = 0;
-                    uint32_t tap_off16 = 0; int tap_s = 0, kc = 0;   // halo: descriptor offset of the current tap, its column, chunk
+                    uint32_t tap_off16 = p.halo ? tap_off(0, 0) : 0; int tap_r = 0, tap_s = 0, kc = 0;   // halo: descriptor offset of the current tap, its row / column, chunk
                     for (int g = 0; g < n_groups; ++g) {
                         mbar_wait(&s_full[st], s_phase);
                         if (pair == first_pair && g == 0) tick(4, lane == 0);
@@ -654,9 +666,10 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                             }
                             accumulate = 1;
                             bd += sub16; ad_ring += sub16;
-                            if (++kc == p.k_chunks) {       // next tap: +1 pixel, or to the start of the next halo row (+10 - 2)
+                            if (++kc == p.k_chunks) {       // next tap
                                 kc = 0;
-                                if (++tap_s == 3) { tap_s = 0; tap_off16 += 8 * px16; } else tap_off16 += px16;
+                                if (++tap_s == 3) { tap_s = 0; ++tap_r; }
+                                if (p.halo) tap_off16 = tap_off(tap_r, tap_s);
                             }
                         }
                         if (elect_one()) umma_commit_pair(&s_empty[st]);
@@ -717,6 +730,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
         }
         else if (p.out_kind == OM_OUT_NCHW) epilogue_loop<2, 0, false>(p, c);
         else if (p.out_kind == OM_OUT_PARTIAL) { if (p.has_res == 2) epilogue_loop<1, 2, false>(p, c); else epilogue_loop<1, 0, false>(p, c); }
+        else if (p.res_direct) epilogue_loop<0, 3, false>(p, c);
         else if (p.has_res == 1) epilogue_loop<0, 1, false>(p, c);
         else if (p.has_res == 2) epilogue_loop<0, 2, false>(p, c);
         else epilogue_loop<0, 0, false>(p, c);
@@ -868,6 +882,17 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
         const long long flat_pairs = ((p.flat_total + kBlockM - 1) / kBlockM + 1) / 2;
         if (flat_pairs * (cout_pad / bn) > 10ll * (sms / 2)) p.flat = 0;
     }
+    p.halo_s2 = d.ksize == 3 && d.stride == 2 && d.in_s2d && d.out_kind != OM_OUT_NCHW && (d.out_w % 8 == 0 || d.out_w >= 64) &&
+                !(halo_env && halo_env[0] == '0') && !getenv("ORIENMASK_B200_NO_HALO_S2");
+    if (p.halo_s2) {
+        // only where all weights stay resident next to two halo stages (the 32 -> 64 layer): with a weight ring the four plane
+        // boxes leave too few stages and the layer gets slower than with per-tap boxes (64 -> 128 @136: 113 -> 165 us)
+        const size_t chunk = ((size_t)(9 * 17) * bk * 2 + 1023) / 1024 * 1024;
+        const size_t need = 2 * 4 * (d.cin / bk) * chunk + (size_t)9 * (d.cin / bk) * (bn / 2) * bk * 2 + 8 * 1024;
+        if (cout_pad / bn != 1 || need > 227 * 1024) p.halo_s2 = 0;
+    }
+    if (p.halo_s2) p.halo = 1;
+    p.halo_planes = p.halo_s2 ? 4 : 1;
     if (p.halo) { p.tw = 8; p.th = 16; p.tiles_x = (d.out_w + 7) / 8; }
     else if (p.flat) { p.tw = kBlockM; p.th = 1; p.tiles_x = 1; }
     else { p.tw = pick_tile_w(d.out_w, d.out_kind == OM_OUT_NCHW); p.th = kBlockM / p.tw; p.tiles_x = d.out_w / p.tw; }
@@ -875,9 +900,16 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     const int tiles_y = p.flat ? (p.flat_total + kBlockM - 1) / kBlockM : (p.total_rows + p.th - 1) / p.th;
     p.pairs_y = (tiles_y + 1) / 2;
     p.taps = d.ksize * d.ksize; p.stride = d.stride; p.k_chunks = d.cin / bk;
-    p.res_direct = (d.residual != nullptr && p.flat) ? 1 : 0;
-    p.residual = d.residual;
-    p.has_res = (d.residual != nullptr && !p.flat) ? 1 : 0;
+    {
+        // the fp16 residual: staged by TMA for the memory-bound layers (its DRAM latency must be covered several chunks ahead),
+        // read by the epilogue threads themselves in flat mode and (experiment: ORIENMASK_B200_RESDIRECT=1) on tensor-bound tiles
+        const char* rd = getenv("ORIENMASK_B200_RESDIRECT");
+        const int cycles = d.ksize * d.ksize * (d.cin / bk) * (bk / 16) * (bn / 2);
+        const bool direct = p.flat || (rd && rd[0] == '1' && cycles >= 8192);
+        p.res_direct = (d.residual != nullptr && direct) ? 1 : 0;
+        p.residual = d.residual;
+        p.has_res = (d.residual != nullptr && !direct) ? 1 : 0;
+    }
     p.up_bw = p.tw / 2 + 1; p.up_bh = p.th / 2 + 1;
     if (d.upadd != nullptr && !p.has_res && d.up_rows * 2 == d.out_rows && d.cout % 32 == 0 && p.up_bw * p.up_bh <= kStageRows)
         p.has_res = 2;
@@ -886,9 +918,10 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     const int tile_cycles_est = p.taps * p.k_chunks * (bk / 16) * (bn / 2);
     p.chunk_cols = (p.has_res == 1 && bn >= 64 && tile_cycles_est < 8192) ? 64 : 32; p.row_bytes = p.has_res == 1 ? p.chunk_cols * 2 : 128;
     p.res_buf_bytes = kStageRows * p.row_bytes;
-    p.a_box_pixels = p.halo ? (p.tw + 2) * (p.th + 2) : p.tw * p.th;
+    p.halo_pitch = p.halo_s2 ? p.tw + 1 : p.tw + 2;
+    p.a_box_pixels = p.halo_s2 ? (p.tw + 1) * (p.th + 1) : p.halo ? (p.tw + 2) * (p.th + 2) : p.tw * p.th;
     p.h_chunk_bytes = p.halo ? ((p.a_box_pixels * bk * 2 + 1023) / 1024) * 1024 : 0;
-    p.h_stage_bytes = p.h_chunk_bytes * p.k_chunks;
+    p.h_stage_bytes = p.h_chunk_bytes * p.k_chunks * p.halo_planes;
     p.h_stages = p.halo ? 2 : 0;
     if (p.halo && getenv("ORIENMASK_B200_HSTAGES")) p.h_stages = atoi(getenv("ORIENMASK_B200_HSTAGES"));
     // per-tap activation block: the tw*th-row box rounded up to the 1024-byte swizzle period (the MMA reads 128 rows; rows
@@ -967,7 +1000,7 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
             const int py = sel >> 1, px = sel & 1;
             cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w / 2, (cuuint64_t)d.batch * d.in_rows / 2};
             cuuint64_t str[2] = {(cuuint64_t)2 * d.cin * esz, (cuuint64_t)2 * d.in_w * d.cin * esz};
-            cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)p.tw, (cuuint32_t)p.th};
+            cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(p.halo_s2 ? p.tw + 1 : p.tw), (cuuint32_t)(p.halo_s2 ? p.th + 1 : p.th)};
             const char* base = reinterpret_cast<const char*>(d.input) + ((size_t)py * d.in_w + px) * d.cin * esz;
             if (d.in_s2d) {                                   // dense parity planes: every tap is a contiguous box
                 str[0] = (cuuint64_t)d.cin * esz; str[1] = (cuuint64_t)(d.in_w / 2) * d.cin * esz;
