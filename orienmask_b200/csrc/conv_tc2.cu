@@ -122,7 +122,11 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     // default (.release.cta) semantics: a cluster-scope release would drain every global store in flight first
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.  The slow path passes a suspend-time hint:
+// the warp is parked by the hardware until the phase completes or the hint expires instead of re-issuing try_wait (with 15 of
+// the 19 warps waiting on something at any time, polling took half of the issue slots of the memory-bound layers away from
+// the four epilogue warps that had work: ncu, 1x1 64->32 @272: 3850 warp instructions per tile at IPC 2).
+__device__ unsigned int g_wait_hint_ns = 20000;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     {
@@ -134,14 +138,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) return;
     }
+    const unsigned int hint = g_wait_hint_ns;
     const long long t0 = clock64();
     while (true) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(ok) : "r"(addr), "r"(parity), "r"(hint) : "memory");
         if (ok) return;
         if (clock64() - t0 > 4000000000ll) __trap();
     }
@@ -309,6 +314,21 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
     int rslot = 0; uint32_t rphase = 0;                 // this group's addend slot and its phase
     int g0 = 0;                                          // sequence number (mod kEpiGroups) of the tile's first chunk
     for (int pair = c.first_pair; pair < c.num_pairs; pair += c.pair_step) {
+        if (pair == c.first_pair) pdl_wait();          // while the first accumulator is still being produced
+        const int j_first = (grp - g0) & (kEpiGroups - 1);
+        if (j_first >= n_chunks) {
+            // Narrow tiles (N = 32 / 64) give work to one or two of the four groups; the others only keep the accumulator
+            // barrier in step, without the tile's coordinate arithmetic (with all 16 warps doing it, a memory-bound 1x1
+            // 64 -> 32 tile cost 3850 warp instructions at IPC 2: issue-bound, not HBM-bound).
+            mbar_wait(&c.tmem_full[as], aphase);
+            tc_fence_after();
+            tc_fence_before();
+            __syncwarp();
+            if (c.lane == 0) mbar_arrive_cluster(c.leader_tmem_empty0 + (uint32_t)(as * 8));
+            g0 = (g0 + n_chunks) & (kEpiGroups - 1);
+            if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
+            continue;
+        }
         const PairCoord t = decode_pair(p, pair);
         int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)c.rank) * p.th;
         int Y = y0 + my, x = x0 + mx;
@@ -323,8 +343,6 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
             Y = img * p.out_rows + y;
         }
         const int n0 = t.tn * p.block_n;
-        if (pair == c.first_pair) pdl_wait();          // while the first accumulator is still being produced
-        const int j_first = (grp - g0) & (kEpiGroups - 1);
         uint4 rr[4] = {};
         const __half* rsrc = nullptr;
         if (ADD == 3) {
@@ -340,11 +358,6 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
         if (ADD == 0 && KIND != 2 && p.upadd != nullptr && valid)
             up = p.upadd + ((size_t)(img * p.up_rows + (y >> 1)) * (p.out_w >> 1) + (x >> 1)) * p.cout;
         const int up_row = ((Y >> 1) - (y0 >> 1)) * p.up_bw + ((x >> 1) - (x0 >> 1));   // source pixel inside the staged box
-        if (j_first >= n_chunks) {                        // nothing for this group in this tile: release at once
-            tc_fence_before();
-            __syncwarp();
-            if (c.lane == 0) mbar_arrive_cluster(c.leader_tmem_empty0 + (uint32_t)(as * 8));
-        }
         for (int j = j_first; j < n_chunks; j += kEpiGroups) {
             const int rb = grp + kEpiGroups * rslot;
             if (ADD == 1 || ADD == 2) mbar_wait(&c.res_full[rb], rphase);
@@ -838,6 +851,8 @@ int pick_tile_w(int w, bool widest) {
 
 namespace om {
 
+int32_t tc2_set_wait_hint(unsigned int ns);
+
 int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     if (d.cin % 32) return fail(OM_ERR_INVALID, "fp16 engine needs cin %% 32 == 0 (got %d)", d.cin);
     if (d.out_kind != OM_OUT_NCHW && (d.cout % 32 || d.cout_stride % 16 || d.cout_stride < d.cout))
@@ -847,6 +862,12 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
         return fail(OM_ERR_INVALID, "stride-2 layers must be 3x3 with in_rows == 2*out_rows and in_w == 2*out_w");
     if (d.stride == 1 && (d.in_rows != d.out_rows || d.in_w != d.out_w))
         return fail(OM_ERR_INVALID, "stride-1 layers need identical input/output geometry");
+    {
+        static bool hint_set = false;
+        const char* wh = getenv("ORIENMASK_B200_WAIT_HINT");
+        if (!hint_set && wh) { tc2_set_wait_hint((unsigned int)atoi(wh)); }
+        hint_set = true;
+    }
     Tc2Plan* plan = new Tc2Plan();
     memset(plan, 0, sizeof(Tc2Plan));
     Tc2Params& p = plan->p;
@@ -1057,6 +1078,11 @@ int32_t tc2_plan_run(const void* vp, cudaStream_t stream) {
 }
 
 void tc2_plan_destroy(void* vp) { delete reinterpret_cast<Tc2Plan*>(vp); }
+
+int32_t tc2_set_wait_hint(unsigned int ns) {
+    OM_CUDA_TRY(cudaMemcpyToSymbol(g_wait_hint_ns, &ns, sizeof(ns)));
+    return OM_OK;
+}
 
 int32_t tc2_set_timeline(void* dev_ptr) {
     OM_CUDA_TRY(cudaMemcpyToSymbol(g_timeline, &dev_ptr, sizeof(void*)));
