@@ -33,6 +33,7 @@ constexpr int kMaxStages = 8;
 constexpr int kStageRows = 128;          // staging tile rows
 constexpr int kStageBytes = kStageRows * 128;
 constexpr int kMaxResBufs = 2 * kEpiGroups;   // addend staging buffers: one lane per epilogue group, up to 2 deep
+constexpr int kMaxAcc = 8;                    // accumulator stages in TMEM (narrow tiles: 512 columns / N)
 
 struct Tc2Params {
     int tiles_x, pairs_y, tiles_n;       // pair grid; linear pair id = (py * tiles_x + tx) * tiles_n + tn
@@ -493,9 +494,9 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     uint64_t* s_empty = bars + kMaxStages;             // [stages]
     uint64_t* h_full = bars + 2 * kMaxStages;          // [h_stages]
     uint64_t* h_empty = bars + 3 * kMaxStages;         // [h_stages]
-    uint64_t* tmem_full = bars + 4 * kMaxStages;       // [4]
-    uint64_t* tmem_empty = tmem_full + 4;              // [4]        (leader's copy: 16 warp arrivals from both CTAs)
-    uint64_t* res_full = tmem_empty + 4;               // [kMaxResBufs]  buffer = group + 2 * slot
+    uint64_t* tmem_full = bars + 4 * kMaxStages;       // [kMaxAcc]
+    uint64_t* tmem_empty = tmem_full + kMaxAcc;        // [kMaxAcc]  (leader's copy: 16 warp arrivals from both CTAs)
+    uint64_t* res_full = tmem_empty + kMaxAcc;         // [kMaxResBufs]  buffer = group + 2 * slot
     uint64_t* res_empty = res_full + kMaxResBufs;      // [kMaxResBufs]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_empty + kMaxResBufs);
     float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);            // [cout_pad]; L1 is carved down to nothing here, so
@@ -512,8 +513,8 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
         if (lane == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
         if (lane < p.stages) { mbar_init(&s_full[lane], 1); mbar_init(&s_empty[lane], 1); }
         if (lane >= 8 && lane - 8 < p.h_stages) { mbar_init(&h_full[lane - 8], 1); mbar_init(&h_empty[lane - 8], 1); }
-        if (lane >= 16 && lane < 20) { mbar_init(&tmem_full[lane - 16], 1); mbar_init(&tmem_empty[lane - 16], 8 * kEpiGroups); }
-        if (lane >= 20 && lane - 20 < kMaxResBufs) { mbar_init(&res_full[lane - 20], 1); mbar_init(&res_empty[lane - 20], 4); }
+        if (lane >= 16 && lane < 16 + kMaxAcc) { mbar_init(&tmem_full[lane - 16], 1); mbar_init(&tmem_empty[lane - 16], 8 * kEpiGroups); }
+        if (lane >= 24 && lane - 24 < kMaxResBufs) { mbar_init(&res_full[lane - 24], 1); mbar_init(&res_empty[lane - 24], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         tick(11, lane == 0);
     }
@@ -958,7 +959,7 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     }
     const int epi_bytes = p.has_res ? kEpiGroups * p.res_depth * p.res_buf_bytes : 0;
     constexpr int kMaxSmem = 227 * 1024;
-    const int fixed = 1024 + epi_bytes + (4 * kMaxStages + 8 + 2 * kMaxResBufs) * 8 + 16 + cout_pad * 4;
+    const int fixed = 1024 + epi_bytes + (4 * kMaxStages + 2 * kMaxAcc + 2 * kMaxResBufs) * 8 + 16 + cout_pad * 4;
     {
         const int total_b = p.taps * p.k_chunks * p.half_n * bk * 2;
         const char* br_env = getenv("ORIENMASK_B200_BRES");
@@ -992,7 +993,12 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
         if (p.stages < 2) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
         if (p.b_resident) { p.n_sub = total; p.stages = 1; }          // the "ring" is the resident weight tensor
     }
+    // 4 accumulators at most: 2 / 4 / 8 in flight measured identical on the narrow memory-bound layers (ORIENMASK_B200_ACC, up to
+    // kMaxAcc, for experiments), and a smaller TMEM allocation lets the next layer's prologue allocate earlier
     p.acc_stages = 512 / bn >= 4 ? 4 : 512 / bn;
+    if (getenv("ORIENMASK_B200_ACC") && atoi(getenv("ORIENMASK_B200_ACC")) >= 2 && atoi(getenv("ORIENMASK_B200_ACC")) <= kMaxAcc &&
+        atoi(getenv("ORIENMASK_B200_ACC")) * bn <= 512)
+        p.acc_stages = atoi(getenv("ORIENMASK_B200_ACC"));
     int cols = 32;
     while (cols < p.acc_stages * bn) cols <<= 1;
     p.tmem_cols = cols;
