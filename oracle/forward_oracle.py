@@ -53,7 +53,8 @@ def _up(x, k):
 
 @torch.no_grad()
 def forward_oracle(sd, x, return_features=False):
-    """sd: state dict (reference key names, fp32 CPU); x: [B,3,H,W] fp32. Returns the 3x(bbox, orien) tuple."""
+    """sd: state dict (reference key names, fp32 CPU); x: [B,3,H,W] fp32. Returns the 3x(bbox, orien) tuple.
+    A state dict without skip convolutions (it has ``route8.0``) is the OrienMaskYOLO variant, model/orienmask_yolo.py:71-86."""
     sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
     x = x.float()
     t = _cbl(sd, 'backbone.conv1', x)
@@ -75,8 +76,11 @@ def forward_oracle(sd, x, return_features=False):
     bbox16 = bbox_head('bbox_head16', neck16)
     bbox8 = bbox_head('bbox_head8', neck8)
 
-    cat4 = torch.cat([_up(_cbl(sd, 'skip32.0', neck32), 8), _up(_cbl(sd, 'skip16.0', neck16), 4),
-                      _up(_cbl(sd, 'skip8.0', neck8), 2), _cbl(sd, 'skip4', x4)], 1)
+    if 'route8.0.conv_block.0.weight' in sd:                       # model/orienmask_yolo.py:83
+        cat4 = torch.cat([_up(_cbl(sd, 'route8.0', neck8), 2), x4], 1)
+    else:                                                           # model/orienmask_yolo_fpnplus.py:85-86
+        cat4 = torch.cat([_up(_cbl(sd, 'skip32.0', neck32), 8), _up(_cbl(sd, 'skip16.0', neck16), 4),
+                          _up(_cbl(sd, 'skip8.0', neck8), 2), _cbl(sd, 'skip4', x4)], 1)
     o = _seq(sd, 'neck4', cat4, 5)
     o = _seq(sd, 'orien_head', o, 5)
     o = F.conv2d(o, sd['orien_head.5.weight'], sd['orien_head.5.bias'])

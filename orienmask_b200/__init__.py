@@ -4,16 +4,19 @@ Public surface (mirrors the reference's names so its infer.py / test.py run unch
 ``orienmask_b200/dropin`` is first on PYTHONPATH):
 
     OrienMaskYOLOFPNPlus       model/orienmask_yolo_fpnplus.py   (forward pass on tcgen05 kernels)
+    OrienMaskYOLO              model/orienmask_yolo.py           (the variant without skip convolutions)
     OrienMaskYOLOPostProcess   eval/orienmask_yolo_postprocess.py (decode + NMS + masks kernels)
     batched_nms, nms           eval/function.py
     FastCOCOTransform, pad     data/transform.py:444-510, infer.py:21-32 (pre-process kernel)
     COCOMetrics                eval/coco_eval.py:23-205 (mask crop/resize/RLE kernel; no AP accumulation)
+    Tester                     trainer/tester.py:11-62 (evaluation loop over a dataloader)
 """
 from .function import batched_nms, nms                      # noqa: F401
-from .model import OrienMaskYOLOFPNPlus                      # noqa: F401
+from .model import OrienMaskYOLOFPNPlus, OrienMaskYOLO       # noqa: F401
 from .postprocess import OrienMaskYOLOPostProcess, PaddedDetections   # noqa: F401
 from .transform import FastCOCOTransform, pad                 # noqa: F401
 from .coco_format import COCOMetrics                          # noqa: F401
+from .tester import Tester                                    # noqa: F401
 
-__all__ = ['OrienMaskYOLOFPNPlus', 'OrienMaskYOLOPostProcess', 'PaddedDetections', 'batched_nms', 'nms',
-           'FastCOCOTransform', 'pad', 'COCOMetrics']
+__all__ = ['OrienMaskYOLOFPNPlus', 'OrienMaskYOLO', 'OrienMaskYOLOPostProcess', 'PaddedDetections', 'batched_nms', 'nms',
+           'FastCOCOTransform', 'pad', 'COCOMetrics', 'Tester']

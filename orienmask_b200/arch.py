@@ -15,8 +15,9 @@ STAGE_CHANNELS = (32, 64, 128, 256, 512)
 STAGE_BLOCKS = (1, 2, 8, 8, 4)
 
 
-def conv_specs(num_anchors=3, num_classes=80):
-    """Every convolution of the network in execution order."""
+def conv_specs(num_anchors=3, num_classes=80, plus=True):
+    """Every convolution of the network in execution order.  plus=False: OrienMaskYOLO (model/orienmask_yolo.py:8-86), the
+    variant without the skip convolutions whose neck4 reads cat[up2(route8(neck8)), x4] (192 channels)."""
     specs = []
 
     def cbl(prefix, cin, cout, k, stride=1):
@@ -45,21 +46,25 @@ def conv_specs(num_anchors=3, num_classes=80):
     for s, c in ((32, 512), (16, 256), (8, 128)):
         cbl('bbox_head%d.0' % s, c, 2 * c, 3)
         specs.append(ConvSpec('bbox_head%d.1' % s, 2 * c, bbox_dim, 1, 1, 'conv'))
-    cbl('skip32.0', 512, 64, 1)
-    cbl('skip16.0', 256, 64, 1)
-    cbl('skip8.0', 128, 64, 1)
-    cbl('skip4', 128, 64, 1)
-    neck('neck4', 256, 128)
+    if plus:
+        cbl('skip32.0', 512, 64, 1)
+        cbl('skip16.0', 256, 64, 1)
+        cbl('skip8.0', 128, 64, 1)
+        cbl('skip4', 128, 64, 1)
+        neck('neck4', 256, 128)
+    else:
+        cbl('route8.0', 128, 64, 1)
+        neck('neck4', 192, 128)
     for i, (cin, cout, k) in enumerate(((128, 256, 3), (256, 128, 1), (128, 256, 3), (256, 128, 1), (128, 256, 3))):
         cbl('orien_head.%d' % i, cin, cout, k)
     specs.append(ConvSpec('orien_head.5', 256, num_anchors * 6, 1, 1, 'conv'))
     return specs
 
 
-def state_dict_shapes(num_anchors=3, num_classes=80):
+def state_dict_shapes(num_anchors=3, num_classes=80, plus=True):
     """Ordered {key: shape} of the reference state dict (524 entries for 3 anchors / 80 classes)."""
     out = {}
-    for s in conv_specs(num_anchors, num_classes):
+    for s in conv_specs(num_anchors, num_classes, plus):
         if s.kind == 'cbl':
             out[s.prefix + '.conv_block.0.weight'] = (s.cout, s.cin, s.k, s.k)
             for name in ('weight', 'bias', 'running_mean', 'running_var'):
@@ -71,7 +76,7 @@ def state_dict_shapes(num_anchors=3, num_classes=80):
     return out
 
 
-def macs_per_image(height, width, num_anchors=3, num_classes=80):
+def macs_per_image(height, width, num_anchors=3, num_classes=80, plus=True):
     """Multiply-accumulates of the 90 convolutions for one HxW image (86.9226e9 @544)."""
     res = {}
     total = 0
@@ -79,7 +84,7 @@ def macs_per_image(height, width, num_anchors=3, num_classes=80):
     # resolution of every conv output, derived from the dataflow
     strides = {}
     cur = 1
-    for s in conv_specs(num_anchors, num_classes):
+    for s in conv_specs(num_anchors, num_classes, plus):
         p = s.prefix
         if p.startswith('backbone'):
             cur *= s.stride
@@ -88,7 +93,7 @@ def macs_per_image(height, width, num_anchors=3, num_classes=80):
             strides[p] = 32
         elif p.startswith(('neck16', 'route16', 'bbox_head16', 'skip16')):
             strides[p] = 16
-        elif p.startswith(('neck8', 'bbox_head8', 'skip8')):
+        elif p.startswith(('neck8', 'bbox_head8', 'skip8', 'route8')):
             strides[p] = 8
         else:
             strides[p] = 4

@@ -6,4 +6,4 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.dirname(os.path.
 if _ROOT not in sys.path:
     sys.path.insert(0, _ROOT)
 
-from orienmask_b200.model import OrienMaskYOLOFPNPlus  # noqa: E402,F401
+from orienmask_b200.model import OrienMaskYOLOFPNPlus, OrienMaskYOLO  # noqa: E402,F401

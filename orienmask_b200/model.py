@@ -42,13 +42,15 @@ def _holder(root, dotted):
 
 
 class OrienMaskYOLOFPNPlus(nn.Module):
+    _plus = True          # False in OrienMaskYOLO: no skip convolutions, neck4 reads cat[up2(route8(neck8)), x4]
+
     def __init__(self, num_anchors, num_classes, pretrained=None, freeze_backbone=False, backbone_batchnorm_eval=False):
         super().__init__()
         self.num_anchors, self.num_classes = num_anchors, num_classes
         self.precision = os.environ.get('ORIENMASK_B200_PRECISION', 'fp16')     # 'fp16' (tcgen05) | 'fp32' (parity)
         # replay the forward's ~95 launches as one CUDA graph (small-batch latency; outputs are overwritten by the next call)
         self.use_cuda_graph = os.environ.get('ORIENMASK_B200_GRAPH', '0') == '1'
-        self._specs = conv_specs(num_anchors, num_classes)
+        self._specs = conv_specs(num_anchors, num_classes, self._plus)
         for s in self._specs:
             fan_in = s.cin * s.k * s.k
             w = torch.empty(s.cout, s.cin, s.k, s.k)
@@ -105,6 +107,12 @@ class OrienMaskYOLOFPNPlus(nn.Module):
         return eng.run_graph(x) if self.use_cuda_graph else eng.run(x)
 
 
+class OrienMaskYOLO(OrienMaskYOLOFPNPlus):
+    """``/root/reference/model/orienmask_yolo.py:8-86``: same backbone, necks and heads; the stride-4 neck takes the up-sampled
+    ``route8`` instead of the four skip convolutions (its own 506 state-dict keys)."""
+    _plus = False
+
+
 class _Engine:
     """Static buffer plan + launch schedule for one (batch, H, W, precision)."""
 
@@ -116,6 +124,7 @@ class _Engine:
         self.prec = _lib.PREC_F16 if precision == 'fp16' else _lib.PREC_F32
         self.adt = torch.float16 if precision == 'fp16' else torch.float32
         self.nA, self.nC = model.num_anchors, model.num_classes
+        self.plus = model._plus
         self.sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in model.state_dict().items()
                    if v.is_floating_point()}
         self.keep = []            # owns every device tensor the plans point to
@@ -292,16 +301,22 @@ class _Engine:
             self.head('bbox_head%d.1' % st, hb, out)
             self.out_bbox.append(out)
 
-        s32, s16, s8, s4 = self.act(32, 64), self.act(16, 64), self.act(8, 64), self.act(4, 64)
-        self.cbl('skip32.0', neck32, s32, 1)
-        self.cbl('skip16.0', neck16, s16, 1)
-        self.cbl('skip8.0', neck8, s8, 1)
-        self.cbl('skip4', x4, s4, 1)
-        q32 = self.partial('neck4.0', (0, 64), s32)
-        q16 = self.partial('neck4.0', (64, 128), s16, upadd=q32)
-        q8 = self.partial('neck4.0', (128, 192), s8, upadd=q16)
         a4, b4 = self.act(4, 128), self.act(4, 256)
-        neck4 = self.chain('neck4', s4, (a4, b4), ks, first_upadd=q8, first_cols=(192, 256))
+        if self.plus:
+            s32, s16, s8, s4 = self.act(32, 64), self.act(16, 64), self.act(8, 64), self.act(4, 64)
+            self.cbl('skip32.0', neck32, s32, 1)
+            self.cbl('skip16.0', neck16, s16, 1)
+            self.cbl('skip8.0', neck8, s8, 1)
+            self.cbl('skip4', x4, s4, 1)
+            q32 = self.partial('neck4.0', (0, 64), s32)
+            q16 = self.partial('neck4.0', (64, 128), s16, upadd=q32)
+            q8 = self.partial('neck4.0', (128, 192), s8, upadd=q16)
+            neck4 = self.chain('neck4', s4, (a4, b4), ks, first_upadd=q8, first_cols=(192, 256))
+        else:                         # model/orienmask_yolo.py:83: neck4(cat[route8(neck8) up2, x4])
+            r8 = self.act(8, 64)
+            self.cbl('route8.0', neck8, r8, 1)
+            p4 = self.partial('neck4.0', (0, 64), r8)
+            neck4 = self.chain('neck4', x4, (a4, b4), ks, first_upadd=p4, first_cols=(64, 192))
         # orien_head.0-4 alternate 3x3 (128->256) and 1x1 (256->128): neck4 lives in a4, so start on b4
         o = self.chain('orien_head', neck4, (b4, a4), (3, 1, 3, 1, 3))
         self.out_orien = torch.empty(B, self.nA * 6, H // 4, W // 4, **f32)

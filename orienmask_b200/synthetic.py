@@ -24,11 +24,11 @@ RESIDUAL_GAMMA = 0.2
 
 
 def synthetic_state_dict(seed=0, num_anchors=3, num_classes=80, obj_bias=-4.0, cls_bias=-2.0,
-                         dtype=torch.float32):
+                         dtype=torch.float32, plus=True):
     g = torch.Generator().manual_seed(seed)
     sd = {}
     slope = 0.1
-    for s in conv_specs(num_anchors, num_classes):
+    for s in conv_specs(num_anchors, num_classes, plus):
         fan_in = s.cin * s.k * s.k
         if s.kind == 'cbl':
             std = TRUNK_GAIN * math.sqrt(2.0 / ((1.0 + slope * slope) * fan_in))

@@ -152,3 +152,24 @@ def test_report_forward_drift_544():
         assert worst < (1e-4 if prec == 'fp32' else 0.03), (prec, worst)
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump(report, open(os.path.join(ROOT, 'gpurun_out', 'drift.json'), 'w'), indent=1)
+
+
+def test_non_plus_model_both_engines():
+    """OrienMaskYOLO (model/orienmask_yolo.py:8-86): reference heads from tests/golden/yolo_small_fwd.npz."""
+    import orienmask_b200 as ob
+    from orienmask_b200.synthetic import synthetic_images, synthetic_state_dict
+    g = np.load(GOLDEN + '/yolo_small_fwd.npz')
+    x = synthetic_images(2, 64, 96, seed=1).cuda()
+    for prec in ('fp32', 'fp16'):
+        m = ob.OrienMaskYOLO(3, 80)
+        assert len(m.state_dict()) == 506
+        m.load_state_dict(synthetic_state_dict(0, plus=False), strict=True)
+        m.precision = prec
+        out = m.to('cuda:0').eval()(x)
+        for i, (bbox, orien) in enumerate(out):
+            for got, ref in ((bbox, g['bbox_%d' % i]), (orien.contiguous(), g['orien_%d' % i])):
+                got = got.cpu().numpy()
+                if prec == 'fp32':
+                    assert np.abs(got - ref).max() < 5e-4
+                else:
+                    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 0.03

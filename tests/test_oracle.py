@@ -117,3 +117,16 @@ def test_forward_oracle_544_probe():
     for i, (bbox, orien) in enumerate(out):
         assert np.abs(bbox.numpy().reshape(-1)[::97] - g['bbox_%d' % i]).max() < 5e-4
         assert np.abs(orien.numpy().reshape(-1)[::97] - g['orien_%d' % i]).max() < 5e-4
+
+
+def test_forward_oracle_non_plus_model_fixture():
+    """OrienMaskYOLO (model/orienmask_yolo.py): heads stored by tests/golden/make_golden_yolo.py from the unmodified reference."""
+    from orienmask_b200.synthetic import synthetic_state_dict, synthetic_images
+    from oracle.forward_oracle import forward_oracle
+    g = np.load(GOLDEN + '/yolo_small_fwd.npz')
+    sd = synthetic_state_dict(0, plus=False)
+    assert len(sd) == int(g['n_keys']) == 506
+    out = forward_oracle(sd, synthetic_images(2, 64, 96, seed=1))
+    for i, (bbox, orien) in enumerate(out):
+        assert np.abs(bbox.numpy() - g['bbox_%d' % i]).max() < 1e-4
+        assert np.abs(orien.numpy() - g['orien_%d' % i]).max() < 1e-4
