@@ -271,14 +271,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation) stalls kernel launches for tens of
+    # milliseconds, which inside a 10-step timed region once read as 10 ms per step; only its 100 ms polling overlaps the timing
+    sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
         step(resident[i % 2])
     barrier()
+    if sampler is not None:
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 3.0:
+            time.sleep(0.05)
+        for i in range(2):
+            step(resident[i % 2])
+        barrier()
 
     # ---- device-resident timing -------------------------------------------------------------
     fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local) if rank == 0 else None
     lib.om_launch_count_reset()
     barrier()
     t0 = time.time()
