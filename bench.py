@@ -263,7 +263,7 @@ def main():
     def step(x):
         heads = model(x)
         out = post.apply_padded(heads)
-        det, cls, cnt = gather_detections(out.det, out.cls, out.count)
+        det, cls, cnt = gather_detections(out.det, out.cls, out.count, packed=out.packed)
         return out, det, cls, cnt
 
     def barrier():
@@ -281,9 +281,9 @@ def main():
         t_wait = time.time()
         while not sampler.rows and time.time() - t_wait < 3.0:
             time.sleep(0.05)
-        for i in range(2):
-            step(resident[i % 2])
-        barrier()
+    for i in range(2):                       # every rank (the step contains a collective): absorbs rank 0's wait above
+        step(resident[i % 2])
+    barrier()
 
     # ---- device-resident timing -------------------------------------------------------------
     fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -297,7 +297,7 @@ def main():
         heads = model(resident[i % 2])
         fwd_ev[i][1].record()
         out = post.apply_padded(heads)
-        gather_detections(out.det, out.cls, out.count)
+        gather_detections(out.det, out.cls, out.count, packed=out.packed)
     e1.record()
     barrier()
     t1 = time.time()

@@ -100,10 +100,13 @@ int32_t om_decode_select(const om_post_config* cfg, const float* const* bbox, co
  *   det_cls    [batch,nms_post]    int64
  *   det_anchor [batch,nms_post]    int32  global anchor index of the prediction (selects the orientation map)
  *   det_keep   [batch,nms_post]    int32  index into the candidate list (the reference's `keep`)
+ *   records    [batch,nms_post*6+1] fp32  optional (may be NULL): cx, cy, w, h, score, cls per slot, then the count -- the
+ *                                         fixed-size row a rank contributes to the multi-GPU all-gather, written by the same
+ *                                         kernel so that the collective's source is this buffer
  */
 int32_t om_batched_nms(const om_post_config* cfg, const int32_t* cand_count, const float* cand_det,
                        const int32_t* cand_cls, const int32_t* cand_pred, int32_t batch, int32_t* det_count,
-                       float* det, int64_t* det_cls, int32_t* det_anchor, int32_t* det_keep, void* stream);
+                       float* det, int64_t* det_cls, int32_t* det_anchor, int32_t* det_keep, float* records, void* stream);
 
 /*
  * Instance masks: mask[b,k,y,x] = |pix_x - xc| < t*w*nW  &&  |pix_y - yc| < t*h*nH on the x4 bilinear

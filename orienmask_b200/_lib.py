@@ -66,7 +66,7 @@ SIGNATURES = {
     'om_post_workspace_bytes': (c_i32, [ctypes.POINTER(PostConfig), c_i32, ctypes.POINTER(ctypes.c_size_t)]),
     'om_decode_select': (c_i32, [ctypes.POINTER(PostConfig), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), c_i32,
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    'om_batched_nms': (c_i32, [ctypes.POINTER(PostConfig), c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'om_batched_nms': (c_i32, [ctypes.POINTER(PostConfig), c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'om_mask_assemble': (c_i32, [ctypes.POINTER(PostConfig), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),
                                  c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'om_nms': (c_i32, [c_vp, c_i32, c_f32, c_vp, c_vp, c_vp]),

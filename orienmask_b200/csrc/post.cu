@@ -280,6 +280,7 @@ struct NmsArgs {
     float thr;
     // batched outputs
     int* det_count; float* det; long long* det_cls; int* det_anchor; int* det_keep;
+    float* records;                 // optional [batch, nms_post*6 + 1]: (cx, cy, w, h, score, cls) per slot, then the count -- the row a rank all-gathers
     // stand-alone outputs
     long long* keep; int* keep_count;
 };
@@ -414,11 +415,13 @@ __global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
         int* danc = a.det_anchor + (long long)b * a.nms_post;
         int* dkeep = a.det_keep + (long long)b * a.nms_post;
         const int* pred = a.pred + (long long)b * cap;
-        if (threadIdx.x == 0) a.det_count[b] = n_out;
+        float* rec = a.records ? a.records + (long long)b * (a.nms_post * 6 + 1) : nullptr;
+        if (threadIdx.x == 0) { a.det_count[b] = n_out; if (rec) rec[a.nms_post * 6] = (float)n_out; }
         for (int i = threadIdx.x; i < a.nms_post; i += blockDim.x)
             if (i >= n_out) {
                 for (int c = 0; c < 5; ++c) det[i * 5 + c] = 0.f;
                 dcls[i] = 0; danc[i] = 0; dkeep[i] = 0;
+                if (rec) for (int c = 0; c < 6; ++c) rec[i * 6 + c] = 0.f;
             }
         for (int e = threadIdx.x; e < n; e += blockDim.x) {
             // e indexes ranks (top-k case, score-descending) or positions (ascending-index case)
@@ -428,6 +431,7 @@ __global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
             const int o = slot[e];
             for (int c = 0; c < 5; ++c) det[o * 5 + c] = dets[p * 5 + c];
             dcls[o] = cls[p];
+            if (rec) { for (int c = 0; c < 5; ++c) rec[o * 6 + c] = dets[p * 5 + c]; rec[o * 6 + 5] = (float)cls[p]; }
             int s, an, cell, plane;
             locate_pred(d, pred[p], s, an, cell, plane);
             danc[o] = d.aidx[s][an];
@@ -690,7 +694,7 @@ extern "C" int32_t om_decode_select(const om_post_config* cfg, const float* cons
 
 extern "C" int32_t om_batched_nms(const om_post_config* cfg, const int32_t* cand_count, const float* cand_det,
                                   const int32_t* cand_cls, const int32_t* cand_pred, int32_t batch, int32_t* det_count,
-                                  float* det, int64_t* det_cls, int32_t* det_anchor, int32_t* det_keep, void* stream) {
+                                  float* det, int64_t* det_cls, int32_t* det_anchor, int32_t* det_keep, float* records, void* stream) {
     PostDev d;
     int32_t rc = make_dev(cfg, d);
     if (rc) return rc;
@@ -700,7 +704,7 @@ extern "C" int32_t om_batched_nms(const om_post_config* cfg, const int32_t* cand
     a.dets = cand_det; a.cls = cand_cls; a.pred = cand_pred; a.counts = cand_count;
     a.n = 0; a.cap = d.nms_pre; a.NP = d.NP; a.nms_post = d.nms_post; a.thr = d.nms_thresh;
     a.det_count = det_count; a.det = det; a.det_cls = reinterpret_cast<long long*>(det_cls);
-    a.det_anchor = det_anchor; a.det_keep = det_keep;
+    a.det_anchor = det_anchor; a.det_keep = det_keep; a.records = records;
     const size_t smem = nms_smem_bytes(a.NP, a.cap);
     if ((rc = allow_smem(nms_kernel<true>, smem))) return rc;
     nms_kernel<true><<<batch, 512, smem, (cudaStream_t)stream>>>(a, d);

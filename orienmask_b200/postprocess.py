@@ -24,6 +24,7 @@ class PaddedDetections:
 
     def __init__(self, det, cls, anchor, keep, count, mask):
         self.det, self.cls, self.anchor, self.keep, self.count, self.mask = det, cls, anchor, keep, count, mask
+        self.packed = None
 
     def records(self):
         """[B, nms_post, 6] fp32 (cx, cy, w, h, score, cls) -- the unit the multi-GPU gather moves."""
@@ -139,13 +140,15 @@ class OrienMaskYOLOPostProcess:
             det_cls = torch.empty(B, self.nms_post, dtype=torch.int64, device=dev)
             det_anchor = torch.empty(B, self.nms_post, **i32)
             det_keep = torch.empty(B, self.nms_post, **i32)
+            packed = torch.empty(B, self.nms_post * 6 + 1, dtype=torch.float32, device=dev)
             _lib.check(lib.om_batched_nms(ctypes.byref(cfg), _lib.ptr(cand_count), _lib.ptr(cand_det), _lib.ptr(cand_cls),
                                           _lib.ptr(cand_pred), B, _lib.ptr(det_count), _lib.ptr(det), _lib.ptr(det_cls),
-                                          _lib.ptr(det_anchor), _lib.ptr(det_keep), stream), 'om_batched_nms')
+                                          _lib.ptr(det_anchor), _lib.ptr(det_keep), _lib.ptr(packed), stream), 'om_batched_nms')
             mask = torch.empty(B, self.nms_post, self.image_h, self.image_w, dtype=torch.uint8, device=dev)
             _lib.check(lib.om_mask_assemble(ctypes.byref(cfg), or_ptr, or_str, _lib.ptr(det_count), _lib.ptr(det),
                                             _lib.ptr(det_anchor), B, _lib.ptr(mask), stream), 'om_mask_assemble')
         out = PaddedDetections(det, det_cls, det_anchor, det_keep, det_count, mask)
+        out.packed = packed          # [B, nms_post*6+1] rows written by the NMS kernel: what sharding.gather_detections moves
         out.candidates = dict(count=cand_count, det=cand_det, cls=cand_cls, pred=cand_pred)
         out._keepalive = (bboxes, oriens, ws)
         return out

@@ -39,15 +39,18 @@ def unpack_records(packed, K):
     return rec[..., :5].contiguous(), rec[..., 5].to(torch.int64), packed[:, K * 6].to(torch.int32)
 
 
-def gather_detections(det, cls, count, group=None):
+def gather_detections(det, cls, count, group=None, packed=None):
     """All-gather the padded detection records of every rank (equal B_local per rank).
 
+    ``packed``: the [B_local, K*6+1] record rows the NMS kernel wrote (``PaddedDetections.packed``); when given, that buffer
+    is the collective's source and nothing is re-packed.
     Returns (det [B_total,K,5], cls [B_total,K], count [B_total]) in rank order, on every rank.
     """
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return det, cls, count
     K = det.shape[1]
-    packed = pack_records(det, cls, count)
+    if packed is None:
+        packed = pack_records(det, cls, count)
     world = dist.get_world_size(group)
     out = torch.empty(world * packed.shape[0], packed.shape[1], dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(out, packed, group=group)

@@ -148,3 +148,17 @@ def test_post_rejects_cpu_tensors():
     heads = synthetic_heads(1, 64, 64, seed=1)
     with pytest.raises(RuntimeError):
         _post(64, 64, 0.005)(heads)
+
+
+def test_nms_kernel_writes_the_gather_records():
+    """PaddedDetections.packed (written by the NMS kernel) is exactly what sharding.pack_records builds from det / cls / count."""
+    import functools
+    import orienmask_b200 as ob
+    from orienmask_b200.sharding import pack_records, unpack_records
+    from tests.common import synthetic_heads, post_config
+    post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5), device=torch.device('cuda:0'),
+                                       **post_config(64, 96, 0.02))
+    out = post.apply_padded([(b.cuda(), o.cuda()) for b, o in synthetic_heads(3, 64, 96, seed=11)])
+    assert torch.equal(out.packed, pack_records(out.det, out.cls, out.count))
+    det, cls, cnt = unpack_records(out.packed, post.nms_post)
+    assert torch.equal(det, out.det) and torch.equal(cls, out.cls) and torch.equal(cnt, out.count)

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
-    assert _lib.lib().om_abi_version() == 3
+    assert _lib.lib().om_abi_version() == 4
 
 
 def test_config_errors_are_reported_without_a_gpu():
@@ -105,3 +105,20 @@ def test_gather_detections_world2_gloo():
     for p in procs:
         p.join(60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` prints one JSON line with the keys the driver reads (CPU only: the oracle port)."""
+    import json
+    import subprocess
+    import sys
+    from tests.common import ROOT
+    out = subprocess.run([sys.executable, 'bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0'], cwd=ROOT,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['cpu_baseline']['kind'] == 'port'
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and line['cpu_baseline']['cores'] >= 1
