@@ -72,24 +72,43 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& 
 // y table in shared memory: source rows (flip applied, relative to the crop) and the weights, per output row
 struct YTab { int r0, r1; float l0, l1; };
 
-// Walks output column x over the occupied output rows [ya, yb] (every other pixel of the column is 0) and calls
-// emit(position) at each change of the column-major bit stream; `prev` is the bit that precedes the column.
-template <typename Emit>
-__device__ __forceinline__ void walk_column(const ColCtx& c, bool occupied, int prev, int x, int oh, int ya, int yb, const YTab* ytab,
-                                            long long pitch, Emit emit) {
-    const unsigned int base = (unsigned int)x * (unsigned int)oh;
-    if (!occupied) { if (prev) emit(base); return; }
-    if (ya > 0 && prev) { emit(base); prev = 0; }
-    for (int y = ya; y <= yb; ++y) {
-        const YTab t = ytab[y];
-        const int bit = resized_bit(c, t.r0 * pitch, t.r1 * pitch, t.l0, t.l1);
-        if (bit != prev) emit(base + (unsigned int)y);
-        prev = bit;
+// One output column as 32-row words of the column-major bit stream.  For every word the CHANGE mask (bit i set = the stream
+// changes at row 32*w + i) goes to `tw[w * kThreads]` (shared memory, one column per thread) and the number of changes is
+// returned, so the second pass only iterates set bits instead of re-evaluating the blend.  Rows outside [ya, yb] are zero
+// without any load; consecutive output rows share source rows (y1 of one row is y0 of the next when resizing by ~1x), so the
+// horizontal blend of a source row is reused instead of reloaded.
+__device__ __forceinline__ int column_changes(const ColCtx& c, bool occupied, int prev, int oh, int ya, int yb, const YTab* ytab,
+                                              long long pitch, unsigned int* tw) {
+    const int nw = (oh + 31) >> 5;
+    int cnt = 0;
+    int rA = -1, rB = -1; float vA = 0.f, vB = 0.f;         // two cached source rows and their horizontal blends
+    for (int w = 0; w < nw; ++w) {
+        unsigned int word = 0;
+        const int y_lo = w << 5, y_hi = min(y_lo + 32, oh);
+        if (occupied && y_lo <= yb && y_hi > ya) {
+            for (int y = max(y_lo, ya); y < min(y_hi, yb + 1); ++y) {
+                const YTab t = ytab[y];
+                float top, bot;
+                if (t.r0 == rA) top = vA; else if (t.r0 == rB) top = vB;
+                else top = __fmaf_rn(c.lx0, (float)__ldg(c.c0 + t.r0 * pitch), __fmul_rn(c.lx1, (float)__ldg(c.c1 + t.r0 * pitch)));
+                if (t.r1 == t.r0) bot = top; else if (t.r1 == rA) bot = vA; else if (t.r1 == rB) bot = vB;
+                else bot = __fmaf_rn(c.lx0, (float)__ldg(c.c0 + t.r1 * pitch), __fmul_rn(c.lx1, (float)__ldg(c.c1 + t.r1 * pitch)));
+                rA = t.r0; vA = top; rB = t.r1; vB = bot;
+                const float v = __fmaf_rn(t.l0, top, __fmul_rn(t.l1, bot));
+                word |= (v > 0.5f ? 1u : 0u) << (y - y_lo);          // torch.round(): half to even, and v is in [0, 1]
+            }
+        }
+        unsigned int change = word ^ ((word << 1) | (unsigned int)prev);
+        if (y_hi - y_lo < 32) change &= (1u << (y_hi - y_lo)) - 1u;          // the column ends inside this word
+        tw[w * kThreads] = change;
+        cnt += __popc(change);
+        prev = (int)(word >> 31);                           // rows past `oh` in the last word are 0: no column follows inside it
     }
-    if (yb < oh - 1 && prev) emit(base + (unsigned int)(yb + 1));
+    return cnt;
 }
 
 __global__ void __launch_bounds__(kThreads) mask_rle_kernel(const om_rle_image* __restrict__ images, int max_inst, int cap, int str_cap,
+                                                            int change_off,
                                                             unsigned int* __restrict__ counts, int* __restrict__ n_counts,
                                                             unsigned char* __restrict__ str, int* __restrict__ str_len) {
     extern __shared__ __align__(16) unsigned char rle_smem[];
@@ -103,6 +122,7 @@ __global__ void __launch_bounds__(kThreads) mask_rle_kernel(const om_rle_image* 
     YTab* ytab = reinterpret_cast<YTab*>(rle_smem);                                  // [oh]
     unsigned char* col_any = rle_smem + (size_t)oh * sizeof(YTab);                   // [mask_w]  any pixel set in this mask column
     unsigned char* row_any = col_any + ((im.mask_w + 15) & ~15);                     // [mask_h]  ... in this mask row
+    unsigned int* changes = reinterpret_cast<unsigned int*>(rle_smem + change_off) + threadIdx.x;   // [(max_oh+31)/32][kThreads]
     const unsigned char* mk = im.mask + (long long)k * im.mask_h * im.mask_w;
     const unsigned char* m = mk + (long long)im.top * im.mask_w + im.left;           // crop origin
     const long long pitch = im.mask_w;
@@ -175,12 +195,23 @@ __global__ void __launch_bounds__(kThreads) mask_rle_kernel(const om_rle_image* 
                     first_prev = resized_bit(pc, t.r0 * pitch, t.r1 * pitch, t.l0, t.l1);
                 }
             }
-            walk_column(c, occ, first_prev, x, oh, ya, yb, ytab, pitch, [&](unsigned int) { ++cnt; });
+            cnt = column_changes(c, occ, first_prev, oh, ya, yb, ytab, pitch, changes);
         }
         int total;
         int w = n_trans + block_exclusive_scan(cnt, warp_sums, total);
-        if (cnt > 0)                              // second walk only over the columns that hold a transition
-            walk_column(c, occ, first_prev, x, oh, ya, yb, ytab, pitch, [&](unsigned int pos) { if (w < cap) out[w] = pos; ++w; });
+        if (cnt > 0) {                            // positions of the set bits, in stream order
+            const unsigned int base = (unsigned int)x * (unsigned int)oh;
+            const int nw = (oh + 31) >> 5;
+            for (int wi = 0; wi < nw; ++wi) {
+                unsigned int ch = changes[wi * kThreads];
+                while (ch) {
+                    const int i = __ffs(ch) - 1;
+                    ch &= ch - 1;
+                    if (w < cap) out[w] = base + (unsigned int)(wi * 32 + i);
+                    ++w;
+                }
+            }
+        }
         n_trans += total;
     }
     // positions -> run lengths in place: counts = [p0, p1 - p0, ..., N - p_last]  (rleEncode).  Chunks are converted from
@@ -246,7 +277,8 @@ extern "C" int32_t om_mask_rle(const om_rle_image* images, int32_t batch, int32_
     if (batch < 1 || batch > 65535 || max_inst < 1 || cap < 1 || str_cap < 1 || max_out_h < 1 || max_mask_h < 1 || max_mask_w < 1)
         return om::fail(OM_ERR_INVALID, "om_mask_rle: non-positive size (or batch > 65535)");
     // per-CTA shared memory: row table of the tallest output + occupancy flags of the largest mask (host copy of the sizes)
-    const size_t smem = (size_t)max_out_h * 16 + (size_t)((max_mask_w + 15) & ~15) + (size_t)max_mask_h;
+    const size_t change_off = ((size_t)max_out_h * 16 + (size_t)((max_mask_w + 15) & ~15) + (size_t)max_mask_h + 15) & ~(size_t)15;
+    const size_t smem = change_off + (size_t)((max_out_h + 31) / 32) * kThreads * 4;
     if (smem > 200 * 1024) return om::fail(OM_ERR_UNSUPPORTED, "om_mask_rle: sizes need %zu bytes of shared memory per CTA (max 204800)", smem);
     static bool attr_set = false;
     if (smem > 48 * 1024 && !attr_set) {
@@ -254,6 +286,6 @@ extern "C" int32_t om_mask_rle(const om_rle_image* images, int32_t batch, int32_
         attr_set = true;
     }
     mask_rle_kernel<<<dim3((unsigned)max_inst, (unsigned)batch), kThreads, smem, (cudaStream_t)stream>>>(
-        images, max_inst, cap, str_cap, counts, n_counts, str, str_len);
+        images, max_inst, cap, str_cap, (int)change_off, counts, n_counts, str, str_len);
     return om::check_launch("mask_rle_kernel");
 }
