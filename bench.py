@@ -355,7 +355,9 @@ def main():
         peaks = measured_peaks()
         value = world * B * args.steps / (total_ms * 1e-3)
         achieved = B * GFLOP_PER_IMAGE / fwd_ms          # GFLOP / ms == TFLOP/s
-        traffic = measured_traffic() if B == BATCH else None
+        traffic = measured_traffic() if (B == BATCH and H == 544) else None
+        eng = next(iter(model._engines.values()))
+        algo_bytes = int(sum(l['bytes'] for l in eng.layers))     # per layer: activations in + out (+ addends) + weights, fp16
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -375,8 +377,10 @@ def main():
             'stages': stages,
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
                          'frac': achieved / peaks['tflops'], 'traffic': traffic['bytes'] if traffic else None,
+                         'traffic_algorithmic': algo_bytes,
                          'traffic_note': ('ncu dram__bytes_read+write summed over the %d conv-engine launches of one step '
-                                          '(profiles/r01_traffic.json); algorithmic HBM bytes of the same launches: see profiles/r01_layers_*.md'
+                                          '(profiles/r01_traffic.json); traffic_algorithmic = the un-fused per-layer in + out + weight bytes of the same launches '
+                                          '(measured < algorithmic: consecutive layers hit in the 126 MB L2)'
                                           % traffic['launches']) if traffic else None,
                          'kernel': 'conv engine = the model forward: 94 conv_tc2_kernel launches (tcgen05 cta_group::2) + stem_tc_kernel, '
                                    '%.3f ms of %.3f ms per step' % (fwd_ms, total_ms / args.steps),
