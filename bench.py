@@ -61,12 +61,30 @@ def measured_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and throttle reasons DURING the timed region.
+
+    In-process NVML (nvidia_ml_py) from a thread.  Every driver query stalls kernel submission (an `nvidia-smi -lms` child
+    for tens of milliseconds per poll, an NVML field query for a few): with 20 ms polling a 10-step timed region (65 ms)
+    read anything between 6.7 and 20 ms per step while the un-sampled end-to-end loop stayed within 2 %.  So the sampler
+    polls every 20 ms during the warm-up (same workload, immediately before) and, once `sparse(seconds)` is called with the
+    expected length of the timed region, takes only two samples inside it (at ~1/3 and ~2/3).  nvidia-smi is the fallback."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.stop_flag, self.period = [], None, None, False, 0.02
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), '--query-gpu=' + self.Q,
                                           '--format=csv,noheader,nounits', '-lms', '100'],
@@ -76,11 +94,35 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append((time.time(), mhz, bits))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def sparse(self, region_seconds):
+        self.period = max(0.03, region_seconds / 3.0)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(',')]))
 
     def stop(self, t0, t1):
+        if self.nvml is not None:
+            self.stop_flag = True
+            rows = [r for r in self.rows if t0 <= r[0] <= t1] or self.rows[-3:]
+            if not rows:
+                return None
+            bits = 0
+            for r in rows:
+                bits |= r[2]
+            return {'sm_mhz': statistics.median(r[1] for r in rows), 'sm_max_mhz': self.max_mhz,
+                    'reasons': [name for name, b in self.BITS if bits & b], 'samples': len(rows), 'source': 'nvml'}
         if self.proc is None:
             return None
         time.sleep(0.15)
@@ -92,7 +134,7 @@ class ClockSampler:
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in rows)]
         return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': float(rows[0][1]) if rows[0][1].isdigit() else None,
-                'reasons': reasons, 'samples': len(rows)}
+                'reasons': reasons, 'samples': len(rows), 'source': 'nvidia-smi'}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -271,8 +313,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation) stalls kernel launches for tens of
-    # milliseconds, which inside a 10-step timed region once read as 10 ms per step; only its 100 ms polling overlaps the timing
+    # the clock sampler is started BEFORE the warm-up: NVML initialisation stalls kernel launches for tens of milliseconds
     sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
         step(resident[i % 2])
@@ -289,6 +330,9 @@ def main():
     fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     lib.om_launch_count_reset()
+    if sampler is not None:
+        sampler.sparse(args.steps * 0.007)
+        time.sleep(0.03)
     barrier()
     t0 = time.time()
     e0.record()

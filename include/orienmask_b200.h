@@ -177,6 +177,9 @@ typedef struct om_conv om_conv;
 /* Validates the descriptor and precomputes launch geometry and TMA descriptors. */
 int32_t om_conv_create(const om_conv_desc* desc, om_conv** out);
 int32_t om_conv_run(const om_conv* conv, void* stream);
+/* Same launch with the result redirected to `output` (same layout and size as desc.output; layers without a residual): the model
+ * wrapper gives every call freshly allocated head tensors, as the reference's forward does. */
+int32_t om_conv_run_to(const om_conv* conv, void* output, void* stream);
 void om_conv_destroy(om_conv* conv);
 
 /*

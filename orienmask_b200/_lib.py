@@ -72,6 +72,7 @@ SIGNATURES = {
     'om_nms': (c_i32, [c_vp, c_i32, c_f32, c_vp, c_vp, c_vp]),
     'om_conv_create': (c_i32, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_vp)]),
     'om_conv_run': (c_i32, [c_vp, c_vp]),
+    'om_conv_run_to': (c_i32, [c_vp, c_vp, c_vp]),
     'om_conv_destroy': (None, [c_vp]),
     'om_preprocess': (c_i32, [ctypes.POINTER(PrepConfig), c_vp, c_i64, c_i32, c_vp, c_vp]),
     'om_mask_rle': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -37,7 +37,7 @@ struct om_conv {
     int tc_version;      // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (ORIENMASK_B200_CONV=v1, kept for A/B measurements)
 };
 
-extern "C" int32_t om_abi_version(void) { return 4; }
+extern "C" int32_t om_abi_version(void) { return 5; }
 extern "C" const char* om_last_error(void) { return om::error_buffer(); }
 extern "C" int64_t om_launch_count(void) { return om::g_launches; }
 extern "C" void om_launch_count_reset(void) { om::g_launches = 0; }
@@ -79,6 +79,18 @@ extern "C" int32_t om_conv_run(const om_conv* c, void* stream) {
     if (c->desc.precision == OM_PREC_F16)
         return c->tc_version == 2 ? om::tc2_plan_run(c->tc_plan, (cudaStream_t)stream) : om::tc_plan_run(c->tc_plan, (cudaStream_t)stream);
     return om::f32_conv_run(c->desc, (cudaStream_t)stream);
+}
+
+extern "C" int32_t om_conv_run_to(const om_conv* c, void* output, void* stream) {
+    if (!c || !output) return om::fail(OM_ERR_INVALID, "om_conv_run_to: null argument");
+    if (c->desc.precision == OM_PREC_F16) {
+        if (c->tc_version != 2) return om::fail(OM_ERR_UNSUPPORTED, "om_conv_run_to needs the CTA-pair engine");
+        return om::tc2_plan_run(c->tc_plan, (cudaStream_t)stream, output);
+    }
+    if (c->desc.residual) return om::fail(OM_ERR_INVALID, "om_conv_run_to: layers with a residual write in place");
+    om_conv_desc d = c->desc;
+    d.output = output;
+    return om::f32_conv_run(d, (cudaStream_t)stream);
 }
 
 extern "C" void om_conv_destroy(om_conv* c) {

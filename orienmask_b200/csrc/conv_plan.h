@@ -14,7 +14,7 @@ void tc_plan_destroy(void* plan);
 
 // fp16 tcgen05 engine on CTA pairs, cta_group::2 (conv_tc2.cu)
 int32_t tc2_plan_create(const om_conv_desc& d, void** out);
-int32_t tc2_plan_run(const void* plan, cudaStream_t stream);
+int32_t tc2_plan_run(const void* plan, cudaStream_t stream, void* output = nullptr);
 void tc2_plan_destroy(void* plan);
 
 // tensor-core first layer (conv_stem_tc.cu)

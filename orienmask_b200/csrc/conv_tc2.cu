@@ -1074,12 +1074,19 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     return OM_OK;
 }
 
-int32_t tc2_plan_run(const void* vp, cudaStream_t stream) {
+// `output` != nullptr redirects the result (the epilogue stores through a plain pointer, no tensor map): the model's head layers
+// write into tensors allocated per call, so results handed to the caller are never overwritten by the next forward.
+int32_t tc2_plan_run(const void* vp, cudaStream_t stream, void* output) {
     const Tc2Plan* plan = reinterpret_cast<const Tc2Plan*>(vp);
+    Tc2Params p = plan->p;
+    if (output != nullptr) {
+        if (p.has_res || p.res_direct) return fail(OM_ERR_INVALID, "om_conv_run_to: layers with a residual write in place");
+        p.output = output;
+    }
     if (plan->bk == 64)
-        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<64>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, plan->p));
+        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<64>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, p));
     else
-        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<32>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, plan->p));
+        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<32>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, p));
     return check_launch("conv_tc2_kernel");
 }
 

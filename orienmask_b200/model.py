@@ -129,6 +129,7 @@ class _Engine:
                    if v.is_floating_point()}
         self.keep = []            # owns every device tensor the plans point to
         self.plans = []           # ('stem', args) | ('conv', handle)
+        self.head_slot = {}       # plan index of a head layer -> output slot (0..2 bbox scales, 3 orientation)
         self.flops = 0
         self.layers = []          # one entry per launch, in launch order (tools/layer_report.py)
         with torch.cuda.device(device):
@@ -242,8 +243,9 @@ class _Engine:
         self.conv(src, w, None, dst, 1, leaky=False, kind=_lib.OUT_PARTIAL, upadd=upadd, name='%s[%d:%d]' % (prefix, cols[0], cols[1]))
         return dst
 
-    def head(self, prefix, src, out):
+    def head(self, prefix, src, out, slot):
         w, b = self.folded(prefix, 'conv')
+        self.head_slot[len(self.plans)] = slot
         self.conv(src, w, b, None, 1, leaky=False, kind=_lib.OUT_NCHW, nchw=out, name=prefix)
 
     # ---- the schedule (model/orienmask_yolo_fpnplus.py:74-90, model/backbone/darknet.py:47-54) ----
@@ -298,7 +300,7 @@ class _Engine:
             hb = self.act(st, 2 * c)
             self.cbl('bbox_head%d.0' % st, neck, hb, 3)
             out = torch.empty(B, nb, H // st, W // st, **f32)
-            self.head('bbox_head%d.1' % st, hb, out)
+            self.head('bbox_head%d.1' % st, hb, out, len(self.out_bbox))
             self.out_bbox.append(out)
 
         a4, b4 = self.act(4, 128), self.act(4, 256)
@@ -320,7 +322,7 @@ class _Engine:
         # orien_head.0-4 alternate 3x3 (128->256) and 1x1 (256->128): neck4 lives in a4, so start on b4
         o = self.chain('orien_head', neck4, (b4, a4), (3, 1, 3, 1, 3))
         self.out_orien = torch.empty(B, self.nA * 6, H // 4, W // 4, **f32)
-        self.head('orien_head.5', o, self.out_orien)
+        self.head('orien_head.5', o, self.out_orien, 3)
 
     def run_graph(self, x):
         """Same as run(), replayed from a CUDA graph captured on first use (input copied into a static buffer)."""
@@ -331,30 +333,35 @@ class _Engine:
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
                 for _ in range(2):
-                    self.run(self._static_x)
+                    self.run(self._static_x, fresh=False)
             torch.cuda.current_stream(self.device).wait_stream(side)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._graph_out = self.run(self._static_x)
+                self._graph_out = self.run(self._static_x, fresh=False)
             self._graph = g
         self._static_x.copy_(x)
         self._graph.replay()
         return self._graph_out
 
-    def run(self, x):
+    def run(self, x, fresh=True):
+        """fresh=True: the head tensors are allocated for this call (the caller owns them, like the reference's forward);
+        fresh=False (CUDA-graph capture): the engine's static tensors, overwritten by the next call."""
         x = x.contiguous().float()
         with torch.cuda.device(self.device):
             stream = _lib.stream_ptr()
-            for kind, arg in self.plans:
-                if kind == 'conv':
+            outs = ([torch.empty_like(t) for t in self.out_bbox] + [torch.empty_like(self.out_orien)]) if fresh else None
+            for i, (kind, arg) in enumerate(self.plans):
+                if kind == 'conv' and outs is not None and i in self.head_slot:
+                    _lib.check(self.lib.om_conv_run_to(arg, _lib.ptr(outs[self.head_slot[i]]), stream), 'om_conv_run_to')
+                elif kind == 'conv':
                     _lib.check(self.lib.om_conv_run(arg, stream), 'om_conv_run')
                 else:
                     _lib.check(self.lib.om_stem_conv(self.prec, _lib.ptr(x), _lib.ptr(self.stem_w), _lib.ptr(self.stem_b),
                                                      _lib.ptr(arg['t']), self.B, self.H, self.W, self.rows(1), 32, int(bool(arg.get('s2d'))), stream),
                                'om_stem_conv')
         n2 = self.nA * 2
-        o = self.out_orien
-        return ((self.out_bbox[0], o[:, 0:n2]), (self.out_bbox[1], o[:, n2:2 * n2]), (self.out_bbox[2], o[:, 2 * n2:3 * n2]))
+        bbox, o = (outs[:3], outs[3]) if outs is not None else (self.out_bbox, self.out_orien)
+        return ((bbox[0], o[:, 0:n2]), (bbox[1], o[:, n2:2 * n2]), (bbox[2], o[:, 2 * n2:3 * n2]))
 
     def time_layers(self, x, iters=5):
         """Per-launch device times (us, mean over `iters` passes) from CUDA events between the launches."""

@@ -173,3 +173,17 @@ def test_non_plus_model_both_engines():
                     assert np.abs(got - ref).max() < 5e-4
                 else:
                     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 0.03
+
+
+def test_forward_returns_tensors_owned_by_the_caller():
+    """The reference's forward returns fresh tensors; results of one call must survive the next call (both engines)."""
+    from orienmask_b200.synthetic import synthetic_images
+    for prec in ('fp16', 'fp32'):
+        m = _model(prec)
+        a = m(synthetic_images(2, 64, 96, seed=1).cuda())
+        keep = [(b.clone(), o.clone()) for b, o in a]
+        b2 = m(synthetic_images(2, 64, 96, seed=2).cuda())
+        torch.cuda.synchronize()
+        for (x, y), (kx, ky), (nx, ny) in zip(a, keep, b2):
+            assert torch.equal(x, kx) and torch.equal(y, ky)
+            assert x.data_ptr() != nx.data_ptr() and not torch.equal(x, nx)
