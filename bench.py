@@ -258,6 +258,8 @@ def main():
     ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ncu-range', action='store_true', help='cudaProfilerStart/Stop around the timed device-resident loop '
+                    '(ncu --profile-from-start off): the launch list of exactly the timed steps; numbers printed under ncu are not bench values')
     ap.add_argument('--size', type=int, default=544, help='square input size (960 with --batch 8 = config 5); the headline metric is 544')
     args = ap.parse_args()
     global H, W, GFLOP_PER_IMAGE
@@ -334,6 +336,8 @@ def main():
         sampler.sparse(args.steps * 0.007)
         time.sleep(0.03)
     barrier()
+    if args.ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     t0 = time.time()
     e0.record()
     for i in range(args.steps):
@@ -344,6 +348,8 @@ def main():
         gather_detections(out.det, out.cls, out.count, packed=out.packed)
     e1.record()
     barrier()
+    if args.ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     t1 = time.time()
     launches = int(lib.om_launch_count())
     clocks = sampler.stop(t0, t1) if sampler else None
