@@ -67,13 +67,13 @@ class ClockSampler:
     for tens of milliseconds per poll, an NVML field query for a few): with 20 ms polling a 10-step timed region (65 ms)
     read anything between 6.7 and 20 ms per step while the un-sampled end-to-end loop stayed within 2 %.  So the sampler
     polls every 20 ms during the warm-up (same workload, immediately before) and, once `sparse(seconds)` is called with the
-    expected length of the timed region, takes only two samples inside it (at ~1/3 and ~2/3).  nvidia-smi is the fallback."""
+    expected length of the timed region, takes only two samples inside it, in its second half.  nvidia-smi is the fallback."""
     Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
     BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, index):
-        self.rows, self.proc, self.nvml, self.stop_flag, self.period = [], None, None, False, 0.02
+        self.rows, self.proc, self.nvml, self.stop_flag, self.period, self.next_at = [], None, None, False, 0.02, None
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -97,16 +97,25 @@ class ClockSampler:
     def _poll(self):
         n = self.nvml
         while not self.stop_flag:
+            if self.next_at is not None:                      # sparse mode: wait for the scheduled instant
+                if time.time() < self.next_at:
+                    time.sleep(0.004)
+                    continue
+                self.next_at += self.period
             try:
                 mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
                 bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
                 self.rows.append((time.time(), mhz, bits))
             except Exception:
                 pass
-            time.sleep(self.period)
+            if self.next_at is None:
+                time.sleep(self.period)
 
     def sparse(self, region_seconds):
-        self.period = max(0.03, region_seconds / 3.0)
+        """Two samples, at ~55 % and ~85 % of the timed region: by then the host is several steps ahead of the GPU, so a driver
+        query that blocks kernel submission for a few milliseconds no longer idles the device."""
+        self.period = max(0.02, 0.3 * region_seconds)
+        self.next_at = time.time() + 0.03 + 0.55 * region_seconds
 
     def _read(self):
         for line in self.proc.stdout:
@@ -317,24 +326,39 @@ def main():
 
     # the clock sampler is started BEFORE the warm-up: NVML initialisation stalls kernel launches for tens of milliseconds
     sampler = ClockSampler(local) if rank == 0 else None
+    # Warm-up with the SAME object lifetimes as the timed loop: `heads` / `out` of step i stay alive until step i+1 has
+    # allocated its own, so the caching allocator must hold two sets of head / mask tensors (~1.3 GB each).  A warm-up that
+    # dropped each result at once left one set cached, and the second step of the timed region paid a synchronising
+    # cudaMalloc (one 20-130 ms step in an otherwise 6.3 ms series).
+    heads = out = None
     for i in range(args.warmup):
-        step(resident[i % 2])
+        heads = model(resident[i % 2])
+        out = post.apply_padded(heads)
+        gather_detections(out.det, out.cls, out.count, packed=out.packed)
     barrier()
     if sampler is not None:
         t_wait = time.time()
         while not sampler.rows and time.time() - t_wait < 3.0:
             time.sleep(0.05)
     for i in range(2):                       # every rank (the step contains a collective): absorbs rank 0's wait above
-        step(resident[i % 2])
+        heads = model(resident[i % 2])
+        out = post.apply_padded(heads)
+        gather_detections(out.det, out.cls, out.count, packed=out.packed)
     barrier()
 
     # ---- device-resident timing -------------------------------------------------------------
     fwd_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_end = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     lib.om_launch_count_reset()
     if sampler is not None:
         sampler.sparse(args.steps * 0.007)
         time.sleep(0.03)
+    # no garbage collection inside the timed regions: a generation-2 pass of the interpreter (tens of milliseconds with torch's object
+    # graph) in the first steps, before the host is ahead of the GPU, showed up as one 15 ms step in an otherwise 6.4 ms series
+    import gc
+    gc.collect()
+    gc.disable()
     barrier()
     if args.ncu_range:
         torch.cuda.cudart().cudaProfilerStart()
@@ -346,6 +370,7 @@ def main():
         fwd_ev[i][1].record()
         out = post.apply_padded(heads)
         gather_detections(out.det, out.cls, out.count, packed=out.packed)
+        step_end[i].record()
     e1.record()
     barrier()
     if args.ncu_range:
@@ -358,6 +383,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     fwd_ms = statistics.mean(a.elapsed_time(b) for a, b in fwd_ev)
+    per_step = [(e0 if i == 0 else step_end[i - 1]).elapsed_time(step_end[i]) for i in range(args.steps)]
     k_avg = int(out.count.float().mean().item())
 
     # ---- end to end through the public API from pinned host memory -----------------------------
@@ -389,12 +415,14 @@ def main():
             cnt_host.copy_(cnt, non_blocking=True)
         torch.cuda.synchronize()
 
-    e2e_loop(3)
+    e2e_loop(6)
+    gc.collect()
     barrier()
     w0 = time.perf_counter()
     e2e_loop(args.steps)
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - w0], device=dev)
+    gc.enable()
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
@@ -422,6 +450,8 @@ def main():
                     'd2h_bytes_per_step': int(rec_host.numel() * 4 + cnt_host.numel() * 4),
                     'note': 'pinned uint8 HWC images (cv2 layout) -> FastCOCOTransform -> model() -> postprocess -> detection records + '
                             'counts to host; copies double-buffered on a side stream'},
+            'step_ms': {'min': min(per_step), 'median': statistics.median(per_step), 'max': max(per_step),
+                        'argmax': per_step.index(max(per_step))},
             'gpu_launches': launches,
             'clocks': clocks,
             'stages': stages,
