@@ -18,6 +18,7 @@
  *                          get_orien_grid, per-instance orientation thresholding)
  *   om_preprocess          data/transform.py:444-510 (FastCOCOTransform: permute + Resize + Normalize) and infer.py:21-32 (pad)
  *   om_mask_rle            eval/coco_eval.py:108-127,191-205 (_recover_shape_segm + maskUtils.encode of every instance)
+ *   om_mask_areas, om_mask_blend  utils/visualizer.py:46-100,122-127 (resized soft masks, area sort key, alpha blend)
  *   om_stem_conv, om_conv_*  model/base.py:104-137 (ConvBNRelu, BN folded), model/backbone/darknet.py:6-15
  *                          (residual add), model/base.py:95-101 + torch.cat in
  *                          model/orienmask_yolo_fpnplus.py:78-79,85-86 (nearest upsample + concat, done
@@ -249,6 +250,28 @@ typedef struct om_rle_image {
  */
 int32_t om_mask_rle(const om_rle_image* images, int32_t batch, int32_t max_inst, int32_t max_out_h, int32_t max_mask_h,
                     int32_t max_mask_w, int32_t cap, int32_t str_cap, uint32_t* counts, int32_t* n_counts, uint8_t* str, int32_t* str_len, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Visualiser mask blend (utils/visualizer.py:46-100, 122-127)                                   */
+/* ------------------------------------------------------------------------------------------- */
+
+typedef struct om_blend_config {
+    int32_t mask_h, mask_w;        /* network-input size of the instance masks                                 */
+    int32_t top, left;             /* pad_info: first row / column kept (utils/visualizer.py:123-124)          */
+    int32_t crop_h, crop_w;        /* size of the kept window                                                  */
+    int32_t out_h, out_w;          /* the image being drawn on: bilinear resize target (not rounded)           */
+    float alpha;                   /* InferenceVisualizer(alpha=...)                                           */
+} om_blend_config;
+
+/* areas[i] = sum over the image of the resized soft mask i (utils/visualizer.py:69 sorts by it).
+ *   mask    device uint8 0/1 [k, mask_h, mask_w];  scratch  device double [k];  areas  device fp32 [k] */
+int32_t om_mask_areas(const om_blend_config* cfg, const uint8_t* mask, int32_t k, double* scratch, float* areas, void* stream);
+
+/* plot_all_mask (utils/visualizer.py:95-100) in place on `image` (device fp32 [out_h, out_w, 3]):
+ *   order   device int32 [k]   instance indices in drawing order (ascending area)
+ *   colors  device fp32 [k,3]  colour of instance i (not of drawing position) */
+int32_t om_mask_blend(const om_blend_config* cfg, const uint8_t* mask, int32_t k, const int32_t* order, const float* colors,
+                      float* image, void* stream);
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,11 @@ class RleImage(ctypes.Structure):
     ]
 
 
+class BlendConfig(ctypes.Structure):
+    _fields_ = [('mask_h', c_i32), ('mask_w', c_i32), ('top', c_i32), ('left', c_i32), ('crop_h', c_i32), ('crop_w', c_i32),
+                ('out_h', c_i32), ('out_w', c_i32), ('alpha', c_f32)]
+
+
 SRC_U8, SRC_F32 = 0, 1
 
 # name -> (restype, argtypes); every symbol declared in include/orienmask_b200.h
@@ -76,6 +81,8 @@ SIGNATURES = {
     'om_conv_destroy': (None, [c_vp]),
     'om_preprocess': (c_i32, [ctypes.POINTER(PrepConfig), c_vp, c_i64, c_i32, c_vp, c_vp]),
     'om_mask_rle': (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'om_mask_areas': (c_i32, [ctypes.POINTER(BlendConfig), c_vp, c_i32, c_vp, c_vp, c_vp]),
+    'om_mask_blend': (c_i32, [ctypes.POINTER(BlendConfig), c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'om_stem_conv': (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
 }
 

@@ -21,6 +21,7 @@ UNITS = [
     ('post.cu', ['-fmad=false']),
     ('prep.cu', ['-fmad=false']),
     ('rle.cu', ['-fmad=false']),
+    ('blend.cu', ['-fmad=false']),
     ('conv_f32.cu', []),
     ('conv_tc.cu', []),
     ('conv_tc2.cu', []),

@@ -37,7 +37,7 @@ struct om_conv {
     int tc_version;      // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (ORIENMASK_B200_CONV=v1, kept for A/B measurements)
 };
 
-extern "C" int32_t om_abi_version(void) { return 5; }
+extern "C" int32_t om_abi_version(void) { return 6; }
 extern "C" const char* om_last_error(void) { return om::error_buffer(); }
 extern "C" int64_t om_launch_count(void) { return om::g_launches; }
 extern "C" void om_launch_count_reset(void) { om::g_launches = 0; }

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
-    assert _lib.lib().om_abi_version() == 5
+    assert _lib.lib().om_abi_version() == 6
 
 
 def test_config_errors_are_reported_without_a_gpu():
