@@ -63,11 +63,13 @@ def test_dropin_packages_resolve_reference_names():
     """trainer/builder.py:61-77 does getattr(model, 'OrienMaskYOLOFPNPlus'), getattr(eval, 'OrienMaskYOLOPostProcess'),
     getattr(eval.function, 'batched_nms')."""
     import subprocess
-    code = ("import sys; sys.path.insert(0, %r); import model, eval, eval.function as f; "
-            "print(model.OrienMaskYOLOFPNPlus.__module__, eval.OrienMaskYOLOPostProcess.__module__, f.batched_nms.__module__)"
+    code = ("import sys; sys.path.insert(0, %r); import model, eval, eval.function as f; from eval.coco_eval import COCOMetrics; "
+            "print(model.OrienMaskYOLOFPNPlus.__module__, eval.OrienMaskYOLOPostProcess.__module__, f.batched_nms.__module__, "
+            "model.OrienMaskYOLO.__module__, COCOMetrics.__module__)"
             % os.path.join(ROOT, 'orienmask_b200', 'dropin'))
     out = subprocess.check_output([sys.executable, '-c', code], cwd='/tmp').decode().split()
-    assert out == ['orienmask_b200.model', 'orienmask_b200.postprocess', 'orienmask_b200.function']
+    assert out == ['orienmask_b200.model', 'orienmask_b200.postprocess', 'orienmask_b200.function', 'orienmask_b200.model',
+                   'orienmask_b200.coco_format']
 
 
 def test_shard_bounds_cover_batch():
