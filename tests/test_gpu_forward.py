@@ -187,3 +187,43 @@ def test_forward_returns_tensors_owned_by_the_caller():
         for (x, y), (kx, ky), (nx, ny) in zip(a, keep, b2):
             assert torch.equal(x, kx) and torch.equal(y, ky)
             assert x.data_ptr() != nx.data_ptr() and not torch.equal(x, nx)
+
+
+def test_report_fp16_detection_agreement_544():
+    """What the fp16 production engine changes at the OUTPUT of the path: detections of two 544x544 images against the oracle
+    (fp32 forward + post-process on the host), matched by class and box.  Writes gpurun_out/fp16_agreement.json; the gate is
+    loose (fp16 storage moves logits by ~1e-3 relative, which reorders near-ties at the top-400 / top-100 cuts and NMS pairs)."""
+    import json
+    import os
+    import orienmask_b200 as ob
+    from orienmask_b200.synthetic import synthetic_images, synthetic_state_dict
+    from oracle.forward_oracle import forward_oracle
+    from tests.common import ROOT
+    x = synthetic_images(2, 544, 544, seed=1)
+    ref_heads = forward_oracle(synthetic_state_dict(0), x)
+    ref = _oracle(544, 544, 0.005)([(b.numpy(), o.numpy()) for b, o in ref_heads])
+    post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5),
+                                       device=torch.device('cuda:0'), **post_config(544, 544, 0.005))
+    got = post(_model('fp16')(x.cuda()))
+    rows = []
+    for r, g in zip(ref, got):
+        gb, gc, gm = g['bbox'].cpu().numpy(), g['cls'].cpu().numpy(), g['mask'].cpu().numpy()
+        matched, box_err, score_err, ious = 0, [], [], []
+        for i in range(len(gb)):
+            d = np.abs(r['bbox'][:, :4] - gb[i, :4]).max(1) + (r['cls'] != gc[i]) * 1e3
+            j = int(np.argmin(d)) if len(d) else -1
+            if j >= 0 and d[j] <= 5e-3:
+                matched += 1
+                box_err.append(float(d[j]))
+                score_err.append(float(abs(r['bbox'][j, 4] - gb[i, 4])))
+                u = (r['mask'][j] | gm[i]).sum()
+                ious.append(float((r['mask'][j] & gm[i]).sum() / u) if u else 1.0)
+        rows.append({'reference_detections': int(len(r['bbox'])), 'engine_detections': int(len(gb)), 'matched': matched,
+                     'max_box_err': max(box_err or [0.0]), 'max_score_err': max(score_err or [0.0]),
+                     'min_mask_iou': min(ious or [1.0]), 'mean_mask_iou': float(np.mean(ious or [1.0]))})
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'fp16_agreement.json'), 'w'), indent=1)
+    print(json.dumps(rows))
+    for row in rows:
+        assert row['matched'] >= 0.7 * row['reference_detections'], row
+        assert row['max_score_err'] < 2e-2 and row['mean_mask_iou'] > 0.95, row
