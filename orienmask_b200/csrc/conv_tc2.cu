@@ -859,8 +859,8 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     if (d.out_kind != OM_OUT_NCHW && (d.cout % 32 || d.cout_stride % 16 || d.cout_stride < d.cout))
         return fail(OM_ERR_INVALID, "fp16 engine needs cout %% 32 == 0 and an aligned channel pitch for NHWC outputs");
     if (d.upadd && (d.out_w % 2 || d.out_kind == OM_OUT_NCHW)) return fail(OM_ERR_INVALID, "upadd needs an even width and an NHWC output");
-    if (d.stride == 2 && (d.in_rows != 2 * d.out_rows || d.in_w != 2 * d.out_w || d.ksize != 3))
-        return fail(OM_ERR_INVALID, "stride-2 layers must be 3x3 with in_rows == 2*out_rows and in_w == 2*out_w");
+    if (d.stride == 2 && (d.in_w != 2 * d.out_w || d.ksize != 3))
+        return fail(OM_ERR_INVALID, "stride-2 layers must be 3x3 with in_w == 2*out_w");
     if (d.stride == 1 && (d.in_rows != d.out_rows || d.in_w != d.out_w))
         return fail(OM_ERR_INVALID, "stride-1 layers need identical input/output geometry");
     {
@@ -903,6 +903,10 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long flat_pairs = ((p.flat_total + kBlockM - 1) / kBlockM + 1) / 2;
         if (flat_pairs * (cout_pad / bn) > 10ll * (sms / 2)) p.flat = 0;
+    }
+    if (d.stride == 2 && !p.flat && d.in_rows != 2 * d.out_rows) {      // rectangular / parity-plane boxes address rows of the whole batch
+        delete plan;
+        return fail(OM_ERR_INVALID, "this stride-2 layer needs in_rows == 2*out_rows (only im2col-gathered tiles are free of it)");
     }
     p.halo_s2 = d.ksize == 3 && d.stride == 2 && d.in_s2d && d.out_kind != OM_OUT_NCHW && (d.out_w % 8 == 0 || d.out_w >= 64) &&
                 !(halo_env && halo_env[0] == '0') && !getenv("ORIENMASK_B200_NO_HALO_S2");

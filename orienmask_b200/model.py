@@ -138,6 +138,12 @@ class _Engine:
 
     # ---- buffers ---------------------------------------------------------------------------------
     def rows(self, stride):
+        """Rows per image of the padded-row layout at this stride.  Strides 1 / 2 / 4 are tied by the parity-split stride-2
+        layers (rows(in) == 2 * rows(out)); the stride-4 maps carry ONE pad row (the 3x3 layers there hold a third of all FLOPs
+        and every pad row is computed), which fixes 4 and 2 pad rows at strides 2 and 1.  Strides 8 / 16 / 32 keep
+        rows(s) == 2 * rows(2s) so that their up-add sources can be staged by TMA."""
+        if stride <= 4 and os.environ.get('ORIENMASK_B200_TIGHT_ROWS', '1') == '1':
+            return (self.H // 4 + 1) * (4 // stride)
         return self.H // stride + 32 // stride
 
     def act(self, stride, channels, dtype=None, s2d=False):
