@@ -142,8 +142,11 @@ class _Engine:
         layers (rows(in) == 2 * rows(out)); the stride-4 maps carry ONE pad row (the 3x3 layers there hold a third of all FLOPs
         and every pad row is computed), which fixes 4 and 2 pad rows at strides 2 and 1.  Strides 8 / 16 / 32 keep
         rows(s) == 2 * rows(2s) so that their up-add sources can be staged by TMA."""
-        if stride <= 4 and os.environ.get('ORIENMASK_B200_TIGHT_ROWS', '1') == '1':
+        tight = os.environ.get('ORIENMASK_B200_TIGHT_ROWS', '1')
+        if stride <= 4 and tight in ('1', '2'):
             return (self.H // 4 + 1) * (4 // stride)
+        if stride == 8 and tight == '2':
+            return self.H // 8 + 1
         return self.H // stride + 32 // stride
 
     def act(self, stride, channels, dtype=None, s2d=False):
