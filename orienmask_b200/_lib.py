@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'liborienmask_b200.so')
+# ORIENMASK_B200_LIB: another build of the same library (A/B of two kernel versions inside one GPU visit)
+LIB_PATH = os.environ.get('ORIENMASK_B200_LIB') or os.path.join(HERE, 'liborienmask_b200.so')
 
 OM_MAX_SCALES = 4
 OM_MAX_ANCHORS = 16

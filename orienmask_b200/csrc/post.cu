@@ -17,6 +17,7 @@ namespace {
 
 constexpr int kSelThreads = 256;
 constexpr int kHistBins = 2048;
+constexpr int kL0Bins = 256;                  // level-0 digit: 8 bits (every block of the head pass flushes its non-empty bins)
 
 struct PostDev {
     int num_scales, C, H, W, h4, w4;
@@ -35,11 +36,21 @@ struct PostDev {
 };
 
 struct SelState {
-    unsigned hist[3][kHistBins];
-    unsigned prefix, k_rem, total, take_all, T, need_eq, eq_taken, n_out, n_list, pad[3];
+    unsigned hist[2][kHistBins];
+    unsigned prefix, k_rem, total, take_all, n_out, n_list, n_edge, done;
 };
 
-constexpr int kListBuf = 4096;                 // staged survivors per block before a flush (>= 2 rounds of 256 x 8)
+// Radix digits of a score.  Scores are fp32 in (conf_thresh, 1], so their bit patterns span only
+// [bits(conf_thresh), 0x3F800000]: the digits are cut from rel = key - kmin (nb significant bits, nb <= 30), not from
+// the raw pattern (whose top 11 bits are the sign, the exponent and two mantissa bits: ~30 distinct values).
+// bin0 = rel >> s0 (8 bits), bin1 = (rel >> s1) & m1 (<= 11 bits), bin2 = rel & m2 (<= 11 bits).
+struct KeyBins {
+    unsigned kmin;
+    int s0, s1;
+    unsigned m1, m2;
+};
+
+constexpr int kTailThreads = 512;
 
 __device__ __forceinline__ float sigmoidf_rn(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -54,123 +65,12 @@ __device__ __forceinline__ void locate_pred(const PostDev& d, int n, int& s, int
     cell = r - a * plane;
 }
 
-// Pass 1 (the only pass over the head tensors): one thread per prediction, 80 plane-strided (coalesced across
-// the warp) class reads each.  Every (prediction, class) whose score clears conf_thresh is appended to the
-// image's candidate list (score bits + flat index, unordered) and counted in the level-0 radix histogram; the
-// remaining radix levels and the collection run over that list, not over the heads, so sigmoid/exp are
-// evaluated once per pair.  Logits that cannot clear the threshold even with sigma(obj) = 1 skip the
-// sigmoid entirely (margin 0.01 in logit space >> any rounding of the fp32 sigmoid).
-__global__ void __launch_bounds__(kSelThreads) conf_compact_kernel(PostDev d, SelState* st, unsigned* keys, unsigned* flats,
-                                                                   long long list_cap, float reject_logit) {
-    __shared__ unsigned sh[kHistBins];
-    __shared__ uint2 s_buf[kListBuf];
-    __shared__ unsigned s_cnt, s_base;
-    const int b = blockIdx.y;
-    SelState& S = st[b];
-    for (int i = threadIdx.x; i < kHistBins; i += kSelThreads) sh[i] = 0;
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    const int n = blockIdx.x * kSelThreads + threadIdx.x;
-    const float* pc = nullptr;
-    int plane = 0;
-    float obj = 0.f;
-    bool live = false;
-    if (n < d.n_pred) {
-        int s, a, cell;
-        locate_pred(d, n, s, a, cell, plane);
-        const float* p = d.bbox[s] + (long long)b * d.bstride[s] + (long long)(a * (5 + d.C)) * plane + cell;
-        const float ol = __ldg(p + 4 * plane);
-        if (ol >= reject_logit) {
-            obj = sigmoidf_rn(ol);
-            live = true;
-        }
-        pc = p + 5 * plane;
-    }
-    unsigned* kout = keys + (long long)b * list_cap;
-    unsigned* fout = flats + (long long)b * list_cap;
-    for (int c0 = 0; c0 < d.C; c0 += 8) {
-        if (live) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (c0 + i < d.C) ? __ldg(pc + (long long)(c0 + i) * plane) : -1e30f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (v[i] < reject_logit) continue;
-                const float conf = sigmoidf_rn(v[i]) * obj;
-                if (conf > d.conf_thresh) {
-                    const unsigned key = __float_as_uint(conf);
-                    atomicAdd(&sh[key >> 21], 1u);
-                    const unsigned slot = atomicAdd(&s_cnt, 1u);
-                    s_buf[slot] = make_uint2(key, (unsigned)(n * d.C + c0 + i));
-                }
-            }
-        }
-        __syncthreads();
-        const unsigned cnt = s_cnt;
-        if (cnt > (unsigned)(kListBuf - kSelThreads * 8) || c0 + 8 >= d.C) {      // block-uniform
-            if (threadIdx.x == 0) s_base = atomicAdd(&S.n_list, cnt);
-            __syncthreads();                              // every thread has read s_cnt by now
-            if (threadIdx.x == 0) s_cnt = 0;
-            const unsigned base = s_base;
-            for (unsigned i = threadIdx.x; i < cnt; i += kSelThreads) {
-                kout[base + i] = s_buf[i].x;
-                fout[base + i] = s_buf[i].y;
-            }
-            __syncthreads();
-        }
-    }
-    for (int i = threadIdx.x; i < kHistBins; i += kSelThreads)
-        if (sh[i]) atomicAdd(&S.hist[0][i], sh[i]);
-}
-
-// Radix levels 1 and 2 (MODE 1, 2: histogram of the next 11 / 10 key bits under the current prefix) and the
-// collection (MODE 3) over the candidate list; a fixed number of blocks per image strides over the list.
-template <int MODE>
-__global__ void __launch_bounds__(kSelThreads) select_list_kernel(PostDev d, SelState* st, const unsigned* keys, const unsigned* flats,
-                                                                  long long list_cap, uint2* raw) {
-    __shared__ unsigned sh[kHistBins];
-    const int b = blockIdx.y;
-    SelState& S = st[b];
-    if (MODE < 3 && S.take_all) return;
-    const unsigned prefix = S.prefix;
-    const unsigned T = S.T, need_eq = S.need_eq, take_all = S.take_all;
-    const unsigned n_list = S.n_list;
-    if (MODE < 3) {
-        for (int i = threadIdx.x; i < kHistBins; i += kSelThreads) sh[i] = 0;
-        __syncthreads();
-    }
-    const unsigned* kin = keys + (long long)b * list_cap;
-    const unsigned* fin = flats + (long long)b * list_cap;
-    for (unsigned i = blockIdx.x * kSelThreads + threadIdx.x; i < n_list; i += gridDim.x * kSelThreads) {
-        const unsigned key = kin[i];
-        if (MODE == 1) {
-            if ((key >> 21) == prefix) atomicAdd(&sh[(key >> 10) & 2047u], 1u);
-        } else if (MODE == 2) {
-            if ((key >> 10) == prefix) atomicAdd(&sh[key & 1023u], 1u);
-        } else {
-            bool take = take_all || key > T;
-            if (!take && key == T) take = atomicAdd(&S.eq_taken, 1u) < need_eq;
-            if (take) {
-                const unsigned slot = atomicAdd(&S.n_out, 1u);
-                if (slot < (unsigned)d.nms_pre) raw[(long long)b * d.nms_pre + slot] = make_uint2(key, fin[i]);
-            }
-        }
-    }
-    if (MODE < 3) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < kHistBins; i += kSelThreads)
-            if (sh[i]) atomicAdd(&S.hist[MODE][i], sh[i]);
-    }
-}
-
-// One warp per image: walk the histogram from the top bin down until k_rem elements are covered.
-template <int PASS>
-__global__ void select_scan_kernel(SelState* st, int k) {
-    SelState& S = st[blockIdx.x];
-    if (PASS > 0 && S.take_all) return;
-    const int lane = threadIdx.x;
+// One warp: walk a 2048-bin histogram from the top bin down until k_rem elements are covered.
+// Returns (to every lane) the bin that holds the k_rem-th largest element, the number of elements still to take
+// from that bin, and the total count.
+__device__ __noinline__ void scan_top(const unsigned* h, unsigned k_rem, int& bin_out, unsigned& rem_out, unsigned& total_out) {
+    const int lane = threadIdx.x & 31;
     constexpr int per = kHistBins / 32;
-    const unsigned* h = S.hist[PASS];
     unsigned sum = 0;
     const int top = kHistBins - 1 - lane * per;          // this lane covers bins top, top-1, ..., top-per+1
     for (int i = 0; i < per; ++i) sum += h[top - i];
@@ -180,30 +80,183 @@ __global__ void select_scan_kernel(SelState* st, int k) {
         unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned k_rem = (PASS == 0) ? (unsigned)k : S.k_rem;
-    if (PASS == 0) {
-        if (lane == 0) S.total = total;
-        if (total <= (unsigned)k) {
-            if (lane == 0) { S.take_all = 1; S.T = 0; S.need_eq = 0; }
-            return;
-        }
-    }
+    total_out = __shfl_sync(0xffffffffu, incl, 31);
     const unsigned excl = incl - sum;
-    if (excl < k_rem && k_rem <= incl) {                 // exactly one lane
+    int bin = 0;
+    unsigned rem = 0;
+    const bool mine = excl < k_rem && k_rem <= incl;     // at most one lane
+    if (mine) {
         unsigned above = excl;
-        int bin = top;
+        bin = top;
         for (int i = 0; i < per; ++i) {
             bin = top - i;
             const unsigned c = h[bin];
             if (above + c >= k_rem) break;
             above += c;
         }
-        const unsigned rem = k_rem - above;
-        if (PASS == 0) { S.prefix = (unsigned)bin; S.k_rem = rem; }
-        if (PASS == 1) { S.prefix = (S.prefix << 11) | (unsigned)bin; S.k_rem = rem; }
-        if (PASS == 2) { S.T = (S.prefix << 10) | (unsigned)bin; S.need_eq = rem; }
+        rem = k_rem - above;
     }
+    const unsigned who = __ballot_sync(0xffffffffu, mine);
+    const int src = who ? __ffs(who) - 1 : 0;
+    bin_out = __shfl_sync(0xffffffffu, bin, src);
+    rem_out = __shfl_sync(0xffffffffu, rem, src);
+}
+
+// Pass 1 (the only pass over the head tensors): one thread per prediction, 80 plane-strided (coalesced across
+// the warp) class reads each.  Every (prediction, class) whose score clears conf_thresh is appended to the
+// image's candidate list (score bits + flat index, unordered; slots handed out per warp and round of 8 classes) and counted in the level-0 radix histogram; the remaining radix levels and the collection
+// run over that list, not over the heads, so sigmoid/exp are evaluated once per pair.  Logits that cannot clear the
+// threshold even with sigma(obj) = 1 skip the sigmoid entirely (margin 0.01 in logit space >> any rounding of the
+// fp32 sigmoid).  The last block of an image to finish walks the level-0 histogram (no separate launch).
+__global__ void __launch_bounds__(kSelThreads) conf_compact_kernel(PostDev d, KeyBins kb, SelState* st, unsigned* keys, unsigned* flats,
+                                                                   long long list_cap, float reject_logit) {
+    __shared__ unsigned sh[kHistBins];
+    __shared__ unsigned s_last;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    SelState& S = st[b];
+    for (int i = threadIdx.x; i < kL0Bins; i += kSelThreads) sh[i] = 0;
+    __syncthreads();
+    const int n = blockIdx.x * kSelThreads + threadIdx.x;
+    const float* pc = nullptr;
+    int plane = 0;
+    float obj = 0.f, rej = reject_logit;
+    bool live = false;
+    if (n < d.n_pred) {
+        int s, a, cell;
+        locate_pred(d, n, s, a, cell, plane);
+        const float* p = d.bbox[s] + (long long)b * d.bstride[s] + (long long)(a * (5 + d.C)) * plane + cell;
+        const float ol = __ldg(p + 4 * plane);
+        if (ol >= reject_logit) {
+            obj = sigmoidf_rn(ol);
+            live = true;
+            // per-prediction bound: sigma(x) * obj > conf_thresh needs x > logit(conf_thresh / obj); 0.05 in logit space
+            // is a relative margin of >= 5e-4 on sigma(x) for conf_thresh / obj < 0.99 -- far above any fp32 rounding
+            // of the sigmoid, the quotient or the product -- so only pairs that certainly fail skip the sigmoid
+            const float r = d.conf_thresh / obj;
+            const float t = r < 0.99f ? logf(r / (1.0f - r)) - 0.05f : 4.0f;      // sigma(4) = 0.982 < 0.99 (1 - 5e-4)
+            rej = fmaxf(rej, t);                                                   // NaN / -inf (conf_thresh <= 0): keeps rej
+        }
+        pc = p + 5 * plane;
+    }
+    unsigned* kout = keys + (long long)b * list_cap;
+    unsigned* fout = flats + (long long)b * list_cap;
+    for (int c0 = 0; c0 < d.C; c0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (live && c0 + i < d.C) ? __ldg(pc + (long long)(c0 + i) * plane) : -1e30f;
+        unsigned okmask = 0, kbits[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            kbits[i] = 0;
+            if (v[i] >= rej) {
+                const float conf = sigmoidf_rn(v[i]) * obj;
+                if (live && conf > d.conf_thresh) okmask |= 1u << i;
+                kbits[i] = __float_as_uint(conf);
+            }
+        }
+        // list slots of the round: one warp scan of the per-lane counts and one atomic on the image's list length per
+        // warp; the warp then owns a contiguous range of the list and there is no block-level synchronisation at all
+        const unsigned mine = __popc(okmask);
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const unsigned wtotal = __shfl_sync(0xffffffffu, incl, 31);
+        if (wtotal) {                                                   // warp-uniform
+            unsigned slot = 0;
+            if (lane == 31) slot = atomicAdd(&S.n_list, wtotal);
+            slot = __shfl_sync(0xffffffffu, slot, 31) + incl - mine;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if ((okmask >> i) & 1u) {
+                    kout[slot] = kbits[i];
+                    fout[slot] = (unsigned)(n * d.C + c0 + i);
+                    ++slot;
+                    atomicAdd(&sh[(kbits[i] - kb.kmin) >> kb.s0], 1u);
+                }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kL0Bins; i += kSelThreads)
+        if (sh[i]) atomicAdd(&S.hist[0][i], sh[i]);
+    // last block of this image: level-0 scan
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&S.done, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int i = threadIdx.x; i < kHistBins; i += kSelThreads) sh[i] = i < kL0Bins ? __ldcg(&S.hist[0][i]) : 0u;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int bin;
+        unsigned rem, total;
+        scan_top(sh, (unsigned)d.nms_pre, bin, rem, total);
+        if (lane == 0) {
+            S.total = total;
+            if (total <= (unsigned)d.nms_pre) { S.take_all = 1; }
+            else { S.prefix = (unsigned)bin; S.k_rem = rem; }
+        }
+    }
+}
+
+// Pass 2, over the candidate list (a fixed number of blocks per image strides over it): candidates above the
+// level-0 boundary bin are certain members of the top-k and go straight to the output; candidates inside it are
+// counted in the level-1 histogram and copied to the image's edge list, the only thing the tail kernel still reads.
+__global__ void __launch_bounds__(kSelThreads) select_edge_kernel(PostDev d, KeyBins kb, SelState* st, const unsigned* keys, const unsigned* flats,
+                                                                  long long list_cap, uint2* edge, uint2* raw) {
+    __shared__ unsigned sh[kHistBins];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    SelState& S = st[b];
+    const unsigned n_list = S.n_list;
+    const unsigned stride = gridDim.x * kSelThreads;
+    if (blockIdx.x * kSelThreads >= n_list) return;
+    const unsigned take_all = S.take_all, prefix = S.prefix;
+    for (int i = threadIdx.x; i < kHistBins; i += kSelThreads) sh[i] = 0;
+    __syncthreads();
+    const unsigned* kin = keys + (long long)b * list_cap;
+    const unsigned* fin = flats + (long long)b * list_cap;
+    uint2* eout = edge + (long long)b * list_cap;
+    constexpr int U = 4;
+    for (unsigned base0 = blockIdx.x * kSelThreads; base0 < n_list; base0 += U * stride) {        // block-uniform trip count
+        const unsigned i0 = base0 + threadIdx.x;
+        unsigned key[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned i = i0 + u * stride;
+            key[u] = i < n_list ? __ldg(kin + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned i = i0 + u * stride;
+            const bool valid = i < n_list;
+            const unsigned rel = key[u] - kb.kmin;
+            const unsigned b0 = rel >> kb.s0;
+            const bool sure = valid && (take_all || b0 > prefix);
+            const bool onedge = valid && !take_all && b0 == prefix;
+            if (sure) {
+                const unsigned slot = atomicAdd(&S.n_out, 1u);
+                if (slot < (unsigned)d.nms_pre) raw[(long long)b * d.nms_pre + slot] = make_uint2(key[u], fin[i]);
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, onedge);
+            if (bal == 0) continue;                                     // warp-uniform
+            const int leader = __ffs(bal) - 1;
+            unsigned base = 0;
+            if (lane == leader) base = atomicAdd(&S.n_edge, (unsigned)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (onedge) {
+                eout[base + __popc(bal & ((1u << lane) - 1u))] = make_uint2(key[u], fin[i]);
+                atomicAdd(&sh[(rel >> kb.s1) & kb.m1], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kHistBins; i += kSelThreads)
+        if (sh[i]) atomicAdd(&S.hist[1][i], sh[i]);
 }
 
 __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int NP) {
@@ -222,15 +275,68 @@ __device__ __forceinline__ void bitonic_sort_u64(unsigned long long* key, int NP
     __syncthreads();
 }
 
-// One CTA per image: order the <= nms_pre raw (key, flat) pairs the way the reference orders its
-// candidates, decode their boxes and emit the candidate arrays.
-__global__ void __launch_bounds__(256) cand_finalize_kernel(PostDev d, SelState* st, const uint2* raw, int* cand_count,
-                                                            float* cand_det, int* cand_cls, int* cand_pred) {
+// One CTA per image, the tail of the selection: level-1 boundary from the histogram of the edge pass, level-2
+// histogram and boundary over the edge list (normally a few dozen entries: one of 256 level-0 bins), collection
+// of the edge candidates above the threshold (ties at the threshold: as many as are still needed), then order the
+// <= nms_pre (key, flat) pairs the way the reference orders its candidates, decode their boxes and emit the
+// candidate arrays.
+__global__ void __launch_bounds__(kTailThreads) select_tail_kernel(PostDev d, KeyBins kb, SelState* st, const uint2* edge, long long list_cap,
+                                                                   uint2* raw, int* cand_count, float* cand_det, int* cand_cls, int* cand_pred) {
     extern __shared__ unsigned long long skey[];
+    __shared__ unsigned sh[kHistBins];
+    __shared__ unsigned s_prefix, s_krem, s_T, s_need, s_eq, s_out;
     const int b = blockIdx.x;
-    const SelState& S = st[b];
-    const int n = min((int)S.n_out, d.nms_pre);
+    SelState& S = st[b];
     const bool take_all = S.take_all != 0;
+    if (!take_all) {
+        const unsigned n_edge = S.n_edge;
+        const uint2* ein = edge + (long long)b * list_cap;
+        if (threadIdx.x < 32) {
+            int bin;
+            unsigned rem, total;
+            scan_top(S.hist[1], S.k_rem, bin, rem, total);
+            if (threadIdx.x == 0) {
+                s_prefix = (S.prefix << (kb.s0 - kb.s1)) | (unsigned)bin;
+                s_krem = rem;
+                s_eq = 0;
+                s_out = S.n_out;
+            }
+        }
+        for (int i = threadIdx.x; i < kHistBins; i += kTailThreads) sh[i] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        for (unsigned i = threadIdx.x; i < n_edge; i += kTailThreads) {
+            const unsigned rel = ein[i].x - kb.kmin;
+            if ((rel >> kb.s1) == prefix) atomicAdd(&sh[rel & kb.m2], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int bin;
+            unsigned rem, total;
+            scan_top(sh, s_krem, bin, rem, total);
+            if (threadIdx.x == 0) {
+                s_T = (prefix << kb.s1) | (unsigned)bin;
+                s_need = rem;
+            }
+        }
+        __syncthreads();
+        const unsigned T = s_T, need_eq = s_need;
+        for (unsigned i = threadIdx.x; i < n_edge; i += kTailThreads) {
+            const uint2 e = ein[i];
+            const unsigned rel = e.x - kb.kmin;
+            bool take = rel > T;
+            if (!take && rel == T) take = atomicAdd(&s_eq, 1u) < need_eq;
+            if (take) {
+                const unsigned slot = atomicAdd(&s_out, 1u);
+                if (slot < (unsigned)d.nms_pre) raw[(long long)b * d.nms_pre + slot] = e;
+            }
+        }
+        __syncthreads();                                   // raw[] of this image is complete and visible to the block
+    } else {
+        if (threadIdx.x == 0) s_out = S.n_out;
+        __syncthreads();
+    }
+    const int n = min((int)s_out, d.nms_pre);
     for (int i = threadIdx.x; i < d.NP; i += blockDim.x) {
         unsigned long long v = ~0ull;
         if (i < n) {
@@ -341,7 +447,12 @@ __global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
 
     for (int i = threadIdx.x; i < a.NP; i += blockDim.x)
         skey[i] = i < n ? (((unsigned long long)(~orderable(dets[i * 5 + 4])) << 32) | (unsigned)i) : ~0ull;
-    bitonic_sort_u64(skey, a.NP);                                    // rank -> position, score desc / index asc
+    __syncthreads();
+    {   // om_decode_select hands its candidates over in exactly this order unless it took every candidate: sort only if needed
+        int unsorted = 0;
+        for (int i = threadIdx.x; i + 1 < a.NP; i += blockDim.x) unsorted |= skey[i] > skey[i + 1];
+        if (__syncthreads_or(unsorted)) bitonic_sort_u64(skey, a.NP); // rank -> position, score desc / index asc
+    }
 
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
         const int p = (int)(skey[r] & 0xffffffffu);
@@ -387,15 +498,34 @@ __global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
     }
     __syncthreads();
 
+    // greedy chain, 32 ranks at a time: every lane fetches the chunk's 32 diagonal words (independent shuffles) and
+    // resolves the chunk's own dependencies in registers (32 unrolled ALU steps), then the full rows of the kept boxes
+    // are OR-ed into the removed set (lane = word) as independent predicated loads -- instead of one dependent
+    // shuffle + shared-memory round trip per rank
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         unsigned removed = 0;
-        for (int r = 0; r < n; ++r) {
-            const unsigned rw = __shfl_sync(0xffffffffu, removed, r >> 5);
-            if (!((rw >> (r & 31)) & 1u)) {
-                if (lane == 0) kept_rank[r] = 1;
-                if (lane < nw) removed |= mask[r * nw + lane];
-            }
+        const int nchunks = (n + 31) >> 5;
+        for (int c = 0; c < nchunks; ++c) {
+            const int r = c * 32 + lane;
+            const unsigned diag = r < n ? mask[r * nw + c] : 0u;
+            unsigned dg[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dg[i] = __shfl_sync(0xffffffffu, diag, i);
+            const int left = n - c * 32;
+            const unsigned validbits = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+            unsigned w = __shfl_sync(0xffffffffu, removed, c) | ~validbits;     // ranks past n count as removed
+            unsigned keptbits = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (!((w >> i) & 1u)) { keptbits |= 1u << i; w |= dg[i]; }
+            if (r < n) kept_rank[r] = (unsigned char)((keptbits >> lane) & 1u);
+            unsigned acc = 0;
+            const unsigned* mrow = mask + (size_t)c * 32 * nw + (lane < nw ? lane : 0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if ((keptbits >> i) & 1u) acc |= mrow[i * nw];
+            if (lane < nw) removed |= acc;
         }
     }
     __syncthreads();
@@ -624,8 +754,8 @@ int32_t allow_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
-// workspace layout: [batch] SelState | [batch][nms_pre] raw (key, flat) | [batch][cap] keys | [batch][cap] flats,
-// cap = n_pred * num_classes (every pair may clear conf_thresh, e.g. untrained weights)
+// workspace layout: [batch] SelState | [batch][nms_pre] raw (key, flat) | [batch][cap] keys | [batch][cap] flats |
+// [batch][cap] edge (key, flat); cap = n_pred * num_classes (every pair may clear conf_thresh, e.g. untrained weights)
 static size_t ws_align(size_t v) { return (v + 255) & ~(size_t)255; }
 
 extern "C" int32_t om_post_workspace_bytes(const om_post_config* cfg, int32_t batch, size_t* bytes) {
@@ -635,8 +765,25 @@ extern "C" int32_t om_post_workspace_bytes(const om_post_config* cfg, int32_t ba
     if (batch < 1 || !bytes) return om::fail(OM_ERR_INVALID, "bad batch / null output");
     const size_t cap = (size_t)d.n_pred * d.C;
     *bytes = ws_align((size_t)batch * sizeof(SelState)) + ws_align((size_t)batch * cfg->nms_pre * sizeof(uint2)) +
-             2 * ws_align((size_t)batch * cap * sizeof(unsigned));
+             2 * ws_align((size_t)batch * cap * sizeof(unsigned)) + ws_align((size_t)batch * cap * sizeof(uint2));
     return OM_OK;
+}
+
+// Radix digits of the scores in (conf_thresh, 1] (see KeyBins).
+static KeyBins make_bins(float conf_thresh) {
+    KeyBins kb{};
+    unsigned kmin = 0;
+    if (conf_thresh > 0.f) memcpy(&kmin, &conf_thresh, 4);
+    const unsigned kmax = 0x3F800000u;                               // 1.0f: sigma(cls) * sigma(obj) <= 1
+    const unsigned span1 = kmin < kmax ? kmax - kmin : 0u;            // largest rel
+    int nb = 0;
+    while (nb < 32 && (span1 >> nb) != 0u) ++nb;
+    kb.kmin = kmin;
+    kb.s0 = nb > 8 ? nb - 8 : 0;
+    kb.s1 = nb > 19 ? nb - 19 : 0;
+    kb.m1 = (1u << (kb.s0 - kb.s1)) - 1u;
+    kb.m2 = (1u << kb.s1) - 1u;
+    return kb;
 }
 
 extern "C" int32_t om_decode_select(const om_post_config* cfg, const float* const* bbox, const int64_t* bbox_batch_stride,
@@ -661,12 +808,15 @@ extern "C" int32_t om_decode_select(const om_post_config* cfg, const float* cons
     unsigned* keys = reinterpret_cast<unsigned*>(ws);
     ws += ws_align((size_t)batch * cap * sizeof(unsigned));
     unsigned* flats = reinterpret_cast<unsigned*>(ws);
+    ws += ws_align((size_t)batch * cap * sizeof(unsigned));
+    uint2* edge = reinterpret_cast<uint2*>(ws);
     OM_CUDA_TRY(cudaMemsetAsync(state, 0, (size_t)batch * sizeof(SelState), st));
     // sigma(x) <= conf_thresh for x <= logit(conf_thresh): such logits can never yield a candidate
     const double t = (double)d.conf_thresh;
     const float reject_logit = t >= 1.0 ? 3.0e38f : (float)(log(t / (1.0 - t)) - 0.01);
+    const KeyBins kb = make_bins(d.conf_thresh);
     dim3 grid(om::ceil_div(d.n_pred, kSelThreads), batch);
-    conf_compact_kernel<<<grid, kSelThreads, 0, st>>>(d, state, keys, flats, cap, reject_logit);
+    conf_compact_kernel<<<grid, kSelThreads, 0, st>>>(d, kb, state, keys, flats, cap, reject_logit);
     if ((rc = om::check_launch("conf_compact"))) return rc;
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -676,20 +826,10 @@ extern "C" int32_t om_decode_select(const om_post_config* cfg, const float* cons
     const int max_useful = (int)((cap + kSelThreads - 1) / kSelThreads);
     if (per_image > max_useful) per_image = max_useful;
     dim3 lgrid(per_image, batch);
-    select_scan_kernel<0><<<batch, 32, 0, st>>>(state, d.nms_pre);
-    if ((rc = om::check_launch("select_scan<0>"))) return rc;
-    select_list_kernel<1><<<lgrid, kSelThreads, 0, st>>>(d, state, keys, flats, cap, raw);
-    if ((rc = om::check_launch("select_list<1>"))) return rc;
-    select_scan_kernel<1><<<batch, 32, 0, st>>>(state, d.nms_pre);
-    if ((rc = om::check_launch("select_scan<1>"))) return rc;
-    select_list_kernel<2><<<lgrid, kSelThreads, 0, st>>>(d, state, keys, flats, cap, raw);
-    if ((rc = om::check_launch("select_list<2>"))) return rc;
-    select_scan_kernel<2><<<batch, 32, 0, st>>>(state, d.nms_pre);
-    if ((rc = om::check_launch("select_scan<2>"))) return rc;
-    select_list_kernel<3><<<lgrid, kSelThreads, 0, st>>>(d, state, keys, flats, cap, raw);
-    if ((rc = om::check_launch("select_list<3>"))) return rc;
-    cand_finalize_kernel<<<batch, 256, (size_t)d.NP * 8, st>>>(d, state, raw, cand_count, cand_det, cand_cls, cand_pred);
-    return om::check_launch("cand_finalize");
+    select_edge_kernel<<<lgrid, kSelThreads, 0, st>>>(d, kb, state, keys, flats, cap, edge, raw);
+    if ((rc = om::check_launch("select_edge"))) return rc;
+    select_tail_kernel<<<batch, kTailThreads, (size_t)d.NP * 8, st>>>(d, kb, state, edge, cap, raw, cand_count, cand_det, cand_cls, cand_pred);
+    return om::check_launch("select_tail");
 }
 
 extern "C" int32_t om_batched_nms(const om_post_config* cfg, const int32_t* cand_count, const float* cand_det,
