@@ -821,7 +821,7 @@ extern "C" int32_t om_decode_select(const om_post_config* cfg, const float* cons
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    int per_image = (4 * sms + batch - 1) / batch;
+    int per_image = (8 * sms + batch - 1) / batch;        // one wave of 8 resident blocks per SM
     if (per_image < 1) per_image = 1;
     const int max_useful = (int)((cap + kSelThreads - 1) / kSelThreads);
     if (per_image > max_useful) per_image = max_useful;
