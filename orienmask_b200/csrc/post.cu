@@ -305,9 +305,16 @@ __global__ void __launch_bounds__(kTailThreads) select_tail_kernel(PostDev d, Ke
         for (int i = threadIdx.x; i < kHistBins; i += kTailThreads) sh[i] = 0;
         __syncthreads();
         const unsigned prefix = s_prefix;
-        for (unsigned i = threadIdx.x; i < n_edge; i += kTailThreads) {
-            const unsigned rel = ein[i].x - kb.kmin;
-            if ((rel >> kb.s1) == prefix) atomicAdd(&sh[rel & kb.m2], 1u);
+        constexpr int U = 4;                               // independent loads in flight (the list is long only when scores tie en masse)
+        for (unsigned i0 = threadIdx.x; i0 < n_edge; i0 += U * kTailThreads) {
+            unsigned key[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) key[u] = i0 + u * kTailThreads < n_edge ? ein[i0 + u * kTailThreads].x : 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned rel = key[u] - kb.kmin;
+                if (i0 + u * kTailThreads < n_edge && (rel >> kb.s1) == prefix) atomicAdd(&sh[rel & kb.m2], 1u);
+            }
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -321,14 +328,20 @@ __global__ void __launch_bounds__(kTailThreads) select_tail_kernel(PostDev d, Ke
         }
         __syncthreads();
         const unsigned T = s_T, need_eq = s_need;
-        for (unsigned i = threadIdx.x; i < n_edge; i += kTailThreads) {
-            const uint2 e = ein[i];
-            const unsigned rel = e.x - kb.kmin;
-            bool take = rel > T;
-            if (!take && rel == T) take = atomicAdd(&s_eq, 1u) < need_eq;
-            if (take) {
-                const unsigned slot = atomicAdd(&s_out, 1u);
-                if (slot < (unsigned)d.nms_pre) raw[(long long)b * d.nms_pre + slot] = e;
+        for (unsigned i0 = threadIdx.x; i0 < n_edge; i0 += U * kTailThreads) {
+            uint2 e[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) e[u] = i0 + u * kTailThreads < n_edge ? ein[i0 + u * kTailThreads] : make_uint2(0u, 0u);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (i0 + u * kTailThreads >= n_edge) continue;
+                const unsigned rel = e[u].x - kb.kmin;
+                bool take = rel > T;
+                if (!take && rel == T) take = atomicAdd(&s_eq, 1u) < need_eq;
+                if (take) {
+                    const unsigned slot = atomicAdd(&s_out, 1u);
+                    if (slot < (unsigned)d.nms_pre) raw[(long long)b * d.nms_pre + slot] = e[u];
+                }
             }
         }
         __syncthreads();                                   // raw[] of this image is complete and visible to the block

@@ -133,6 +133,17 @@ def test_post_nonsquare_small_limits():
         _compare(res[b], ref[b]['bbox'], ref[b]['cls'], ref[b]['mask'], ordered=True)
 
 
+@pytest.mark.parametrize('thr', [1e-6, 0.05, 0.5, 0.97])
+def test_post_conf_thresholds_radix_digit_shapes(thr):
+    """The selection cuts its radix digits from bits(score) - bits(conf_thresh): 28 significant bits at threshold 1e-6
+    (8 + 11 + 9; the library rejects thresholds <= 0), 26 at the north-star 0.005, a handful just below 1 -- every shape must select like the oracle."""
+    heads = synthetic_heads(2, 64, 96, seed=31)
+    ref = _oracle(64, 96, thr)([(b.numpy(), o.numpy()) for b, o in heads])
+    res = _post(64, 96, thr)([(b.cuda(), o.cuda()) for b, o in heads])
+    for b in range(2):
+        _compare(res[b], ref[b]['bbox'], ref[b]['cls'], ref[b]['mask'], ordered=True)
+
+
 def test_post_all_tied_scores():
     """Every (prediction, class) score identical: selection among exact ties is unspecified in the
     reference (torch.topk); the kernel must still return exactly nms_pre candidates and a legal result."""
