@@ -73,7 +73,8 @@ typedef struct om_post_config {
     int32_t nms_post;                           /* <= nms_pre                                     */
 } om_post_config;
 
-/* Bytes of device scratch om_decode_select needs for `batch` images. */
+/* Bytes of device scratch om_decode_select needs for `batch` images: 16 bytes per (prediction, class) pair and image
+ * (candidate keys + flat indices, edge list) plus the radix state -- every pair may clear conf_thresh. */
 int32_t om_post_workspace_bytes(const om_post_config* cfg, int32_t batch, size_t* bytes);
 
 /*
