@@ -71,6 +71,9 @@ class OrienMaskYOLOFPNPlus(nn.Module):
                 conv.bias = nn.Parameter(torch.empty(s.cout).uniform_(-bound, bound))
         for p in self.parameters():
             p.requires_grad_(False)
+        # one engine (buffer plan of ~0.1 GB per image at 544x544) per distinct (batch, H, W); least recently used plans are
+        # dropped beyond this many so that a stream of differently padded batches cannot grow without bound
+        self.max_engines = max(1, int(os.environ.get('ORIENMASK_B200_MAX_ENGINES', '4')))
         self._engines = {}
         self._weights_version = 0
         if pretrained is not None:            # backbone checkpoint: take every key that exists with the same shape
@@ -99,12 +102,17 @@ class OrienMaskYOLOFPNPlus(nn.Module):
             raise RuntimeError('orienmask_b200 runs on CUDA (sm_100a) only; got a %s tensor and there is no CPU fallback' % x.device)
         if x.dim() != 4 or x.size(1) != 3 or x.size(2) % 32 or x.size(3) % 32:
             raise ValueError('expected [B,3,H,W] with H, W multiples of 32, got %s' % (tuple(x.shape),))
-        key = (int(x.size(0)), int(x.size(2)), int(x.size(3)), self.precision, x.device.index)
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = _Engine(self, *key[:3], precision=self.precision, device=x.device)
-            self._engines[key] = eng
+        eng = self._engine_for((int(x.size(0)), int(x.size(2)), int(x.size(3)), self.precision, x.device.index), x.device)
         return eng.run_graph(x) if self.use_cuda_graph else eng.run(x)
+
+    def _engine_for(self, key, device):
+        eng = self._engines.pop(key, None)
+        if eng is None:
+            while len(self._engines) >= self.max_engines:        # dicts keep insertion order: the first key is the oldest use
+                del self._engines[next(iter(self._engines))]
+            eng = _Engine(self, *key[:3], precision=self.precision, device=device)
+        self._engines[key] = eng                                  # (re-)inserted last = most recently used
+        return eng
 
 
 class OrienMaskYOLO(OrienMaskYOLOFPNPlus):

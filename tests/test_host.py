@@ -49,6 +49,29 @@ def test_model_state_dict_layout_and_loud_cpu_failure():
         m(torch.zeros(1, 3, 64, 64))
 
 
+def test_engine_plans_are_bounded_lru(monkeypatch):
+    """A stream of differently shaped batches keeps at most max_engines buffer plans, dropping the least recently used."""
+    import orienmask_b200 as ob
+    from orienmask_b200 import model as mod
+    built = []
+
+    class FakeEngine:
+        def __init__(self, model, B, H, W, precision, device):
+            built.append((B, H, W))
+    monkeypatch.setattr(mod, '_Engine', FakeEngine)
+    monkeypatch.setenv('ORIENMASK_B200_MAX_ENGINES', '2')
+    m = ob.OrienMaskYOLOFPNPlus(3, 80)
+    key = lambda b: (b, 64, 64, 'fp16', 0)
+    a = m._engine_for(key(1), 'cuda:0')
+    m._engine_for(key(2), 'cuda:0')
+    assert m._engine_for(key(1), 'cuda:0') is a and len(built) == 2        # hit: nothing rebuilt, (1) becomes most recent
+    m._engine_for(key(3), 'cuda:0')                                          # evicts (2), the least recently used
+    assert list(m._engines) == [key(1), key(3)]
+    assert m._engine_for(key(1), 'cuda:0') is a and len(built) == 3
+    m.load_state_dict(m.state_dict())                                        # new weights: every packed plan is dropped
+    assert not m._engines
+
+
 def test_postprocess_constructor_mirrors_reference():
     import orienmask_b200 as ob
     cfg = post_config(544, 544)
