@@ -95,6 +95,34 @@ def test_dropin_packages_resolve_reference_names():
                    'orienmask_b200.coco_format']
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/trainer'), reason='needs the reference checkout (build container only)')
+def test_reference_builder_builds_the_engine_from_its_own_config():
+    """The seam end to end on the reference's side: its unmodified trainer/builder.py (which also imports trainer.trainer ->
+    eval.counter, trainer.tester -> eval.coco_eval at import time) and its own north-star config dict, with the drop-in
+    packages first on sys.path, construct this repo's model / post-process / COCOMetrics."""
+    import subprocess
+    from oracle import build_ref
+    build_ref.write_stubs()
+    code = '''
+import sys
+sys.path[:0] = [%r, %r, '/root/reference']
+import torch
+import config as config_module
+from trainer import builder
+import eval, model
+cfg = getattr(config_module, 'orienmask_yolo_coco_544_anchor4_fpn_plus_infer')
+cfg['model']['pretrained'] = None                                   # infer.py:79
+m = builder.build(cfg['model'], builder.model_module)
+p = builder.build_postprocess(cfg['postprocess'], device=torch.device('cuda:0'))
+assert builder.tester_module.COCOMetrics.__module__ == 'orienmask_b200.coco_format'
+assert eval.EvalCounter.__module__ == 'eval.counter'                # not replaced: the reference's own file
+print(type(m).__module__, type(p).__module__, len(m.state_dict()), p.nms_thresh, p.conf_thresh, p.nms_pre, p.nms_post, p.grid_size)
+''' % (os.path.join(ROOT, 'orienmask_b200', 'dropin'), build_ref.STUBS)
+    out = subprocess.check_output([sys.executable, '-c', code], cwd='/tmp').decode().split(None, 7)
+    assert out[:7] == ['orienmask_b200.model', 'orienmask_b200.postprocess', '524', '0.5', '0.005', '400', '100']
+    assert out[7].strip() == '[(17, 17), (34, 34), (68, 68)]'
+
+
 def test_shard_bounds_cover_batch():
     from orienmask_b200.sharding import shard_bounds
     for total in (1, 7, 32, 33):
