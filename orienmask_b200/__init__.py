@@ -8,7 +8,7 @@ Public surface (mirrors the reference's names so its infer.py / test.py run unch
     OrienMaskYOLOPostProcess   eval/orienmask_yolo_postprocess.py (decode + NMS + masks kernels)
     batched_nms, nms           eval/function.py
     FastCOCOTransform, pad     data/transform.py:444-510, infer.py:21-32 (pre-process kernel)
-    COCOMetrics                eval/coco_eval.py:23-205 (mask crop/resize/RLE kernel; no AP accumulation)
+    COCOMetrics                eval/coco_eval.py:23-205 (mask crop/resize/RLE kernel; AP accumulation delegated to pycocotools)
     Tester                     trainer/tester.py:11-62 (evaluation loop over a dataloader)
     InferenceVisualizer        utils/visualizer.py:33-127 (mask area sort + alpha-blend kernels; boxes drawn by cv2)
 """

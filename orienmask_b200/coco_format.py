@@ -6,8 +6,10 @@
 ``{'bbox': [...], 'segm': [...]}`` lists of dicts.  What differs is where the work happens: the reference copies every
 instance mask to the host (one synchronising D2H each) and resizes / encodes it on the CPU; here the crop, flips,
 bilinear resize, rounding, run-length encoding and the COCO string compression of all instances of the batch are one
-kernel, and only the strings cross PCIe.  ``coco_eval`` (pycocotools' AP accumulation) is out of scope.
+kernel, and only the strings cross PCIe.  ``coco_eval`` hands the collected results to pycocotools' ``COCOeval`` (the AP
+accumulation itself is that library's CPU code, outside the path) and fills the attributes ``trainer/tester.py:52-67`` reads.
 """
+import contextlib
 import ctypes
 import json
 import os
@@ -109,9 +111,13 @@ class COCOMetrics:
         self.segm_pred_file = os.path.join(save_dir, 'segm_prediction.json')
         self.reset()
 
+    metric_keys = ['AP', 'AP50', 'AP75', 'APS', 'APM', 'APL', 'AR1', 'AR10', 'AR100', 'ARS', 'ARM', 'ARL']
+
     def reset(self):
         self.bbox_results = []
         self.segm_results = []
+        self.bbox_eval_stats, self.segm_eval_stats = [], []
+        self.bbox_eval_per_cats_stats, self.segm_eval_per_cats_stats = [], []
 
     def to_coco_format(self, image_info, detections):
         result = {'bbox': self._to_bbox_coco_format(image_info, detections)}
@@ -134,8 +140,51 @@ class COCOMetrics:
         self.segm_results += update['segm']
 
     def coco_eval(self, per_cats=False):
-        raise NotImplementedError('AP accumulation is pycocotools\' COCOeval (not part of the hot path): dump the results with '
-                                  'save_as_json() and evaluate them with the reference')
+        """AP / AR accumulation (eval/coco_eval.py:77-106,206-219).  The accumulation is pycocotools' ``COCOeval`` -- a
+        third-party CPU library outside the path; this method only hands it the results collected here, so that
+        ``trainer/tester.py:52-55`` runs unchanged.  Raises when pycocotools is not installed (it is not in this image)."""
+        try:
+            from pycocotools.coco import COCO
+            from pycocotools.cocoeval import COCOeval
+        except ImportError as e:
+            raise RuntimeError('COCOMetrics.coco_eval needs pycocotools (AP accumulation is not part of orienmask_b200); the '
+                               'results are available through save_as_json(): %s' % e)
+        log = {}
+        quiet = open(os.devnull, 'w')
+        try:
+            with contextlib.redirect_stdout(quiet):
+                gt = COCO(self.gt_file)
+                jobs = [('bbox', self.bbox_pred_file, self.bbox_results)]
+                if self.with_mask:
+                    jobs.append(('segm', self.segm_pred_file, self.segm_results))
+                for kind, path, results in jobs:
+                    with open(path, 'w') as handle:
+                        json.dump(results, handle)
+                    ev = COCOeval(gt, gt.loadRes(path), iouType=kind)
+                    ev.evaluate()
+                    ev.accumulate()
+                    ev.summarize()
+                    setattr(self, kind + '_eval_stats', ev.stats)
+                    if per_cats:
+                        setattr(self, kind + '_eval_per_cats_stats', self._per_category_ap(ev))
+                    for key, value in zip(self.metric_keys, ev.stats.tolist()):
+                        log['%s_%s' % (kind, key)] = value
+        finally:
+            quiet.close()
+        return log
+
+    def _per_category_ap(self, ev):
+        """AP per category in percent: mean of the valid (> -1) precisions over IoU thresholds and recall points, all areas,
+        the largest max-dets setting (precision axes: iou, recall, category, area range, max dets)."""
+        prec = ev.eval['precision']
+        if prec.shape[2] != self.cat2label.numel():
+            raise ValueError('%d categories evaluated, %d in cat2label' % (prec.shape[2], self.cat2label.numel()))
+        out = []
+        for c in range(prec.shape[2]):
+            p = prec[:, :, c, 0, -1]
+            p = p[p > -1]
+            out.append(float(np.mean(p) * 100) if p.size else float('nan'))
+        return out
 
     # ---- eval/coco_eval.py:129-188 -------------------------------------------------------------
     @staticmethod

@@ -1,5 +1,9 @@
 """Detections -> COCO format: oracle vs the reference's golden outputs and hand-derived RLE known
 answers (CPU); CUDA kernel vs oracle, bit-exact on counts and strings (GPU)."""
+import json
+import os
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -196,3 +200,58 @@ def test_tester_loop_over_a_loader(tmp_path):
     ref = tester.coco_metrics.to_coco_format(batches[0][2], dets)
     n0 = len(ref['segm'])
     assert [r['segmentation'] for r in saved['segm'][:n0]] == [r['segmentation'] for r in ref['segm']]
+
+
+def test_coco_eval_hands_results_to_pycocotools(tmp_path, monkeypatch):
+    """COCOMetrics.coco_eval (eval/coco_eval.py:77-106,206-219) only drives pycocotools' COCOeval: checked against a
+    stand-in that records the calls, since pycocotools is not in this image.  Without it the method fails loudly."""
+    import types
+    import numpy as np
+    from orienmask_b200.coco_format import COCOMetrics
+    calls = []
+
+    class COCO:
+        def __init__(self, gt):
+            calls.append(('gt', gt))
+
+        def loadRes(self, path):
+            calls.append(('res', os.path.basename(path), json.load(open(path))))
+            return path
+
+    class COCOeval:
+        def __init__(self, gt, res, iouType):
+            self.kind = iouType
+            calls.append(('eval', iouType))
+
+        def evaluate(self):
+            calls.append('evaluate')
+
+        def accumulate(self):
+            prec = -np.ones((10, 101, 2, 4, 3))
+            prec[:, :, 0, 0, -1] = 0.5                      # category 0: AP 50; category 1 has no valid entry -> nan
+            self.eval = {'precision': prec}
+
+        def summarize(self):
+            print('noise that must not reach stdout')
+            self.stats = np.arange(12) / 10.0 + (1 if self.kind == 'segm' else 0)
+
+    pkg = types.ModuleType('pycocotools')
+    coco_mod, eval_mod = types.ModuleType('pycocotools.coco'), types.ModuleType('pycocotools.cocoeval')
+    coco_mod.COCO, eval_mod.COCOeval = COCO, COCOeval
+    for name, mod in (('pycocotools', pkg), ('pycocotools.coco', coco_mod), ('pycocotools.cocoeval', eval_mod)):
+        monkeypatch.setitem(sys.modules, name, mod)
+    m = COCOMetrics(gt_file='gt.json', cat2label=[1, 2], with_mask=True, save_dir=str(tmp_path))
+    m.update_results({'bbox': [{'image_id': 1, 'category_id': 1, 'bbox': [0, 0, 1, 1], 'score': 0.5}],
+                      'segm': [{'image_id': 1, 'category_id': 1, 'segmentation': {'size': [2, 2], 'counts': '04'}, 'score': 0.5}]})
+    log = m.coco_eval(per_cats=True)
+    assert calls[0] == ('gt', 'gt.json') and calls[1][:2] == ('res', 'bbox_prediction.json') and calls[1][2] == m.bbox_results
+    assert ('eval', 'bbox') in calls and ('eval', 'segm') in calls and calls.count('evaluate') == 2
+    assert log['bbox_AP'] == 0.0 and abs(log['segm_AR1'] - 1.6) < 1e-12 and len(log) == 24
+    assert list(m.bbox_eval_stats) == list(np.arange(12) / 10.0) and m.segm_eval_stats[0] == 1.0
+    assert m.bbox_eval_per_cats_stats[0] == 50.0 and np.isnan(m.bbox_eval_per_cats_stats[1])
+    m.reset()
+    assert m.bbox_results == [] and m.segm_eval_per_cats_stats == []
+    for name in ('pycocotools', 'pycocotools.coco', 'pycocotools.cocoeval'):
+        monkeypatch.setitem(sys.modules, name, None)       # import now raises ImportError
+    with pytest.raises(RuntimeError, match='needs pycocotools'):
+        m.coco_eval()
