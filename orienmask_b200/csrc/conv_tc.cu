@@ -446,7 +446,11 @@ int32_t tc_plan_create(const om_conv_desc& d, void** out) {
     plan->grid = tiles < sms ? tiles : sms;
     // the attribute is per kernel function, not per launch: always opt in to the full 227 KB
     constexpr int kMaxSmem = 227 * 1024;
-    if (plan->smem > (size_t)kMaxSmem) { delete plan; return fail(OM_ERR_INVALID, "tile needs %zu bytes of shared memory", plan->smem); }
+    if (plan->smem > (size_t)kMaxSmem) {
+        const size_t need = plan->smem;
+        delete plan;
+        return fail(OM_ERR_INVALID, "tile needs %zu bytes of shared memory", need);
+    }
     cudaError_t e = bk == 64
         ? cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
         : cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
