@@ -55,6 +55,8 @@ extern "C" int32_t om_conv_create(const om_conv_desc* d, om_conv** out) {
     if (d->out_h != (d->in_h + d->stride - 1) / d->stride || d->out_w != (d->in_w + d->stride - 1) / d->stride)
         return om::fail(OM_ERR_INVALID, "output geometry does not match 'same' padding with stride %d", d->stride);
     if (!d->input || !d->weights || !d->output) return om::fail(OM_ERR_INVALID, "om_conv_create: null tensor pointer");
+    if (d->out_kind != OM_OUT_NCHW && d->cout_stride < d->cout)
+        return om::fail(OM_ERR_INVALID, "cout_stride %d is smaller than cout %d", d->cout_stride, d->cout);
     if (d->residual && d->out_kind != OM_OUT_ACT) return om::fail(OM_ERR_INVALID, "residual only with activation outputs");
     if (d->upadd && d->up_rows < 1) return om::fail(OM_ERR_INVALID, "upadd needs up_rows");
     if (d->in_s2d && (d->stride != 2 || d->in_rows % 2 || d->in_w % 2)) return om::fail(OM_ERR_INVALID, "in_s2d needs a stride-2 layer over even rows/width");

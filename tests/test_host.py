@@ -34,6 +34,75 @@ def test_config_errors_are_reported_without_a_gpu():
     assert rc == -1 and b'num_scales' in lib.om_last_error()
 
 
+def test_conv_descriptor_errors_are_reported_without_a_gpu():
+    """om_conv_create validates the descriptor before it touches CUDA: each bad field gives OM_ERR_* and a message."""
+    from orienmask_b200 import _lib
+    lib = _lib.lib()
+
+    def desc(**kw):
+        d = _lib.ConvDesc()
+        d.precision, d.batch = _lib.PREC_F16, 1
+        d.in_h = d.in_w = d.out_h = d.out_w = 16
+        d.in_rows = d.out_rows = 17
+        d.cin, d.cout, d.cout_stride, d.ksize, d.stride, d.leaky, d.out_kind = 64, 64, 64, 3, 1, 1, _lib.OUT_ACT
+        d.input = d.weights = d.output = 256
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+
+    cases = [(dict(ksize=5), -3, b'ksize'), (dict(stride=3), -3, b'stride'), (dict(precision=7), -1, b'precision'),
+             (dict(in_rows=16), -1, b'in_rows'), (dict(out_h=8), -1, b'geometry'), (dict(input=0), -1, b'null tensor'),
+             (dict(cout_stride=32), -1, b'cout_stride'), (dict(cin=48), -1, b'cin'), (dict(batch=0), -1, b'non-positive'),
+             (dict(residual=256, out_kind=_lib.OUT_NCHW), -1, b'residual'), (dict(in_s2d=1), -1, b'in_s2d')]
+    for kw, code, text in cases:
+        handle = _lib.c_vp()
+        rc = lib.om_conv_create(desc(**kw), handle)
+        assert rc == code and text in lib.om_last_error(), (kw, rc, lib.om_last_error())
+        assert not handle.value
+    assert lib.om_conv_run(None, None) == -1 and lib.om_conv_run_to(None, None, None) == -1
+    lib.om_conv_destroy(None)
+
+
+def test_entry_point_argument_errors_without_a_gpu():
+    """Every C-ABI entry point rejects bad arguments with OM_ERR_* + a message before any CUDA call."""
+    import orienmask_b200 as ob
+    from orienmask_b200 import _lib
+    lib = _lib.lib()
+    post = ob.OrienMaskYOLOPostProcess(**post_config(544, 544))
+    cfg, null = ctypes.byref(post._cfg), None
+
+    def err(rc, text, code=-1):
+        assert rc == code and text in lib.om_last_error(), (rc, lib.om_last_error())
+
+    n = ctypes.c_size_t(0)
+    assert lib.om_post_workspace_bytes(cfg, 32, ctypes.byref(n)) == 0
+    assert n.value >= 32 * 18207 * 80 * 16                         # 16 bytes per (prediction, class) pair and image
+    err(lib.om_post_workspace_bytes(cfg, 0, ctypes.byref(n)), b'bad batch')
+    err(lib.om_decode_select(cfg, null, null, 1, null, null, null, null, null, null), b'om_decode_select')
+    err(lib.om_batched_nms(cfg, null, null, null, null, 1, null, null, null, null, null, null, null), b'om_batched_nms')
+    err(lib.om_mask_assemble(cfg, null, null, null, null, null, 1, null, null), b'om_mask_assemble')
+    err(lib.om_nms(null, 2000, 0.5, null, null, null), b'outside [0, 1024]')
+    err(lib.om_nms(null, 4, 0.5, null, null, null), b'null argument')
+    bad = _lib.PostConfig.from_buffer_copy(post._cfg)
+    bad.nms_post = 500
+    err(lib.om_post_workspace_bytes(ctypes.byref(bad), 1, ctypes.byref(n)), b'nms_post')
+    bad = _lib.PostConfig.from_buffer_copy(post._cfg)
+    bad.image_h = 500
+    err(lib.om_post_workspace_bytes(ctypes.byref(bad), 1, ctypes.byref(n)), b'multiple of 32')
+    prep = _lib.PrepConfig()
+    err(lib.om_preprocess(ctypes.byref(prep), null, 0, 1, null, null), b'om_preprocess')
+    prep.src_h = prep.src_w = prep.resize_h = prep.resize_w = 8
+    prep.out_h = prep.out_w = 4
+    prep.src_dtype = _lib.SRC_U8
+    err(lib.om_preprocess(ctypes.byref(prep), 256, 0, 1, 256, null), b'does not fit')
+    err(lib.om_mask_rle(null, 1, 1, 1, 1, 1, 1, 1, null, null, null, null, null), b'om_mask_rle')
+    blend = _lib.BlendConfig()
+    err(lib.om_mask_areas(ctypes.byref(blend), null, 1, null, null, null), b'')
+    err(lib.om_mask_blend(ctypes.byref(blend), null, 1, null, null, null, null), b'')
+    err(lib.om_stem_conv(_lib.PREC_F16, 256, 256, 256, 256, 1, 16, 32, 17, 64, 0, null), b'cout must be 32', code=-3)
+    err(lib.om_stem_conv(_lib.PREC_F16, 256, 256, 256, 256, 1, 16, 32, 16, 32, 0, null), b'bad geometry')
+
+
 def test_model_state_dict_layout_and_loud_cpu_failure():
     import orienmask_b200 as ob
     from orienmask_b200.arch import state_dict_shapes, macs_per_image
