@@ -191,7 +191,7 @@ def run_reference(args, rank):
                       'e2e': {'value': v, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
 
-def measure_stages(torch, ob, transform, host_u8, out, dev, iters=10):
+def measure_stages(torch, ob, transform, host_u8, out, dev, iters=10, post=None, heads=None):
     """The two neighbours of the path, each timed alone with CUDA events against the HBM roofline:
     pre-process (uint8 HWC -> fp32 NCHW) and detections -> COCO RLE (masks -> run-length strings for 480x640 originals)."""
     from orienmask_b200.coco_format import encode_masks
@@ -229,6 +229,15 @@ def measure_stages(torch, ob, transform, host_u8, out, dev, iters=10):
                          'what': 'uint8 HWC [%d,%d,%d,3] -> fp32 NCHW, one prep_kernel launch' % tuple(x.shape[:3])}
     dets = out.to_list()
     counts = [int(d['bbox'].shape[0]) for d in dets]
+    if post is not None and heads is not None:
+        # the post-process half of the headline step alone (decode/select + NMS + masks: 6 launches), against the HBM roofline.
+        # Algorithmic bytes: every head value read once, one mask byte written per (instance, pixel).
+        us = timed(lambda: post.apply_padded(heads))
+        nbytes = sum(int(b.numel()) * 4 for b, _ in heads) + int(heads[0][1].numel()) * 3 * 4 + sum(counts) * H * W
+        res['postprocess'] = {'us': us, 'bytes': nbytes, 'GBps': nbytes / us / 1e3, 'frac_of_hbm': nbytes / us / 1e3 / hbm,
+                              'what': 'decode + confidence filter + top-%d + class-wise NMS + top-%d + mask assembly for %d images '
+                                      '(%d instances); the mask kernel is write-only (measured write ceiling 3.9 TB/s, DESIGN finding 12)'
+                                      % (post.nms_pre, post.nms_post, len(counts), sum(counts))}
     infos = [{'id': i, 'height': 480 * H // 544, 'width': 640 * W // 544, 'collate_pad': [0, 0, 0, 0, H, W]} for i in range(len(dets))]
     masks = [d['mask'] for d in dets]
     lib = _lib.lib()
@@ -434,7 +443,7 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s, e2e_wall_s = (float(v) for v in e2e_t.tolist())
 
-    stages = measure_stages(torch, ob, transform, host[0], out, dev) if rank == 0 else None
+    stages = measure_stages(torch, ob, transform, host[0], out, dev, post=post, heads=heads) if rank == 0 else None
 
     if rank == 0:
         peaks = measured_peaks()
