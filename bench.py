@@ -230,7 +230,7 @@ def measure_stages(torch, ob, transform, host_u8, out, dev, iters=10, post=None,
     dets = out.to_list()
     counts = [int(d['bbox'].shape[0]) for d in dets]
     if post is not None and heads is not None:
-        # the post-process half of the headline step alone (decode/select + NMS + masks: 6 launches), against the HBM roofline.
+        # the post-process half of the headline step alone (decode/select + NMS + masks: 5 launches), against the HBM roofline.
         # Algorithmic bytes: every head value read once, one mask byte written per (instance, pixel).
         us = timed(lambda: post.apply_padded(heads))
         nbytes = sum(int(b.numel()) * 4 for b, _ in heads) + int(heads[0][1].numel()) * 3 * 4 + sum(counts) * H * W
