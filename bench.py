@@ -186,7 +186,9 @@ def run_reference(args, rank):
     print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/sec', 'n_gpus': args.gpus,
                       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
                       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                      'config': {'workload': 'bs=32 544x544 forward+decode+NMS+masks (bounded CPU sample of %d images/step)' % sample},
+                      'config': {'workload': 'bs=%d %dx%d per GPU: DarkNet-53+FPNPlus forward + decode + batched NMS + mask assembly' % (BATCH, H, W),
+                                 'sample': 'each step is a bounded CPU sample of %d images of that workload' % sample,
+                                 'weights': 'synthetic_state_dict(seed 0)', 'precision': 'fp32 (torch CPU / oneDNN)'},
                       'cpu_baseline': desc,
                       'e2e': {'value': v, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}))
 
