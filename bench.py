@@ -268,6 +268,11 @@ def measure_stages(torch, ob, transform, host_u8, out, dev, iters=10, post=None,
     return res
 
 
+def bench_device(torch, local):
+    """The rank's GPU (a seam for tests/test_bench_flow.py, which walks main() on stand-ins without a GPU)."""
+    return torch.device('cuda', local)
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -306,7 +311,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (the product path has no CPU fallback)')
     torch.cuda.set_device(local)
-    dev = torch.device('cuda', local)
+    dev = bench_device(torch, local)
     if world > 1:
         os.environ.setdefault('NCCL_DEBUG', 'WARN')        # keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
