@@ -76,11 +76,19 @@ class OrienMaskYOLOFPNPlus(nn.Module):
         self.max_engines = max(1, int(os.environ.get('ORIENMASK_B200_MAX_ENGINES', '4')))
         self._engines = {}
         self._weights_version = 0
-        if pretrained is not None:            # backbone checkpoint: take every key that exists with the same shape
+        if pretrained is not None:
+            # model/base.py:48-64: a *backbone* checkpoint (keys relative to DarkNet53: 'conv1.conv_block.0.weight', ...);
+            # every key the backbone has with the same shape is taken, the others are reported and ignored
             ckpt = torch.load(pretrained, map_location='cpu')
             own = self.state_dict()
-            own.update({k: v for k, v in ckpt.items() if k in own and v.shape == own[k].shape})
+            taken = {'backbone.' + k: v for k, v in ckpt.items()
+                     if 'backbone.' + k in own and tuple(v.shape) == tuple(own['backbone.' + k].shape)}
+            ignored = [k for k in ckpt if 'backbone.' + k not in taken]
+            own.update(taken)
             self.load_state_dict(own)
+            print('[%s] Load pretrained model %s' % (type(self).__name__, pretrained))
+            if ignored:
+                print('Ignore keys:', ignored)
 
     # -- weight-version tracking: any reload or device/dtype move drops the packed weights ---------
     def load_state_dict(self, *a, **k):

@@ -118,6 +118,23 @@ def test_model_state_dict_layout_and_loud_cpu_failure():
         m(torch.zeros(1, 3, 64, 64))
 
 
+def test_pretrained_backbone_checkpoint_is_loaded_like_the_reference(tmp_path, capsys):
+    """model/base.py:48-64 + darknet.py:39: `pretrained` names a DarkNet-53 checkpoint whose keys are relative to the backbone;
+    matching keys are taken, shape mismatches and unknown keys are ignored (and listed)."""
+    import orienmask_b200 as ob
+    ckpt = {'conv1.conv_block.0.weight': torch.full((32, 3, 3, 3), 0.25), 'conv1.conv_block.1.running_var': torch.full((32,), 3.0),
+            'conv2.0.conv_block.0.weight': torch.zeros(1, 1), 'fc.weight': torch.zeros(1000, 1024)}
+    path = str(tmp_path / 'darknet53.pth')
+    torch.save(ckpt, path)
+    m = ob.OrienMaskYOLOFPNPlus(3, 80, pretrained=path)
+    sd = m.state_dict()
+    assert torch.equal(sd['backbone.conv1.conv_block.0.weight'], ckpt['conv1.conv_block.0.weight'])
+    assert torch.equal(sd['backbone.conv1.conv_block.1.running_var'], ckpt['conv1.conv_block.1.running_var'])
+    assert sd['backbone.conv2.0.conv_block.0.weight'].shape == (64, 32, 3, 3)
+    out = capsys.readouterr().out
+    assert 'Ignore keys' in out and 'fc.weight' in out and 'conv2.0.conv_block.0.weight' in out
+
+
 def test_engine_plans_are_bounded_lru(monkeypatch):
     """A stream of differently shaped batches keeps at most max_engines buffer plans, dropping the least recently used."""
     import orienmask_b200 as ob
