@@ -4,8 +4,8 @@ Same constructor arguments and call signature (``visualizer(detections, image, p
 part -- resizing every kept instance mask to the image (bilinear, not rounded), ordering the instances by area and the
 alpha blend of ``plot_all_mask`` -- is two kernels (``om_mask_areas``, ``om_mask_blend``) that never materialise the resized
 masks; boxes and labels are drawn by the same cv2 calls as the reference, on the host, after the one D2H copy of the image.
-The class names / category ids come from the caller (``classes=``, ``cat2label=``) because the reference takes them from its
-dataset classes; the defaults are the 80 COCO category ids and ``str(label)`` names.
+The class names / category ids default to the tables of the reference's dataset classes for ``dataset='COCO'`` / ``'VOC'``
+(``data/dataset.py:42-62,104-112``); other datasets pass ``classes=`` / ``cat2label=``.
 """
 import random
 
@@ -18,6 +18,19 @@ PALETTE = ((244, 67, 54), (233, 30, 99), (156, 39, 176), (103, 58, 183), (63, 81
            (0, 188, 212), (0, 150, 136), (76, 175, 80), (139, 195, 74), (205, 220, 57), (255, 235, 59), (255, 193, 7),
            (255, 152, 0), (255, 87, 34), (121, 85, 72), (158, 158, 158), (96, 125, 139))
 COCO_CAT_IDS = [i for i in range(1, 91) if i not in (12, 26, 29, 30, 45, 66, 68, 69, 71, 83)]
+# label text per dataset name, as the reference's dataset classes spell it (data/dataset.py:42-62,104-112: darknet-style names)
+DATASET_LABELS = {
+    'COCO': (COCO_CAT_IDS, (
+        'person bicycle car motorbike aeroplane bus train truck boat traffic-light fire-hydrant stop-sign parking-meter bench '
+        'bird cat dog horse sheep cow elephant bear zebra giraffe backpack umbrella handbag tie suitcase frisbee skis snowboard '
+        'sports-ball kite baseball-bat baseball-glove skateboard surfboard tennis-racket bottle wine-glass cup fork knife spoon '
+        'bowl banana apple sandwich orange broccoli carrot hot-dog pizza donut cake chair sofa potted-plant bed dining-table '
+        'toilet tv-monitor laptop mouse remote keyboard cell-phone microwave oven toaster sink refrigerator book clock vase '
+        'scissors teddy-bear hair-drier toothbrush').split()),
+    'VOC': (list(range(1, 21)), (
+        'aeroplane bicycle bird boat bottle bus car cat chair cow dining-table dog horse motorbike person potted-plant sheep '
+        'sofa train tv-monitor').split()),
+}
 
 
 def blend_masks(image, masks, colors, pad_info, alpha):
@@ -52,8 +65,9 @@ def blend_masks(image, masks, colors, pad_info, alpha):
 class InferenceVisualizer:
     def __init__(self, dataset, device, with_mask=True, conf_thresh=0.3, alpha=0.5, line_thickness=1, classes=None, cat2label=None):
         self.dataset = dataset
-        self.cat2label = torch.tensor(cat2label if cat2label is not None else COCO_CAT_IDS, dtype=torch.uint8, device=device)
-        self.classes = list(classes) if classes is not None else [str(int(c)) for c in self.cat2label.tolist()]
+        ids, names = DATASET_LABELS.get(dataset, (COCO_CAT_IDS, None))          # utils/visualizer.py:36-38: <dataset>Dataset.CAT2LABEL / .CLASSES
+        self.cat2label = torch.tensor(cat2label if cat2label is not None else ids, dtype=torch.uint8, device=device)
+        self.classes = list(classes) if classes is not None else (names or [str(int(c)) for c in self.cat2label.tolist()])
         self.device = device
         self.with_mask = with_mask
         self.conf_thresh = conf_thresh

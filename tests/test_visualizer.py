@@ -61,3 +61,22 @@ def test_visualizer_call_on_post_process_output():
     random.seed(7)
     blended = plain(det, image.cuda(), pad_info)
     assert np.abs(blended.astype(np.int32) - np.round(ref).astype(np.int32)).max() <= 1
+
+
+def test_default_label_tables_match_the_reference_dataset_classes():
+    """InferenceVisualizer('COCO' | 'VOC', ...) labels boxes with the reference's own class names (utils/visualizer.py:36-38)."""
+    import os
+    import re
+    from orienmask_b200.visualizer import DATASET_LABELS, InferenceVisualizer
+    assert len(DATASET_LABELS['COCO'][0]) == len(DATASET_LABELS['COCO'][1]) == 80 and len(DATASET_LABELS['VOC'][1]) == 20
+    v = InferenceVisualizer('COCO', 'cpu')
+    assert v.classes[0] == 'person' and v.classes[79] == 'toothbrush' and int(v.cat2label[79]) == 90
+    assert InferenceVisualizer('Other', 'cpu', classes=['a'], cat2label=[7]).classes == ['a']
+    src = '/root/reference/data/dataset.py'
+    if os.path.isfile(src):                                    # build container: compare with the reference's tables
+        text = open(src).read()
+        tables = re.findall(r"CLASSES = \[(.*?)\]", text, re.S)
+        ids = re.findall(r"CAT2LABEL = \[(.*?)\]", text, re.S)
+        for name, names_src, ids_src in zip(('COCO', 'VOC'), tables, ids):
+            assert re.findall(r"'([^']+)'", names_src) == DATASET_LABELS[name][1]
+            assert [int(t) for t in re.findall(r"\d+", ids_src)] == list(DATASET_LABELS[name][0])
