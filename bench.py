@@ -160,6 +160,20 @@ def cpu_reference_step(n_images, sd, post, threads):
     return time.perf_counter() - t0
 
 
+def cpu_description():
+    """Host the CPU arm ran on: model string, os.cpu_count(), torch intra-op threads."""
+    import torch
+    model = None
+    try:
+        for line in open('/proc/cpuinfo'):
+            if line.lower().startswith('model name'):
+                model = line.split(':', 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {'cpu_model': model, 'os_cpu_count': os.cpu_count(), 'torch_threads': torch.get_num_threads()}
+
+
 def make_cpu_reference():
     from oracle.post_oracle import PostProcessOracle
     from orienmask_b200.synthetic import synthetic_state_dict
@@ -183,6 +197,7 @@ def run_reference(args, rank):
     v = sample * args.steps / t
     desc = {'value': v, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
             'sample': '%d images of 544x544 per step (forward via torch CPU/oneDNN fp32 + numpy/C post-process)' % sample}
+    desc.update(cpu_description())
     print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/sec', 'n_gpus': args.gpus,
                       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
                       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -500,6 +515,7 @@ def main():
             t = sum(cpu_reference_step(n_img, sd, cpost, threads) for _ in range(reps))
             line['cpu_baseline'] = {'value': n_img * reps / t, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
                                     'sample': '%d passes over %d images of 544x544 (oracle: torch CPU fp32 forward + numpy/C post-process)' % (reps, n_img)}
+            line['cpu_baseline'].update(cpu_description())
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

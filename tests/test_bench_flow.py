@@ -118,7 +118,9 @@ def test_gpu_arm_flow_and_json_contract(monkeypatch, capsys):
     monkeypatch.setattr(coco_format, 'encode_masks', lambda masks, counts, infos: [[{'size': [1, 1], 'counts': 'ab'}] * n for n in counts])
     from orienmask_b200 import synthetic
     monkeypatch.setattr(synthetic, 'synthetic_state_dict', lambda seed=0: {})
-    monkeypatch.setattr(sys, 'argv', ['bench.py', '--steps', '3', '--warmup', '1', '--batch', str(B), '--no-cpu-baseline'])
+    monkeypatch.setattr(bench, 'make_cpu_reference', lambda: ({}, None))                  # the CPU leg itself: test_host.py (reference arm)
+    monkeypatch.setattr(bench, 'cpu_reference_step', lambda n, sd, post, threads: 0.5 * n)
+    monkeypatch.setattr(sys, 'argv', ['bench.py', '--steps', '3', '--warmup', '1', '--batch', str(B)])
     for key in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
         monkeypatch.delenv(key, raising=False)
     bench.main()
@@ -138,5 +140,8 @@ def test_gpu_arm_flow_and_json_contract(monkeypatch, capsys):
     assert rf['bound'] == 'tensor' and rf['unit'] == 'TFLOP/s' and abs(rf['frac'] - rf['achieved'] / rf['peak']) < 1e-12
     assert rf['traffic_algorithmic'] == 15
     assert set(line['stages']) == {'preprocess', 'postprocess', 'coco_format'}
+    cb = line['cpu_baseline']
+    assert cb['kind'] == 'port' and cb['unit'] == 'images/sec' and abs(cb['value'] - 2.0) < 1e-9 and cb['cores'] >= 1 and 'sample' in cb
+    assert cb['os_cpu_count'] == cb['cores'] and cb['torch_threads'] >= 1 and 'cpu_model' in cb
     pp = line['stages']['postprocess']
     assert pp['bytes'] == B * (255 * (17 * 17 + 34 * 34 + 68 * 68) + 18 * 136 * 136) * 4 + 2 * 3 * bench.H * bench.W
