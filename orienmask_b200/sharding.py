@@ -39,11 +39,14 @@ def unpack_records(packed, K):
     return rec[..., :5].contiguous(), rec[..., 5].to(torch.int64), packed[:, K * 6].to(torch.int32)
 
 
-def gather_detections(det, cls, count, group=None, packed=None):
-    """All-gather the padded detection records of every rank (equal B_local per rank).
+def gather_detections(det, cls, count, group=None, packed=None, total=None):
+    """All-gather the padded detection records of every rank.
 
     ``packed``: the [B_local, K*6+1] record rows the NMS kernel wrote (``PaddedDetections.packed``); when given, that buffer
     is the collective's source and nothing is re-packed.
+    ``total``: global batch size when it does not divide evenly over the ranks (``shard_bounds`` gives the earlier ranks one
+    image more): every rank pads its rows to ``ceil(total / world)`` so that the collective stays fixed-size, and the pad
+    rows are dropped on arrival -- the shard sizes follow from ``total`` alone, so no size exchange is needed.
     Returns (det [B_total,K,5], cls [B_total,K], count [B_total]) in rank order, on every rank.
     """
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -52,6 +55,17 @@ def gather_detections(det, cls, count, group=None, packed=None):
     if packed is None:
         packed = pack_records(det, cls, count)
     world = dist.get_world_size(group)
-    out = torch.empty(world * packed.shape[0], packed.shape[1], dtype=packed.dtype, device=packed.device)
-    dist.all_gather_into_tensor(out, packed, group=group)
+    rows = packed.shape[0]
+    if total is not None:
+        sizes = [hi - lo for lo, hi in (shard_bounds(total, r, world) for r in range(world))]
+        if sizes[dist.get_rank(group)] != rows:
+            raise ValueError('rank %d holds %d images but shard_bounds(%d, ...) assigns it %d'
+                             % (dist.get_rank(group), rows, total, sizes[dist.get_rank(group)]))
+        rows = max(sizes)
+        if packed.shape[0] < rows:
+            packed = torch.cat([packed, packed.new_zeros(rows - packed.shape[0], packed.shape[1])], dim=0)
+    out = torch.empty(world * rows, packed.shape[1], dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+    if total is not None and min(sizes) != rows:
+        out = torch.cat([out[r * rows:r * rows + n] for r, n in enumerate(sizes)], dim=0)
     return unpack_records(out, K)

@@ -228,7 +228,18 @@ def _gather_worker(rank, world, port, q):
     cnt = torch.randint(0, 11, (4,), generator=g, dtype=torch.int32)
     lo, hi = shard_bounds(4, rank, world)
     d, c, n = gather_detections(det[lo:hi], cls[lo:hi], cnt[lo:hi])
-    q.put((rank, torch.equal(d, det) and torch.equal(c, cls) and torch.equal(n, cnt)))
+    ok = torch.equal(d, det) and torch.equal(c, cls) and torch.equal(n, cnt)
+    # ragged split: 5 images over 2 ranks (3 + 2); the collective stays fixed-size, the pad row is dropped on arrival
+    det5, cls5, cnt5 = torch.rand(5, 10, 5, generator=g), torch.randint(0, 80, (5, 10), generator=g), torch.arange(5, dtype=torch.int32)
+    lo, hi = shard_bounds(5, rank, world)
+    d, c, n = gather_detections(det5[lo:hi], cls5[lo:hi], cnt5[lo:hi], total=5)
+    ok = ok and torch.equal(d, det5) and torch.equal(c, cls5) and torch.equal(n, cnt5)
+    try:
+        gather_detections(det5[:1], cls5[:1], cnt5[:1], total=5)
+        ok = False
+    except ValueError:
+        pass
+    q.put((rank, ok))
     dist.destroy_process_group()
 
 
