@@ -1,0 +1,41 @@
+"""Differential run of the post-process oracle against the LIVE unmodified reference (build container only: needs
+/root/reference) on fresh seeded head tensors -- sizes, seeds and thresholds the committed fixtures do not contain.
+Run by tests/test_oracle.py::test_post_oracle_matches_live_reference_on_fresh_cases in a subprocess (importing the
+reference shadows the top-level package names ``eval`` / ``model`` / ``utils``).  Prints one JSON line."""
+import functools
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from oracle import build_ref
+from oracle.post_oracle import PostProcessOracle
+from tests.common import synthetic_heads, post_config, ANCHORS, ANCHOR_MASK
+config, ref_model, builder = build_ref.import_reference()
+import eval as ref_eval
+worst = 0.0
+n_cmp = 0
+for (H, W) in ((64, 96), (96, 64), (128, 128)):
+    for seed in (11, 12, 13):
+        for thr in (0.005, 0.05, 0.3):
+            heads = synthetic_heads(2, H, W, seed=seed)
+            cfg = post_config(H, W, thr)
+            post = ref_eval.OrienMaskYOLOPostProcess(nms_func=functools.partial(ref_eval.batched_nms, threshold=0.5), device=torch.device('cpu'), **cfg)
+            with torch.no_grad():
+                ref = post(heads)
+            orc = PostProcessOracle(cfg['grid_size'], cfg['image_size'], ANCHORS, ANCHOR_MASK, 80, conf_thresh=thr)
+            got = orc([(b.numpy(), o.numpy()) for b, o in heads])
+            for r, g in zip(ref, got):
+                rb, rc, rm = r['bbox'].numpy(), r['cls'].numpy(), r['mask'].numpy()
+                assert rb.shape == g['bbox'].shape, (H, W, seed, thr, rb.shape, g['bbox'].shape)
+                if rb.shape[0]:
+                    # reference order among equal scores is unspecified: align by (cls, box)
+                    key_r = np.lexsort((rb[:, 0], rb[:, 1], rc, -rb[:, 4]))
+                    key_g = np.lexsort((g['bbox'][:, 0], g['bbox'][:, 1], g['cls'], -g['bbox'][:, 4]))
+                    assert np.array_equal(rc[key_r], g['cls'][key_g]), (H, W, seed, thr)
+                    worst = max(worst, float(np.abs(rb[key_r] - g['bbox'][key_g]).max()))
+                    assert np.array_equal(rm[key_r], g['mask'][key_g]), (H, W, seed, thr, 'mask')
+                n_cmp += 1
+print(json.dumps({'cases': n_cmp, 'max_box_diff': worst}))

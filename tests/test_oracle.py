@@ -1,9 +1,11 @@
 """Pins the oracle (oracle/) against the reference's own outputs stored in tests/golden/.
 
 CPU only.  The fixtures were produced by the unmodified reference (tests/golden/make_golden.py);
-when /root/reference is present the live reference is also compared for the native NMS.
+when /root/reference is present the live reference is also compared: the native NMS, and the whole post-process on 54
+fresh (size, seed, threshold) cases (tests/live_reference_diff.py).
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -57,6 +59,21 @@ def test_nms_oracle_matches_live_reference_when_present():
         d = torch.cat([torch.rand(n, 2, generator=g), torch.rand(n, 2, generator=g) * 0.3 + 0.01,
                        torch.rand(n, 1, generator=g)], 1)
         assert np.array_equal(nms_oracle(d.numpy(), 0.5), nms.nms(d, 0.5).numpy())
+
+
+def test_post_oracle_matches_live_reference_on_fresh_cases():
+    """54 (size, seed, threshold) cases outside the committed fixtures: same classes, bit-equal masks, boxes within 1 ulp."""
+    import json
+    import subprocess
+    import sys
+    from oracle import build_ref
+    if not build_ref.reference_available():
+        pytest.skip('reference tree not present')
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, 'live_reference_diff.py')], capture_output=True, text=True, timeout=600, cwd='/tmp')
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res['cases'] == 54 and res['max_box_diff'] <= 1e-6
 
 
 def test_bilinear_matches_torch():
