@@ -38,4 +38,25 @@ for (H, W) in ((64, 96), (96, 64), (128, 128)):
                     worst = max(worst, float(np.abs(rb[key_r] - g['bbox'][key_g]).max()))
                     assert np.array_equal(rm[key_r], g['mask'][key_g]), (H, W, seed, thr, 'mask')
                 n_cmp += 1
-print(json.dumps({'cases': n_cmp, 'max_box_diff': worst}))
+
+# ---- forward oracle vs the reference nn.Modules on fresh weights / sizes (both model variants) ----------------------------
+from oracle.forward_oracle import forward_oracle  # noqa: E402
+from orienmask_b200.synthetic import synthetic_state_dict, synthetic_images  # noqa: E402
+fwd_rel = 0.0
+n_fwd = 0
+for plus, cls in ((True, ref_model.OrienMaskYOLOFPNPlus), (False, ref_model.OrienMaskYOLO)):
+    for wseed, (H, W) in ((3, (64, 96)), (4, (96, 128))):
+        sd = synthetic_state_dict(wseed, plus=plus)
+        net = cls(3, 80, pretrained=None)
+        net.load_state_dict(sd, strict=True)
+        net.eval()
+        x = synthetic_images(2, H, W, seed=20 + wseed)
+        with torch.no_grad():
+            ref = net(x)
+        got = forward_oracle(sd, x)
+        for (rb, ro), (gb, go) in zip(ref, got):
+            for r, g in ((rb, gb), (ro, go)):
+                assert r.shape == g.shape
+                fwd_rel = max(fwd_rel, float((r - g).norm() / r.norm()))
+        n_fwd += 1
+print(json.dumps({'cases': n_cmp, 'max_box_diff': worst, 'forward_cases': n_fwd, 'forward_rel_l2': fwd_rel}))

@@ -74,6 +74,7 @@ def test_post_oracle_matches_live_reference_on_fresh_cases():
     assert out.returncode == 0, out.stderr[-3000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res['cases'] == 54 and res['max_box_diff'] <= 1e-6
+    assert res['forward_cases'] == 4 and res['forward_rel_l2'] <= 1e-6          # both model variants, fresh weights and sizes
 
 
 def test_bilinear_matches_torch():
