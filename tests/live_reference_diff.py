@@ -17,27 +17,35 @@ config, ref_model, builder = build_ref.import_reference()
 import eval as ref_eval
 worst = 0.0
 n_cmp = 0
+def compare(H, W, seed, thr, num_classes=80):
+    global worst, n_cmp
+    heads = synthetic_heads(2, H, W, seed=seed, num_classes=num_classes)
+    cfg = dict(post_config(H, W, thr), num_classes=num_classes)
+    post = ref_eval.OrienMaskYOLOPostProcess(nms_func=functools.partial(ref_eval.batched_nms, threshold=0.5),
+                                             device=torch.device('cpu'), **cfg)
+    with torch.no_grad():
+        ref = post(heads)
+    orc = PostProcessOracle(cfg['grid_size'], cfg['image_size'], ANCHORS, ANCHOR_MASK, num_classes, conf_thresh=thr)
+    got = orc([(b.numpy(), o.numpy()) for b, o in heads])
+    for r, g in zip(ref, got):
+        rb, rc, rm = r['bbox'].numpy(), r['cls'].numpy(), r['mask'].numpy()
+        assert rb.shape == g['bbox'].shape, (H, W, seed, thr, rb.shape, g['bbox'].shape)
+        if rb.shape[0]:
+            # the reference's order among equal scores is unspecified: align by (score, class, box)
+            key_r = np.lexsort((rb[:, 0], rb[:, 1], rc, -rb[:, 4]))
+            key_g = np.lexsort((g['bbox'][:, 0], g['bbox'][:, 1], g['cls'], -g['bbox'][:, 4]))
+            assert np.array_equal(rc[key_r], g['cls'][key_g]), (H, W, seed, thr)
+            worst = max(worst, float(np.abs(rb[key_r] - g['bbox'][key_g]).max()))
+            assert np.array_equal(rm[key_r], g['mask'][key_g]), (H, W, seed, thr, 'mask')
+        n_cmp += 1
+
+
 for (H, W) in ((64, 96), (96, 64), (128, 128)):
     for seed in (11, 12, 13):
         for thr in (0.005, 0.05, 0.3):
-            heads = synthetic_heads(2, H, W, seed=seed)
-            cfg = post_config(H, W, thr)
-            post = ref_eval.OrienMaskYOLOPostProcess(nms_func=functools.partial(ref_eval.batched_nms, threshold=0.5), device=torch.device('cpu'), **cfg)
-            with torch.no_grad():
-                ref = post(heads)
-            orc = PostProcessOracle(cfg['grid_size'], cfg['image_size'], ANCHORS, ANCHOR_MASK, 80, conf_thresh=thr)
-            got = orc([(b.numpy(), o.numpy()) for b, o in heads])
-            for r, g in zip(ref, got):
-                rb, rc, rm = r['bbox'].numpy(), r['cls'].numpy(), r['mask'].numpy()
-                assert rb.shape == g['bbox'].shape, (H, W, seed, thr, rb.shape, g['bbox'].shape)
-                if rb.shape[0]:
-                    # reference order among equal scores is unspecified: align by (cls, box)
-                    key_r = np.lexsort((rb[:, 0], rb[:, 1], rc, -rb[:, 4]))
-                    key_g = np.lexsort((g['bbox'][:, 0], g['bbox'][:, 1], g['cls'], -g['bbox'][:, 4]))
-                    assert np.array_equal(rc[key_r], g['cls'][key_g]), (H, W, seed, thr)
-                    worst = max(worst, float(np.abs(rb[key_r] - g['bbox'][key_g]).max()))
-                    assert np.array_equal(rm[key_r], g['mask'][key_g]), (H, W, seed, thr, 'mask')
-                n_cmp += 1
+            compare(H, W, seed, thr)
+for thr in (0.005, 0.05, 0.3):                      # the VOC head layout: 20 classes, 75 channels per scale
+    compare(64, 64, 14, thr, num_classes=20)
 
 # ---- forward oracle vs the reference nn.Modules on fresh weights / sizes (both model variants) ----------------------------
 from oracle.forward_oracle import forward_oracle  # noqa: E402

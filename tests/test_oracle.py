@@ -1,7 +1,7 @@
 """Pins the oracle (oracle/) against the reference's own outputs stored in tests/golden/.
 
 CPU only.  The fixtures were produced by the unmodified reference (tests/golden/make_golden.py);
-when /root/reference is present the live reference is also compared: the native NMS, and the whole post-process on 54
+when /root/reference is present the live reference is also compared: the native NMS, and the whole post-process on 60
 fresh (size, seed, threshold) cases (tests/live_reference_diff.py).
 """
 import hashlib
@@ -62,7 +62,7 @@ def test_nms_oracle_matches_live_reference_when_present():
 
 
 def test_post_oracle_matches_live_reference_on_fresh_cases():
-    """54 (size, seed, threshold) cases outside the committed fixtures: same classes, bit-equal masks, boxes within 1 ulp."""
+    """60 (size, seed, threshold, class-count) cases outside the committed fixtures: same classes, bit-equal masks, boxes within 1 ulp."""
     import json
     import subprocess
     import sys
@@ -73,7 +73,7 @@ def test_post_oracle_matches_live_reference_on_fresh_cases():
     out = subprocess.run([sys.executable, os.path.join(here, 'live_reference_diff.py')], capture_output=True, text=True, timeout=600, cwd='/tmp')
     assert out.returncode == 0, out.stderr[-3000:]
     res = json.loads(out.stdout.strip().splitlines()[-1])
-    assert res['cases'] == 54 and res['max_box_diff'] <= 1e-6
+    assert res['cases'] == 60 and res['max_box_diff'] <= 1e-6
     assert res['forward_cases'] == 4 and res['forward_rel_l2'] <= 1e-6          # both model variants, fresh weights and sizes
 
 
