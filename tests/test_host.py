@@ -25,6 +25,27 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().om_abi_version() == 6
 
 
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/orienmask_b200.h compiles as strict C99 in a caller without CUDA or torch, every declared entry point
+    resolves at link time, and the struct layouts the C compiler sees are the ones the ctypes binding declares."""
+    import subprocess
+    from orienmask_b200 import _lib, build
+    build.build()
+    exe = str(tmp_path / 'abi_check')
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(['gcc', '-std=c99', '-Wall', '-Wextra', '-Werror', '-pedantic',
+                           '-I', os.path.join(ROOT, 'include'), os.path.join(ROOT, 'tests', 'c_abi', 'abi_check.c'),
+                           '-o', exe, '-L', libdir, '-lorienmask_b200', '-Wl,-rpath,' + libdir])
+    words = subprocess.check_output([exe]).decode().split()
+    got = {words[i]: int(words[i + 1]) for i in range(0, len(words), 2)}
+    assert got['abi'] == 6 and got['entries'] == len(_lib.SIGNATURES)
+    assert got['sizeof(om_post_config)'] == ctypes.sizeof(_lib.PostConfig)
+    assert got['sizeof(om_conv_desc)'] == ctypes.sizeof(_lib.ConvDesc)
+    assert got['sizeof(om_prep_config)'] == ctypes.sizeof(_lib.PrepConfig)
+    assert got['sizeof(om_rle_image)'] == ctypes.sizeof(_lib.RleImage)
+    assert got['sizeof(om_blend_config)'] == ctypes.sizeof(_lib.BlendConfig)
+
+
 def test_config_errors_are_reported_without_a_gpu():
     from orienmask_b200 import _lib
     lib = _lib.lib()
