@@ -1,6 +1,7 @@
 /* Compiled and run by tests/test_host.py::test_header_is_plain_c_and_links: the header must be valid C99 for a caller that
  * knows nothing about CUDA or torch, and the library must resolve every entry point at link time.  No kernel is launched:
  * only the argument-checking paths run (they return before any CUDA call). */
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -26,5 +27,10 @@ int main(void) {
            "sizeof(om_rle_image) %d sizeof(om_blend_config) %d\n", (int)om_abi_version(), (int)(sizeof entry / sizeof entry[0]),
            (int)sizeof(om_post_config), (int)sizeof(om_conv_desc), (int)sizeof(om_prep_config), (int)sizeof(om_rle_image),
            (int)sizeof(om_blend_config));
+    printf("offsetof(om_post_config.anchor_w) %d offsetof(om_post_config.nms_post) %d offsetof(om_conv_desc.input) %d "
+           "offsetof(om_conv_desc.out_s2d) %d offsetof(om_prep_config.pad_value) %d offsetof(om_rle_image.vflip) %d "
+           "offsetof(om_blend_config.alpha) %d\n", (int)offsetof(om_post_config, anchor_w), (int)offsetof(om_post_config, nms_post),
+           (int)offsetof(om_conv_desc, input), (int)offsetof(om_conv_desc, out_s2d), (int)offsetof(om_prep_config, pad_value),
+           (int)offsetof(om_rle_image, vflip), (int)offsetof(om_blend_config, alpha));
     return 0;
 }

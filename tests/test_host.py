@@ -44,6 +44,11 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert got['sizeof(om_prep_config)'] == ctypes.sizeof(_lib.PrepConfig)
     assert got['sizeof(om_rle_image)'] == ctypes.sizeof(_lib.RleImage)
     assert got['sizeof(om_blend_config)'] == ctypes.sizeof(_lib.BlendConfig)
+    for name, (struct, field) in {'om_post_config.anchor_w': (_lib.PostConfig, 'anchor_w'), 'om_post_config.nms_post': (_lib.PostConfig, 'nms_post'),
+                                  'om_conv_desc.input': (_lib.ConvDesc, 'input'), 'om_conv_desc.out_s2d': (_lib.ConvDesc, 'out_s2d'),
+                                  'om_prep_config.pad_value': (_lib.PrepConfig, 'pad_value'), 'om_rle_image.vflip': (_lib.RleImage, 'vflip'),
+                                  'om_blend_config.alpha': (_lib.BlendConfig, 'alpha')}.items():
+        assert got['offsetof(%s)' % name] == getattr(struct, field).offset, name
 
 
 def test_config_errors_are_reported_without_a_gpu():
