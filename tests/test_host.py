@@ -79,7 +79,9 @@ def test_conv_descriptor_errors_are_reported_without_a_gpu():
     cases = [(dict(ksize=5), -3, b'ksize'), (dict(stride=3), -3, b'stride'), (dict(precision=7), -1, b'precision'),
              (dict(in_rows=16), -1, b'in_rows'), (dict(out_h=8), -1, b'geometry'), (dict(input=0), -1, b'null tensor'),
              (dict(cout_stride=32), -1, b'cout_stride'), (dict(cin=48), -1, b'cin'), (dict(batch=0), -1, b'non-positive'),
-             (dict(residual=256, out_kind=_lib.OUT_NCHW), -1, b'residual'), (dict(in_s2d=1), -1, b'in_s2d')]
+             (dict(residual=256, out_kind=_lib.OUT_NCHW), -1, b'residual'), (dict(in_s2d=1), -1, b'in_s2d'),
+             # a 20-class head (75 channels -> 80 padded): N = 80 cannot be halved over a CTA pair; loud, not wrong
+             (dict(cout=75, ksize=1, out_kind=_lib.OUT_NCHW), -1, b'cannot be split over a CTA pair')]
     for kw, code, text in cases:
         handle = _lib.c_vp()
         rc = lib.om_conv_create(desc(**kw), handle)
