@@ -105,3 +105,12 @@ extern "C" void om_conv_destroy(om_conv* c) {
 // conv_tc2 launches fills with %globaltimer stamps (prologue / first load / first MMA / first epilogue / exit).
 namespace om { int32_t tc2_set_timeline(void* dev_ptr); }
 extern "C" int32_t om_debug_conv_timeline(void* dev_ptr) { return om::tc2_set_timeline(dev_ptr); }
+// Debug only: the planner's decisions for a layer of the CTA-pair engine -- info[16] = halo, flat, halo_s2, b_resident, tw, th,
+// block_n, tiles_n, stages, n_sub, h_stages, acc_stages, has_res (1 fp16 residual, 2 staged up-add), res_direct, smem bytes, grid.
+extern "C" int32_t om_debug_conv_plan_info(const om_conv* c, int32_t* info) {
+    if (!c || !info || c->desc.precision != OM_PREC_F16 || c->tc_version != 2 || !c->tc_plan)
+        return om::fail(OM_ERR_INVALID, "om_debug_conv_plan_info: not a plan of the CTA-pair engine");
+    om::tc2_plan_info(c->tc_plan, info);
+    return OM_OK;
+}
+

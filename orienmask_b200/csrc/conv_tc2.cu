@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "conv_plan.h"
@@ -761,6 +762,39 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     }
 }
 
+// ORIENMASK_B200_PLAN_DRYRUN=1 (tests/test_planner.py): om_conv_create plans a layer without a GPU -- 148 SMs assumed, tensor maps
+// left zeroed after checking the arguments against the documented limits of cuTensorMapEncode*, no kernel attribute set.  A plan
+// made this way is never launched (tc2_plan_run refuses).
+bool plan_dryrun() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("ORIENMASK_B200_PLAN_DRYRUN"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+int sm_count() {
+    if (plan_dryrun()) return 148;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+// The argument rules of cuTensorMapEncodeTiled / Im2col without interleave (CUDA driver API reference).
+int32_t check_map_args(const char* who, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                       int inner_elems, int esz, int inner_bytes) {
+    if (rank < 1 || rank > 5) return om::fail(OM_ERR_INVALID, "%s: rank %d", who, rank);
+    if (reinterpret_cast<uintptr_t>(base) & 15) return om::fail(OM_ERR_INVALID, "%s: base address not 16-byte aligned", who);
+    for (int i = 0; i < rank; ++i)
+        if (dims[i] < 1 || dims[i] > (1ull << 32)) return om::fail(OM_ERR_INVALID, "%s: dim %d = %llu", who, i, (unsigned long long)dims[i]);
+    for (int i = 0; i + 1 < rank; ++i)
+        if (strides_bytes[i] % 16 || strides_bytes[i] >= (1ull << 40))
+            return om::fail(OM_ERR_INVALID, "%s: stride %d = %llu bytes", who, i, (unsigned long long)strides_bytes[i]);
+    if (inner_bytes != 128 && inner_bytes != 64) return om::fail(OM_ERR_INVALID, "%s: swizzle span %d", who, inner_bytes);
+    if (inner_elems < 1 || inner_elems > 256 || inner_elems * esz > inner_bytes || (inner_elems * esz) % 16)
+        return om::fail(OM_ERR_INVALID, "%s: inner box of %d x %d bytes does not fit the %d-byte swizzle span", who, inner_elems, esz, inner_bytes);
+    return OM_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -778,6 +812,12 @@ EncodeTiledFn get_encode() {
 
 int32_t encode(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const cuuint64_t* dims,
                const cuuint64_t* strides_bytes, const cuuint32_t* box, int inner_bytes) {
+    if (plan_dryrun()) {
+        memset(map, 0, sizeof(*map));
+        for (int i = 0; i < rank; ++i)
+            if (box[i] < 1 || box[i] > 256) return om::fail(OM_ERR_INVALID, "tiled map: box dim %d = %u", i, box[i]);
+        return check_map_args("tiled map", base, rank, dims, strides_bytes, (int)box[0], dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 ? 4 : 2, inner_bytes);
+    }
     EncodeTiledFn fn = get_encode();
     if (!fn) return om::fail(OM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint32_t ones[5] = {1, 1, 1, 1, 1};
@@ -796,6 +836,13 @@ typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 // pixels per load; k x k filter with padding k/2 and traversal stride `stride` (bounding-box corners as cuDNN / CUTLASS fprop).
 int32_t encode_im2col(CUtensorMap* map, const void* base, int c, int c_stride, int w, int h, int rows, int batch, int channels, int ksize,
                       int stride, int inner_bytes) {
+    if (plan_dryrun()) {
+        memset(map, 0, sizeof(*map));
+        cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)batch};
+        cuuint64_t str[3] = {(cuuint64_t)c_stride * 2, (cuuint64_t)w * c_stride * 2, (cuuint64_t)rows * w * c_stride * 2};
+        if (kBlockM > 1024 || stride < 1 || stride > 8) return om::fail(OM_ERR_INVALID, "im2col map: pixels per column / traversal stride");
+        return check_map_args("im2col map", base, 4, dims, str, channels, 2, inner_bytes);
+    }
     static EncodeIm2colFn fn = nullptr;
     if (!fn) {
         void* ptr = nullptr;
@@ -854,7 +901,7 @@ namespace om {
 
 int32_t tc2_set_wait_hint(unsigned int ns);
 
-int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
+static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, bool* halo_used) {
     if (d.cin % 32) return fail(OM_ERR_INVALID, "fp16 engine needs cin %% 32 == 0 (got %d)", d.cin);
     if (d.out_kind != OM_OUT_NCHW && (d.cout % 32 || d.cout_stride % 16 || d.cout_stride < d.cout))
         return fail(OM_ERR_INVALID, "fp16 engine needs cout %% 32 == 0 and an aligned channel pitch for NHWC outputs");
@@ -888,7 +935,8 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     p.block_n = bn; p.half_n = bn / 2; p.cout_pad = cout_pad; p.tiles_n = cout_pad / bn;
     const char* halo_env = getenv("ORIENMASK_B200_HALO");
     p.halo = d.ksize == 3 && d.stride == 1 && d.out_kind != OM_OUT_NCHW && (d.out_w % 8 == 0 || d.out_w >= 64) &&
-             !(halo_env && halo_env[0] == '0');
+             !(halo_env && halo_env[0] == '0') && allow_halo;
+    *halo_used = p.halo != 0;
     // Flat tiles: every layer that is not served by a halo box, a parity-split input or a TMA-staged up-add computes tiles of 128
     // consecutive real pixels (image, y, x) gathered by im2col-mode TMA: no pad rows and no partially filled tiles, which at
     // 17x17 / 34x34 is the difference between 3 and 2 (5 and 4) waves of CTA pairs.
@@ -898,11 +946,10 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     if (p.flat && !(flat_env && flat_env[0] == '2')) {
         // ... but im2col-mode loads cost ~6.5 cycles per pixel, which the memory-bound layers with many waves of tiles cannot
         // afford: keep rectangular boxes when quantisation is not the problem (more than ~10 waves of pairs)
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int sms = sm_count();
         const long long flat_pairs = ((p.flat_total + kBlockM - 1) / kBlockM + 1) / 2;
-        if (flat_pairs * (cout_pad / bn) > 10ll * (sms / 2)) p.flat = 0;
+        // (a stride-2 layer whose input and output row pitches are not 2:1 has no rectangular alternative: it stays flat)
+        if (flat_pairs * (cout_pad / bn) > 10ll * (sms / 2) && !(d.stride == 2 && d.in_rows != 2 * d.out_rows)) p.flat = 0;
     }
     if (d.stride == 2 && !p.flat && d.in_rows != 2 * d.out_rows) {      // rectangular / parity-plane boxes address rows of the whole batch
         delete plan;
@@ -1064,13 +1111,17 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     if (rc != OM_OK) { delete plan; return rc; }
 
     plan->smem = (size_t)fixed + (size_t)p.h_stages * p.h_stage_bytes + (size_t)p.stages * p.n_sub * sub_bytes;
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = sm_count();
     const int pairs = p.tiles_x * p.pairs_y * p.tiles_n;
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
     plan->grid = 2 * clusters;
-    cudaError_t e = bk == 64
+    if (plan->smem > (size_t)kMaxSmem || p.tmem_cols > 512 || plan->grid < 2) {       // cannot happen by construction; the dry-run sweep proves it
+        const size_t need = plan->smem;
+        const int cols = p.tmem_cols;
+        delete plan;
+        return fail(OM_ERR_INVALID, "plan out of budget: %zu bytes of shared memory, %d TMEM columns", need, cols);
+    }
+    cudaError_t e = plan_dryrun() ? cudaSuccess : bk == 64
         ? cudaFuncSetAttribute(conv_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
         : cudaFuncSetAttribute(conv_tc2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) { delete plan; return fail(OM_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); }
@@ -1078,10 +1129,22 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
     return OM_OK;
 }
 
+int32_t tc2_plan_create(const om_conv_desc& d, void** out) {
+    bool halo_used = false;
+    int32_t rc = plan_create(d, out, true, &halo_used);
+    // The halo box of a wide-K 3x3 layer (cin >= 256: 94 KB per stage) does not fit next to a staged residual; such a layer is
+    // planned without the halo (flat or per-tap tiles, the modes the 17x17 / 34x34 layers use).  Found by tests/test_planner.py:
+    // widths whose stride-16 map is a multiple of 8 wide (640, 1024, 1280, ...) could not be planned at all.
+    if (rc == OM_ERR_INVALID && halo_used && strstr(om::error_buffer(), "does not fit shared memory") != nullptr)
+        rc = plan_create(d, out, false, &halo_used);
+    return rc;
+}
+
 // `output` != nullptr redirects the result (the epilogue stores through a plain pointer, no tensor map): the model's head layers
 // write into tensors allocated per call, so results handed to the caller are never overwritten by the next forward.
 int32_t tc2_plan_run(const void* vp, cudaStream_t stream, void* output) {
     const Tc2Plan* plan = reinterpret_cast<const Tc2Plan*>(vp);
+    if (plan_dryrun()) return fail(OM_ERR_UNSUPPORTED, "plans made under ORIENMASK_B200_PLAN_DRYRUN cannot be launched");
     Tc2Params p = plan->p;
     if (output != nullptr) {
         if (p.has_res || p.res_direct) return fail(OM_ERR_INVALID, "om_conv_run_to: layers with a residual write in place");
@@ -1095,6 +1158,14 @@ int32_t tc2_plan_run(const void* vp, cudaStream_t stream, void* output) {
 }
 
 void tc2_plan_destroy(void* vp) { delete reinterpret_cast<Tc2Plan*>(vp); }
+
+void tc2_plan_info(const void* vp, int32_t* info) {
+    const Tc2Plan* plan = reinterpret_cast<const Tc2Plan*>(vp);
+    const Tc2Params& p = plan->p;
+    const int32_t v[16] = {p.halo, p.flat, p.halo_s2, p.b_resident, p.tw, p.th, p.block_n, p.tiles_n, p.stages, p.n_sub, p.h_stages,
+                           p.acc_stages, p.has_res, p.res_direct, (int32_t)plan->smem, plan->grid};
+    memcpy(info, v, sizeof(v));
+}
 
 int32_t tc2_set_wait_hint(unsigned int ns) {
     OM_CUDA_TRY(cudaMemcpyToSymbol(g_wait_hint_ns, &ns, sizeof(ns)));
