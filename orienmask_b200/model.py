@@ -105,6 +105,13 @@ class OrienMaskYOLOFPNPlus(nn.Module):
         self._engines = {}
         self._weights_version += 1
 
+    def __getstate__(self):
+        # copy.deepcopy / pickle (torch.save of the whole module) take the parameters, never the buffer plans: those hold
+        # native plan handles and gigabytes of activation buffers, and are rebuilt on the first forward of the copy
+        state = self.__dict__.copy()
+        state['_engines'] = {}
+        return state
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError('orienmask_b200 runs on CUDA (sm_100a) only; got a %s tensor and there is no CPU fallback' % x.device)

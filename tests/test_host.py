@@ -163,6 +163,19 @@ def test_pretrained_backbone_checkpoint_is_loaded_like_the_reference(tmp_path, c
     assert 'Ignore keys' in out and 'fc.weight' in out and 'conv2.0.conv_block.0.weight' in out
 
 
+def test_model_copies_and_pickles_without_its_buffer_plans():
+    import copy
+    import pickle
+    import orienmask_b200 as ob
+    m = ob.OrienMaskYOLOFPNPlus(3, 80)
+    m._engines[(1, 64, 64, 'fp16', 0)] = ctypes.c_void_p(1234)          # a native handle: neither copyable state nor picklable
+    twin = copy.deepcopy(m)
+    assert twin._engines == {} and len(m._engines) == 1
+    assert torch.equal(twin.state_dict()['backbone.conv1.conv_block.0.weight'], m.state_dict()['backbone.conv1.conv_block.0.weight'])
+    back = pickle.loads(pickle.dumps(m))
+    assert back._engines == {} and len(back.state_dict()) == 524 and back.num_classes == 80
+
+
 def test_engine_plans_are_bounded_lru(monkeypatch):
     """A stream of differently shaped batches keeps at most max_engines buffer plans, dropping the least recently used."""
     import orienmask_b200 as ob
