@@ -1,6 +1,6 @@
 #!/bin/bash
 # Standard GPU visit: parity tests (one process per file), bench, ncu launch list + one full capture.
-# Logs -> gpurun_out/.  Usage: bash tools/gpu_round.sh [tests] [probe] [bench] [ncu] [full]
+# Logs -> gpurun_out/.  Usage: bash tools/gpu_round.sh [tests] [queued] [probe] [bench] [events] [ncu] [traffic] [full] [abtest] [fullx]
 mkdir -p gpurun_out
 what="${*:-tests bench ncu}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
@@ -9,6 +9,11 @@ if [[ $what == *tests* ]]; then
     timeout 900 python -m pytest $( [[ $f == prep || $f == coco_format ]] && echo tests/test_$f.py || echo tests/test_gpu_$f.py ) -q -m gpu -x --timeout 600 > gpurun_out/test_$f.log 2>&1
     echo "test_gpu_$f exit $?"; tail -4 gpurun_out/test_$f.log
   done
+fi
+if [[ $what == *queued* ]]; then
+  # tests written without a GPU (tests/test_gpu_queued.py): opt-in, one process so that a fault cannot poison the regular files
+  ORIENMASK_B200_QUEUED=1 timeout 900 python -m pytest tests/test_gpu_queued.py -q -m gpu --timeout 600 > gpurun_out/test_queued.log 2>&1
+  echo "test_gpu_queued exit $?"; tail -15 gpurun_out/test_queued.log
 fi
 if [[ $what == *probe* ]]; then
   timeout 900 python tools/tc_probe.py > gpurun_out/tc_probe.log 2>&1; cat gpurun_out/tc_probe.log
