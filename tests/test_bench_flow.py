@@ -4,6 +4,7 @@ are meaningless here; the real run happens on the B200 box."""
 import contextlib
 import io
 import json
+import os
 import sys
 import types
 
@@ -44,11 +45,20 @@ class _Graph:
         pass
 
 
-def test_gpu_arm_flow_and_json_contract(monkeypatch, capsys):
+B, K = 2, 100
+
+
+class _Patcher:
+    """monkeypatch.setattr for a spawned worker (no pytest fixtures there)."""
+
+    def setattr(self, obj, name, value):
+        setattr(obj, name, value)
+
+
+def install_stand_ins(monkeypatch):
     import bench
     import orienmask_b200 as ob
     from orienmask_b200 import coco_format
-    B, K = 2, 100
     cur = _Stream()
     for name, value in dict(is_available=lambda: True, set_device=lambda d: None, synchronize=lambda *a: None, Event=_Event,
                             Stream=_Stream, current_stream=lambda *a: cur, stream=lambda s: contextlib.nullcontext(),
@@ -100,6 +110,7 @@ def test_gpu_arm_flow_and_json_contract(monkeypatch, capsys):
         def apply_padded(self, heads):
             out = types.SimpleNamespace(det=torch.zeros(B, K, 5), cls=torch.zeros(B, K, dtype=torch.int64),
                                         count=torch.full((B,), 3, dtype=torch.int32), packed=torch.zeros(B, K * 6 + 1))
+            out.packed[:, -1] = 3.0
             out.to_list = lambda: [{'bbox': torch.zeros(3, 5), 'mask': torch.zeros(3, bench.H, bench.W, dtype=torch.bool),
                                     'cls': torch.zeros(3, dtype=torch.int64)} for _ in range(B)]
             return out
@@ -118,6 +129,11 @@ def test_gpu_arm_flow_and_json_contract(monkeypatch, capsys):
     monkeypatch.setattr(coco_format, 'encode_masks', lambda masks, counts, infos: [[{'size': [1, 1], 'counts': 'ab'}] * n for n in counts])
     from orienmask_b200 import synthetic
     monkeypatch.setattr(synthetic, 'synthetic_state_dict', lambda seed=0: {})
+    return bench
+
+
+def test_gpu_arm_flow_and_json_contract(monkeypatch, capsys):
+    bench = install_stand_ins(monkeypatch)
     monkeypatch.setattr(bench, 'make_cpu_reference', lambda: ({}, None))                  # the CPU leg itself: test_host.py (reference arm)
     monkeypatch.setattr(bench, 'cpu_reference_step', lambda n, sd, post, threads: 0.5 * n)
     monkeypatch.setattr(sys, 'argv', ['bench.py', '--steps', '3', '--warmup', '1', '--batch', str(B)])
@@ -145,3 +161,41 @@ def test_gpu_arm_flow_and_json_contract(monkeypatch, capsys):
     assert cb['os_cpu_count'] == cb['cores'] and cb['torch_threads'] >= 1 and 'cpu_model' in cb
     pp = line['stages']['postprocess']
     assert pp['bytes'] == B * (255 * (17 * 17 + 34 * 34 + 68 * 68) + 18 * 136 * 136) * 4 + 2 * 3 * bench.H * bench.W
+
+
+def _rank_worker(rank, world, port, q):
+    """One rank of `torchrun bench.py --gpus 2` on stand-ins: gloo instead of NCCL, CPU tensors instead of device tensors."""
+    import io
+    import torch.distributed as dist
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    bench = install_stand_ins(_Patcher())
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, device_id=None: real_init('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    sys.argv = ['bench.py', '--gpus', str(world), '--steps', '3', '--warmup', '3', '--batch', str(B)]
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        bench.main()
+    q.put((rank, buf.getvalue()))
+
+
+def test_two_rank_flow_on_gloo():
+    """The N > 1 path of bench.py (barriers, max-over-ranks reductions, the detection all-gather, rank 0 alone printing)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_rank_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert results[1].strip() == ''                                   # only rank 0 prints
+    lines = [l for l in results[0].splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line['n_gpus'] == 2 and line['config']['global_batch'] == 2 * B and line['config']['parallelism'] == 'dp2'
+    assert line['scaling'] == 'weak' and 'cpu_baseline' not in line    # the CPU baseline is an N = 1 leg
+    assert line['e2e']['h2d_bytes_per_step'] == 2 * B * 544 * 544 * 3 and line['e2e']['d2h_bytes_per_step'] == 2 * B * K * 5 * 4 + 2 * B * 4
+    assert line['e2e']['value'] > 0 and line['value'] > 0
