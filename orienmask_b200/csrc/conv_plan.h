@@ -17,7 +17,7 @@ int32_t tc2_plan_create(const om_conv_desc& d, void** out);
 int32_t tc2_plan_run(const void* plan, cudaStream_t stream, void* output = nullptr);
 void tc2_plan_destroy(void* plan);
 // debug / tests: the planner's decisions for one layer (see om_debug_conv_plan_info in api.cu for the field order)
-void tc2_plan_info(const void* plan, int32_t* info16);
+void tc2_plan_info(const void* plan, int32_t* info24);
 
 // tensor-core first layer (conv_stem_tc.cu)
 int32_t stem_tc_run(const float* image, const float* weights, const float* bias, void* output, int batch, int h, int w, int rows,

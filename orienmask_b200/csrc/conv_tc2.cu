@@ -1162,8 +1162,9 @@ void tc2_plan_destroy(void* vp) { delete reinterpret_cast<Tc2Plan*>(vp); }
 void tc2_plan_info(const void* vp, int32_t* info) {
     const Tc2Plan* plan = reinterpret_cast<const Tc2Plan*>(vp);
     const Tc2Params& p = plan->p;
-    const int32_t v[16] = {p.halo, p.flat, p.halo_s2, p.b_resident, p.tw, p.th, p.block_n, p.tiles_n, p.stages, p.n_sub, p.h_stages,
-                           p.acc_stages, p.has_res, p.res_direct, (int32_t)plan->smem, plan->grid};
+    const int32_t v[24] = {p.halo, p.flat, p.halo_s2, p.b_resident, p.tw, p.th, p.block_n, p.tiles_n, p.stages, p.n_sub, p.h_stages,
+                           p.acc_stages, p.has_res, p.res_direct, (int32_t)plan->smem, plan->grid,
+                           p.tiles_x * p.pairs_y * p.tiles_n, p.taps, p.k_chunks, plan->bk, p.tmem_cols, p.cout, p.out_h, p.out_w};
     memcpy(info, v, sizeof(v));
 }
 

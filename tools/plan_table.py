@@ -18,7 +18,7 @@ import orienmask_b200 as ob  # noqa: E402
 from orienmask_b200 import _lib, model as mod  # noqa: E402
 
 FIELDS = ('halo', 'flat', 'halo_s2', 'b_resident', 'tw', 'th', 'block_n', 'tiles_n', 'stages', 'n_sub', 'h_stages', 'acc_stages',
-          'has_res', 'res_direct', 'smem', 'grid')
+          'has_res', 'res_direct', 'smem', 'grid', 'pairs', 'taps', 'k_chunks', 'bk', 'tmem_cols', 'cout', 'out_h', 'out_w')
 
 
 class Buf:
@@ -79,9 +79,14 @@ def plan(plus, batch, height, width):
     for (kind, arg), layer in zip(eng.plans, eng.layers):
         if kind != 'conv':
             continue
-        info = (ctypes.c_int32 * 16)()
+        info = (ctypes.c_int32 * 24)()
         _lib.check(lib.om_debug_conv_plan_info(arg, info), 'om_debug_conv_plan_info')
-        rows.append(dict(zip(FIELDS, info), name=layer['name'], shape=layer['shape']))
+        r = dict(zip(FIELDS, info), name=layer['name'], shape=layer['shape'], flops=layer['flops'])
+        # tile efficiency: useful output elements over the elements the issued tiles cover, whole waves of 74 CTA pairs counted
+        clusters = r['grid'] // 2
+        r['waves'] = -(-r['pairs'] // clusters)
+        r['tile_eff'] = batch * r['out_h'] * r['out_w'] * r['cout'] / float(r['waves'] * clusters * 256 * r['block_n'])
+        rows.append(r)
     return eng, rows
 
 
@@ -97,13 +102,16 @@ def main():
     install_stand_ins()
     _, rows = plan(True, args.batch, args.size, args.size)
     print('Plan of the fp16 engine, bs %d, %dx%d (planner dry run, 148 SMs; tools/plan_table.py)\n' % (args.batch, args.size, args.size))
-    print('| # | layer | shape | mode | tile | N tile x count | stages x blocks | halo stages | weights resident | acc | addend | smem KB | CTAs |')
-    print('|---|---|---|---|---|---|---|---|---|---|---|---|---|')
+    print('| # | layer | shape | mode | tile | N tile x count | stages x blocks | halo stages | weights resident | acc | addend | smem KB | CTAs | pair tiles | waves | tile eff |')
+    print('|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|')
     for i, r in enumerate(rows, 1):
         addend = {0: 'direct' if r['res_direct'] else '-', 1: 'TMA fp16', 2: 'TMA up-add'}[r['has_res']]
-        print('| %d | %s | %s | %s | %dx%d | %d x %d | %d x %d | %d | %s | %d | %s | %.1f | %d |' % (
+        print('| %d | %s | %s | %s | %dx%d | %d x %d | %d x %d | %d | %s | %d | %s | %.1f | %d | %d | %d | %.3f |' % (
             i, r['name'], r['shape'], mode(r), r['tw'], r['th'], r['block_n'], r['tiles_n'], r['stages'], r['n_sub'], r['h_stages'],
-            'yes' if r['b_resident'] else '-', r['acc_stages'], addend, r['smem'] / 1024.0, r['grid']))
+            'yes' if r['b_resident'] else '-', r['acc_stages'], addend, r['smem'] / 1024.0, r['grid'], r['pairs'], r['waves'], r['tile_eff']))
+    total = sum(r['flops'] for r in rows)
+    print('\nFLOP-weighted tile efficiency of the forward (useful / issued tensor work, pad rows + partial tiles + padded head channels + '
+          'wave quantisation): %.3f' % (total / sum(r['flops'] / r['tile_eff'] for r in rows)))
 
 
 if __name__ == '__main__':
