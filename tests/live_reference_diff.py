@@ -67,4 +67,48 @@ for plus, cls in ((True, ref_model.OrienMaskYOLOFPNPlus), (False, ref_model.Orie
                 assert r.shape == g.shape
                 fwd_rel = max(fwd_rel, float((r - g).norm() / r.norm()))
         n_fwd += 1
-print(json.dumps({'cases': n_cmp, 'max_box_diff': worst, 'forward_cases': n_fwd, 'forward_rel_l2': fwd_rel}))
+
+# ---- the neighbours of the path on fresh cases -------------------------------------------------------------
+import data.transform as T  # noqa: E402  (the reference's own data package)
+from eval.coco_eval import COCOMetrics as RefMetrics  # noqa: E402
+from oracle import prep_oracle, coco_oracle  # noqa: E402
+from tests.common import blob_masks  # noqa: E402
+rng = np.random.default_rng(17)
+prep_worst, n_prep = 0.0, 0
+for (h, w), size in (((37, 50), (64, 96)), ((480, 640), (544, 544)), ((211, 150), (96, 64)), ((64, 64), (64, 64))):
+    img = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+    tr = T.FastCOCOTransform([T.FastCOCOTransform.Resize(size=size), T.FastCOCOTransform.Normalize(mean=(0, 0, 0), std=(255, 255, 255))],
+                             use_cuda=False)
+    ref = tr(torch.tensor(img, dtype=torch.float32)).numpy()
+    got = prep_oracle.fast_transform_oracle(img, size)
+    assert got.shape == ref.shape
+    prep_worst = max(prep_worst, float(np.abs(got - ref).max()))       # in units of 1 (inputs 0..255 scaled to 0..1)
+    n_prep += 1
+img = rng.integers(0, 256, (1, 90, 61, 3), dtype=np.uint8)
+tr = T.FastCOCOTransform([T.FastCOCOTransform.ShortEdgeResize(short_length=64, max_size=100),
+                          T.FastCOCOTransform.Normalize(mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375))], use_cuda=False)
+ref = tr(torch.tensor(img, dtype=torch.float32)).numpy()
+got = prep_oracle.fast_transform_oracle(img, prep_oracle.short_edge_size(90, 61, 64, 100), mean=(123.675, 116.28, 103.53), std=(58.395, 57.12, 57.375))
+assert got.shape == ref.shape
+short_worst = float(np.abs(got - ref).max())                            # in units of one standard deviation (~58 grey levels)
+
+segm_min_iou, box_worst, n_coco = 1.0, 0.0, 0
+infos = [(96, 128, {'id': 1, 'height': 333, 'width': 500}),
+         (96, 128, {'id': 2, 'height': 60, 'width': 77, 'collate_pad': [3, 5, 0, 8, 96, 128]}),
+         (64, 64, {'id': 3, 'height': 100, 'width': 40, 'collate_pad': [0, 0, 0, 0, 64, 64], 'pad': (2, 2, 20, 20, 64, 64), 'vflip': True}),
+         (128, 96, {'id': 4, 'height': 128, 'width': 96, 'hflip': True})]
+for H, W, info in infos:
+    masks = blob_masks(5, H, W, seed=H + info['id'])
+    boxes = torch.rand(5, 4, generator=torch.Generator().manual_seed(info['id'])) * 0.5 + 0.2
+    ref_m = RefMetrics._recover_shape_segm(torch.from_numpy(masks), info).numpy().astype(bool)
+    got_m = np.asarray(coco_oracle.recover_shape_segm(masks, info)).astype(bool)
+    assert ref_m.shape == got_m.shape
+    for a, b in zip(ref_m, got_m):
+        union = (a | b).sum()
+        segm_min_iou = min(segm_min_iou, 1.0 if union == 0 else float((a & b).sum()) / float(union))
+    ref_b = RefMetrics._recover_shape_bbox(boxes, info).numpy()
+    box_worst = max(box_worst, float(np.abs(np.asarray(coco_oracle.recover_shape_bbox(boxes.numpy(), info)) - ref_b).max()))
+    n_coco += 1
+print(json.dumps({'cases': n_cmp, 'max_box_diff': worst, 'forward_cases': n_fwd, 'forward_rel_l2': fwd_rel,
+                  'prep_cases': n_prep, 'prep_max_diff': prep_worst, 'prep_short_edge_diff': short_worst,
+                  'coco_cases': n_coco, 'coco_min_mask_iou': segm_min_iou, 'coco_max_box_diff_px': box_worst}))

@@ -75,6 +75,9 @@ def test_post_oracle_matches_live_reference_on_fresh_cases():
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert res['cases'] == 60 and res['max_box_diff'] <= 1e-6
     assert res['forward_cases'] == 4 and res['forward_rel_l2'] <= 1e-6          # both model variants, fresh weights and sizes
+    # the neighbours of the path: FastCOCOTransform (Resize and ShortEdgeResize pipelines), _recover_shape_segm / _recover_shape_bbox
+    assert res['prep_cases'] == 4 and res['prep_max_diff'] <= 2e-5 and res['prep_short_edge_diff'] <= 1e-4
+    assert res['coco_cases'] == 4 and res['coco_min_mask_iou'] >= 0.999 and res['coco_max_box_diff_px'] <= 1e-3
 
 
 def test_bilinear_matches_torch():
