@@ -109,6 +109,27 @@ for H, W, info in infos:
     ref_b = RefMetrics._recover_shape_bbox(boxes, info).numpy()
     box_worst = max(box_worst, float(np.abs(np.asarray(coco_oracle.recover_shape_bbox(boxes.numpy(), info)) - ref_b).max()))
     n_coco += 1
+
+# ---- visualiser blend on fresh cases ------------------------------------------------------------------------
+from utils.visualizer import InferenceVisualizer as RefVis, PALETTE  # noqa: E402
+from oracle.visualizer_oracle import blend_oracle  # noqa: E402
+blend_worst, n_blend = 0.0, 0
+for (H, W), (height, width), pad_info, alpha in (((96, 128), (333, 500), [0, 0, 0, 0, 96, 128], 0.5),
+                                                 ((64, 96), (40, 61), [3, 5, 2, 8, 64, 96], 0.35)):
+    masks = blob_masks(6, H, W, seed=H + width)[:4]
+    image = torch.rand(height, width, 3, generator=torch.Generator().manual_seed(width)) * 255
+    colors = torch.tensor(PALETTE, dtype=torch.float32)[(torch.arange(4) * 5 + 7) % len(PALETTE)]
+    vis = RefVis.__new__(RefVis)
+    vis.alpha = alpha
+    soft = RefVis._recover_shape_segm(torch.from_numpy(masks), width, height, pad_info)
+    order = soft.sum(dim=2).sum(dim=1).argsort()
+    out = image.clone()
+    vis.plot_all_mask(soft[order], out, colors[order])
+    got, got_order, _ = blend_oracle(image.numpy(), masks, colors.numpy(), pad_info, alpha)
+    assert np.array_equal(np.asarray(got_order), order.numpy())
+    blend_worst = max(blend_worst, float(np.abs(np.asarray(got) - out.numpy()).max()))      # grey levels (0..255)
+    n_blend += 1
 print(json.dumps({'cases': n_cmp, 'max_box_diff': worst, 'forward_cases': n_fwd, 'forward_rel_l2': fwd_rel,
+                  'blend_cases': n_blend, 'blend_max_diff': blend_worst,
                   'prep_cases': n_prep, 'prep_max_diff': prep_worst, 'prep_short_edge_diff': short_worst,
                   'coco_cases': n_coco, 'coco_min_mask_iou': segm_min_iou, 'coco_max_box_diff_px': box_worst}))

@@ -78,6 +78,7 @@ def test_post_oracle_matches_live_reference_on_fresh_cases():
     # the neighbours of the path: FastCOCOTransform (Resize and ShortEdgeResize pipelines), _recover_shape_segm / _recover_shape_bbox
     assert res['prep_cases'] == 4 and res['prep_max_diff'] <= 2e-5 and res['prep_short_edge_diff'] <= 1e-4
     assert res['coco_cases'] == 4 and res['coco_min_mask_iou'] >= 0.999 and res['coco_max_box_diff_px'] <= 1e-3
+    assert res['blend_cases'] == 2 and res['blend_max_diff'] <= 1e-3                # visualiser blend, grey levels of 255
 
 
 def test_bilinear_matches_torch():
