@@ -51,6 +51,31 @@ def test_header_is_plain_c_and_links(tmp_path):
         assert got['offsetof(%s)' % name] == getattr(struct, field).offset, name
 
 
+def test_built_library_contains_blackwell_tensor_and_tma_code():
+    """SASS of the in-tree .so (cuobjdump, no GPU needed): the conv engine is tcgen05 (UTCHMMA.2CTA) fed by TMA (UTMALDG) with
+    accumulators read from TMEM (LDTM); no kernel uses the legacy mma.sync path (HMMA) -- B200_PROFILING.md's mnemonics."""
+    import shutil
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not on PATH')
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    try:
+        import sass_report
+    finally:
+        sys.path.pop(0)
+    from orienmask_b200 import build
+    build.build()
+    counts = dict(sass_report.sass_counts())
+    assert len(counts) >= 20
+    for name in ('conv_tc2_kernel<32>', 'conv_tc2_kernel<64>'):
+        c = counts[name]
+        assert c['UTCHMMA'] > 100 and c['UTMALDG'] >= 5 and c['LDTM'] >= 4 and c['UTCBAR'] >= 2 and c['ACQBULK'] >= 1, (name, dict(c))
+    assert counts['stem_tc_kernel']['UTCHMMA'] >= 2 and counts['stem_tc_kernel']['LDTM'] >= 1
+    assert all(c['HMMA'] == 0 and c['HGMMA'] == 0 for c in counts.values())
+    for name in ('mask_kernel', 'conf_compact_kernel', 'select_edge_kernel', 'select_tail_kernel', 'nms_kernel<true>', 'prep_kernel<unsigned char>',
+                 'mask_rle_kernel', 'mask_blend_kernel'):
+        assert name in counts, name
+
+
 def test_config_errors_are_reported_without_a_gpu():
     from orienmask_b200 import _lib
     lib = _lib.lib()
