@@ -156,8 +156,22 @@ def cpu_reference_step(n_images, sd, post, threads):
     x = synthetic_images(n_images, H, W, seed=1)
     t0 = time.perf_counter()
     heads = forward_oracle(sd, x)
+    t1 = time.perf_counter()
     post([(b.numpy(), o.numpy()) for b, o in heads])
-    return time.perf_counter() - t0
+    t2 = time.perf_counter()
+    CPU_SPLIT[0] += t1 - t0                 # forward / post-process seconds of the CPU arm, reported next to its throughput
+    CPU_SPLIT[1] += t2 - t1
+    return t2 - t0
+
+
+CPU_SPLIT = [0.0, 0.0]
+
+
+def cpu_split(images):
+    """Per-image forward / post-process milliseconds accumulated by cpu_reference_step since the last call."""
+    fwd, post = CPU_SPLIT
+    CPU_SPLIT[0] = CPU_SPLIT[1] = 0.0
+    return {'forward_ms_per_image': 1e3 * fwd / images, 'postprocess_ms_per_image': 1e3 * post / images}
 
 
 def cpu_description():
@@ -193,11 +207,14 @@ def run_reference(args, rank):
     sample = 2
     for _ in range(args.warmup):
         cpu_reference_step(sample, sd, post, threads)
+    cpu_split(1)
     t = sum(cpu_reference_step(sample, sd, post, threads) for _ in range(args.steps))
     v = sample * args.steps / t
+    split = cpu_split(sample * args.steps)
     desc = {'value': v, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
             'sample': '%d images of 544x544 per step (forward via torch CPU/oneDNN fp32 + numpy/C post-process)' % sample}
     desc.update(cpu_description())
+    desc.update(split)
     print(json.dumps({'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/sec', 'n_gpus': args.gpus,
                       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t / args.steps,
                       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -512,10 +529,12 @@ def main():
             sd, cpost = make_cpu_reference()
             cpu_reference_step(1, sd, cpost, threads)
             n_img, reps = 4, 3
+            cpu_split(1)
             t = sum(cpu_reference_step(n_img, sd, cpost, threads) for _ in range(reps))
             line['cpu_baseline'] = {'value': n_img * reps / t, 'unit': 'images/sec', 'cores': threads, 'kind': 'port',
                                     'sample': '%d passes over %d images of 544x544 (oracle: torch CPU fp32 forward + numpy/C post-process)' % (reps, n_img)}
             line['cpu_baseline'].update(cpu_description())
+            line['cpu_baseline'].update(cpu_split(n_img * reps))
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -67,6 +67,17 @@ def batched_nms_oracle(dets, cats, threshold=0.5):
     return nms_oracle(shifted, threshold)
 
 
+def _threads(fn, items):
+    """Map over independent slices on the host's cores (numpy releases the GIL inside its loops).  Same arithmetic per element as
+    the serial form; only used so that the CPU baseline of bench.py runs the reference's algorithm on all cores, as torch does."""
+    items = list(items)
+    if len(items) <= 1 or (os.cpu_count() or 1) == 1:
+        return [fn(i) for i in items]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(items), os.cpu_count() or 1)) as pool:
+        return list(pool.map(fn, items))
+
+
 def _fma(a, b, c):
     return (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(f32)
 
@@ -84,6 +95,8 @@ def _lerp_index(n_out, n_in):
 def bilinear_x4(x):
     """[..., h, w] fp32 -> [..., 4h, 4w]; torch F.interpolate(scale_factor=4, bilinear, align_corners=False)."""
     x = np.asarray(x, dtype=f32)
+    if x.ndim > 2 and x.shape[0] > 1 and x.shape[-1] * x.shape[-2] >= 64 * 64:       # independent maps: one per thread
+        return np.stack(_threads(bilinear_x4, [x[i] for i in range(x.shape[0])]), axis=0)
     h, w = x.shape[-2:]
     y0, y1, ly0, ly1 = _lerp_index(4 * h, h)
     x0, x1, lx0, lx1 = _lerp_index(4 * w, w)
@@ -195,7 +208,10 @@ class PostProcessOracle:
         tw = (f32(self.orien_thresh) * dets[:, 2] * gw).astype(f32)[:, None, None]
         th = (f32(self.orien_thresh) * dets[:, 3] * gh).astype(f32)[:, None, None]
         if keep.size:
-            mask = (np.abs(pix[anc, 0] - xc) < tw) & (np.abs(pix[anc, 1] - yc) < th)
+            def part(sl):
+                return (np.abs(pix[anc[sl], 0] - xc[sl]) < tw[sl]) & (np.abs(pix[anc[sl], 1] - yc[sl]) < th[sl])
+            n, step = int(keep.size), max(1, -(-int(keep.size) // (os.cpu_count() or 1)))
+            mask = np.concatenate(_threads(part, [slice(i, min(i + step, n)) for i in range(0, n, step)]), axis=0)
         else:
             mask = np.zeros((0, self.H, self.W), dtype=bool)
         return {'bbox': dets, 'mask': mask, 'cls': cats.astype(np.int64), 'keep': keep,
