@@ -12,7 +12,8 @@ What this does (outputs only into ``oracle/_ref/``, which is git-ignored):
   patched temporary (``dets.type()`` -> ``dets.scalar_type()`` on that line) written to
   ``oracle/_ref/build``; no reference source is ever committed.
 * writes empty stub modules for the packages the reference imports but this image lacks
-  (``torchsummary``, ``prettytable``, ``tensorboardX``, ``pycocotools``) to ``oracle/_ref/stubs``.
+  (``torchsummary``, ``prettytable``, ``tensorboardX``, ``pycocotools``, and ``matplotlib`` for ``infer.py`` itself) to
+  ``oracle/_ref/stubs``.
 
 ``import_reference()`` then imports the reference's own ``config`` / ``model`` / ``eval`` packages
 from ``/root/reference`` (only possible in the build container -- the GPU box has no reference).
@@ -35,6 +36,8 @@ _STUB_SOURCES = {
     'pycocotools/mask.py': '',
     'pycocotools/coco.py': 'class COCO:\n    pass\n',
     'pycocotools/cocoeval.py': 'class COCOeval:\n    pass\n',
+    'matplotlib/__init__.py': '',                 # only the reference's infer.py itself imports it (infer.py:9)
+    'matplotlib/pyplot.py': '',
 }
 
 

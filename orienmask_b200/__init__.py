@@ -1,7 +1,7 @@
 """orienmask_b200 -- B200-native inference engine for OrienMask's hot path.
 
-Public surface (mirrors the reference's names so its infer.py / test.py run unchanged when
-``orienmask_b200/dropin`` is first on PYTHONPATH):
+Public surface (mirrors the reference's names so its infer.py / test.py run unchanged through
+``python -m orienmask_b200.dropin infer.py ...``):
 
     OrienMaskYOLOFPNPlus       model/orienmask_yolo_fpnplus.py   (forward pass on tcgen05 kernels)
     OrienMaskYOLO              model/orienmask_yolo.py           (the variant without skip convolutions)

@@ -275,6 +275,49 @@ print(type(m).__module__, type(p).__module__, len(m.state_dict()), p.nms_thresh,
     assert out[7].strip() == '[(17, 17), (34, 34), (68, 68)]'
 
 
+def test_launcher_puts_the_dropin_before_the_script_directory(tmp_path):
+    """`python script.py` puts the script's directory first on sys.path, ahead of PYTHONPATH: a reference-like tree imports its own
+    `model` package then.  `python -m orienmask_b200.dropin script.py` resolves the same import to the drop-in."""
+    import subprocess
+    ref = tmp_path / 'ref'
+    (ref / 'model').mkdir(parents=True)
+    (ref / 'model' / '__init__.py').write_text("OrienMaskYOLOFPNPlus = 'the reference class'\n")
+    (ref / 'main.py').write_text("import sys, model\nprint(getattr(model.OrienMaskYOLOFPNPlus, '__module__', model.OrienMaskYOLOFPNPlus), sys.argv[1:])\n")
+    dropin = os.path.join(ROOT, 'orienmask_b200', 'dropin')
+    plain = subprocess.check_output([sys.executable, 'main.py', '-x'], cwd=str(ref), env=dict(os.environ, PYTHONPATH=dropin)).decode()
+    assert 'the reference class' in plain                                          # PYTHONPATH alone is not enough
+    via = subprocess.check_output([sys.executable, '-m', 'orienmask_b200.dropin', 'main.py', '-x', '1'], cwd=str(ref),
+                                  env=dict(os.environ, PYTHONPATH=ROOT)).decode()
+    assert via.split()[0] == 'orienmask_b200.model' and "['-x', '1']" in via
+    rc = subprocess.run([sys.executable, '-m', 'orienmask_b200.dropin'], cwd=str(ref), env=dict(os.environ, PYTHONPATH=ROOT), capture_output=True)
+    assert rc.returncode == 2 and b'usage' in rc.stderr
+
+
+@pytest.mark.skipif(not os.path.isfile('/root/reference/infer.py'), reason='needs the reference checkout (build container only)')
+def test_reference_infer_py_runs_unchanged_up_to_the_first_forward(tmp_path):
+    """The reference's own infer.py, unmodified, through the launcher: its config (as JSON with n_gpu = 0, so that everything up to
+    the forward runs on this GPU-less box), its builder, this repo's model constructed and strictly loaded from a checkpoint with
+    the reference's 524 keys, the reference's transform / pad / visualiser, this repo's post-process -- until infer.py:155 calls the
+    model, which refuses the CPU tensor (the engine has no CPU path).  On the B200 box the same command runs through."""
+    import json
+    import subprocess
+    from oracle import build_ref
+    from orienmask_b200.synthetic import synthetic_state_dict
+    build_ref.write_stubs()
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, build_ref.STUBS]))
+    code = ("import json, sys; sys.path.insert(0, '/root/reference'); import config as C; "
+            "cfg = dict(C.orienmask_yolo_coco_544_anchor4_fpn_plus_infer); cfg['n_gpu'] = 0; json.dump(cfg, open(sys.argv[1], 'w'))")
+    cfg_file, weights = str(tmp_path / 'infer_cpu.json'), str(tmp_path / 'weights.pth')
+    subprocess.check_call([sys.executable, '-c', code, cfg_file], cwd='/tmp', env=env)
+    assert json.load(open(cfg_file))['model']['type'] == 'OrienMaskYOLOFPNPlus'
+    torch.save({'state_dict': synthetic_state_dict(0)}, weights)                     # infer.py:82 accepts {'state_dict': ...}
+    out = subprocess.run([sys.executable, '-m', 'orienmask_b200.dropin', 'infer.py', '-c', cfg_file, '-w', weights,
+                          '-i', 'assets/000000163126.jpg'], cwd='/root/reference', env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0
+    assert 'infer.py", line 155' in out.stderr and 'predictions = model(image)' in out.stderr, out.stderr[-2000:]
+    assert 'orienmask_b200 runs on CUDA (sm_100a) only' in out.stderr and 'no CPU fallback' in out.stderr
+
+
 def test_shard_bounds_cover_batch():
     from orienmask_b200.sharding import shard_bounds
     for total in (1, 7, 32, 33):
