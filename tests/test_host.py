@@ -318,6 +318,43 @@ def test_reference_infer_py_runs_unchanged_up_to_the_first_forward(tmp_path):
     assert 'orienmask_b200 runs on CUDA (sm_100a) only' in out.stderr and 'no CPU fallback' in out.stderr
 
 
+@pytest.mark.skipif(not os.path.isfile('/root/reference/test.py'), reason='needs the reference checkout (build container only)')
+def test_reference_test_py_runs_unchanged_up_to_the_first_forward(tmp_path):
+    """The reference's own test.py, unmodified, through the launcher: build_tester reads the model config from the checkpoint,
+    builds this repo's model and post-process by name, loads the 524 keys strictly, builds the reference's dataset / transform /
+    dataloader on a one-image COCO-style set, and the reference's Tester (holding this repo's COCOMetrics) reaches
+    trainer/tester.py:40 `predict = self.model(image)`, where the engine refuses the CPU tensor (n_gpu = 0 on this GPU-less box)."""
+    import json
+    import subprocess
+    from oracle import build_ref
+    from orienmask_b200.synthetic import synthetic_state_dict
+    build_ref.write_stubs()
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, build_ref.STUBS]))
+    (tmp_path / 'list.txt').write_text('000000163126.jpg\n')
+    (tmp_path / 'anno.json').write_text(json.dumps({'000000163126.jpg': {'image_id': 163126, 'anno': {'bbox': [], 'cls': [], 'mask': []}}}))
+    code = '''
+import copy, json, sys, torch
+sys.path.insert(0, '/root/reference')
+import config as C
+out = sys.argv[1]
+cfg = copy.deepcopy(C.orienmask_yolo_coco_544_anchor4_fpn_plus_test)
+cfg['n_gpu'], cfg['gt_file'] = 0, None
+cfg['test_loader'].update(batch_size=1, num_workers=0)
+cfg['test_loader']['dataset'].update(list_file=out + '/list.txt', image_dir='/root/reference/assets', anno_file=out + '/anno.json')
+json.dump(cfg, open(out + '/test_cpu.json', 'w'))
+json.dump(copy.deepcopy(C.orienmask_yolo_coco_544_anchor4_fpn_plus['model']), open(out + '/model.json', 'w'))
+'''
+    subprocess.check_call([sys.executable, '-c', code, str(tmp_path)], cwd='/tmp', env=env)
+    model_cfg = json.load(open(str(tmp_path / 'model.json')))
+    assert model_cfg['type'] == 'OrienMaskYOLOFPNPlus' and model_cfg['pretrained']            # build_tester must override it with None
+    torch.save({'state_dict': synthetic_state_dict(0), 'config': {'model': model_cfg}}, str(tmp_path / 'ckpt.pth'))
+    out = subprocess.run([sys.executable, '-m', 'orienmask_b200.dropin', 'test.py', '-c', str(tmp_path / 'test_cpu.json'),
+                          '-w', str(tmp_path / 'ckpt.pth')], cwd='/root/reference', env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0
+    assert 'trainer/tester.py", line 40' in out.stderr and 'predict = self.model(image)' in out.stderr, out.stderr[-2000:]
+    assert 'orienmask_b200 runs on CUDA (sm_100a) only' in out.stderr
+
+
 def test_shard_bounds_cover_batch():
     from orienmask_b200.sharding import shard_bounds
     for total in (1, 7, 32, 33):
