@@ -300,6 +300,108 @@ def measure_stages(torch, ob, transform, host_u8, out, dev, iters=10, post=None,
     return res
 
 
+def _timed_steps(torch, fn, steps, warmup):
+    """ms per call of fn(i) over `steps` calls after `warmup`, CUDA events on the launching stream."""
+    keep = None
+    for i in range(warmup):
+        keep = fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        keep = fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    del keep
+    return e0.elapsed_time(e1) / steps
+
+
+def measure_extras(torch, ob, model, post, resident, dev, peaks):
+    """Secondary, driver-visible measurements on rank 0 at N = 1, after the headline region (each a few hundred milliseconds of GPU time):
+
+    * `parity_mode`   the same step with the conv engine in its tensor-core parity mode (the configuration whose outputs meet the
+                      north-star tolerances end to end: tests/test_gpu_forward.py::test_end_to_end_parity_vs_oracle_544);
+    * `reference_api` the headline step through `post(heads)` -- the reference's return type (trimmed per-image dicts: one host
+                      synchronisation per step on the per-image counts) instead of the padded device-resident result;
+    * `latency_bs1`   BASELINE config 2: batch 1, forward + post-process latency, median of 200 iterations (CUDA graph of the forward);
+    * `config5_960`   BASELINE config 5: batch 8 at 960x960."""
+    import functools
+    import statistics
+    from orienmask_b200.arch import macs_per_image
+    from orienmask_b200.synthetic import synthetic_images
+    res = {}
+
+    def fwd_ms_of(m, x, iters=5):
+        return _timed_steps(torch, lambda i: m(x), iters, 2)
+
+    # ---- reference API: post() returns the reference's list of dicts (host sync on the counts inside) ----
+    ms = _timed_steps(torch, lambda i: post(model(resident[i % 2])), 10, 3)
+    res['reference_api'] = {'value': BATCH * 1e3 / ms, 'unit': 'images/sec', 'ms_per_step': ms,
+                            'what': 'model(x) -> postprocess(heads) returning the per-image dicts of trimmed tensors '
+                                    '(eval/orienmask_yolo_postprocess.py:124,166); the host waits for the NMS kernel only, the mask '
+                                    'kernel overlaps the slicing'}
+    # ---- parity mode ----
+    model.precision = 'parity'
+    ms = _timed_steps(torch, lambda i: post.apply_padded(model(resident[i % 2])), 6, 3)
+    f_ms = fwd_ms_of(model, resident[0])
+    ach = BATCH * GFLOP_PER_IMAGE / f_ms
+    res['parity_mode'] = {'value': BATCH * 1e3 / ms, 'unit': 'images/sec', 'ms_per_step': ms, 'forward_ms': f_ms, 'steps': 6, 'warmup': 3,
+                          'dtype': 'f16x2 (hi+lo pairs, three tcgen05 MMAs per product, fp32 accumulate)',
+                          'roofline': {'bound': 'tensor', 'achieved': ach, 'issued': 3 * ach, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                                       'frac': ach / peaks['tflops'], 'frac_issued': 3 * ach / peaks['tflops'],
+                                       'note': 'achieved = algorithmic FLOPs (173.845 GFLOP/image) / forward time; issued = the 3x tensor work '
+                                               'the split-precision products cost'},
+                          'parity': 'north-star tolerances end to end (boxes/scores 1e-3, mask IoU 0.999, kept sets identical up to listed '
+                                    'margin-limited pairs): tests/test_gpu_forward.py::test_end_to_end_parity_vs_oracle_544'}
+    model.precision = 'fp16'
+    model._engines = {}
+    torch.cuda.empty_cache()
+    # ---- config 2: bs 1 latency ----
+    x1 = resident[0][:1].contiguous()
+    lat = {}
+    for mode in ('eager', 'graph'):
+        model.use_cuda_graph = mode == 'graph'
+        for _ in range(20):
+            post.apply_padded(model(x1))
+        torch.cuda.synchronize()
+        fwd, tot = [], []
+        for _ in range(200):
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            hd = model(x1)
+            e[1].record()
+            post.apply_padded(hd)
+            e[2].record()
+            torch.cuda.synchronize()
+            fwd.append(e[0].elapsed_time(e[1]))
+            tot.append(e[0].elapsed_time(e[2]))
+        lat[mode] = {'forward_ms_median': statistics.median(fwd), 'total_ms_median': statistics.median(tot),
+                     'total_ms_p90': sorted(tot)[int(0.9 * len(tot))]}
+        model._engines = {}
+    model.use_cuda_graph = False
+    best = min(lat, key=lambda k: lat[k]['total_ms_median'])
+    res['latency_bs1'] = {'value': lat[best]['total_ms_median'], 'unit': 'ms', 'higher_is_better': False, 'mode': best, 'iters': 200, 'warmup': 20,
+                          'images_per_s': 1e3 / lat[best]['total_ms_median'], **lat,
+                          'what': 'BASELINE config 2: bs=1 544x544, fp16 forward + decode + NMS + mask assembly, one synchronised iteration at a time'}
+    torch.cuda.empty_cache()
+    # ---- config 5: 960x960, bs 8 ----
+    S, B5 = 960, 8
+    post5 = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5), device=dev,
+                                        grid_size=[[S // s, S // s] for s in (32, 16, 8)], image_size=[S, S], anchors=ANCHORS,
+                                        anchor_mask=ANCHOR_MASK, num_classes=80, conf_thresh=0.005, nms_pre=400, nms_post=100, orien_thresh=0.3)
+    xs = [synthetic_images(B5, S, S, seed=11 + i).to(dev) for i in range(2)]
+    ms = _timed_steps(torch, lambda i: post5.apply_padded(model(xs[i % 2])), 10, 3)
+    f_ms = fwd_ms_of(model, xs[0])
+    gflop = 2e-9 * macs_per_image(S, S)[0]
+    res['config5_960'] = {'value': B5 * 1e3 / ms, 'unit': 'images/sec', 'ms_per_step': ms, 'forward_ms': f_ms, 'steps': 10, 'warmup': 3,
+                          'roofline': {'bound': 'tensor', 'achieved': B5 * gflop / f_ms, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                                       'frac': B5 * gflop / f_ms / peaks['tflops'], 'algorithmic': '%.3f GFLOP/image x %d' % (gflop, B5)},
+                          'what': 'BASELINE config 5: bs=8 960x960 (stride-4 map 240x240, 56 700 predictions), fp16 forward + post-process'}
+    model._engines = {}
+    torch.cuda.empty_cache()
+    return res
+
+
 def bench_device(torch, local):
     """The rank's GPU (a seam for tests/test_bench_flow.py, which walks main() on stand-ins without a GPU)."""
     return torch.device('cuda', local)
@@ -312,7 +414,9 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours')
-    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'parity', 'fp32'],
+                    help="conv engine of the headline line: fp16 (production), parity (tensor cores on fp16 hi+lo pairs, fp32-grade), fp32 (FFMA)")
+    ap.add_argument('--no-extras', action='store_true', help='skip the secondary measurements (parity mode, bs 1 latency, 960x960 bs 8, reference API)')
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ncu-range', action='store_true', help='cudaProfilerStart/Stop around the timed device-resident loop '
@@ -364,7 +468,7 @@ def main():
     def step(x):
         heads = model(x)
         out = post.apply_padded(heads)
-        det, cls, cnt = gather_detections(out.det, out.cls, out.count, packed=out.packed)
+        det, cls, cnt = gather_detections(out.det, out.cls, out.count, packed=out.packed, ready=out.nms_done)
         return out, det, cls, cnt
 
     def barrier():
@@ -382,7 +486,7 @@ def main():
     for i in range(args.warmup):
         heads = model(resident[i % 2])
         out = post.apply_padded(heads)
-        gather_detections(out.det, out.cls, out.count, packed=out.packed)
+        gather_detections(out.det, out.cls, out.count, packed=out.packed, ready=out.nms_done)
     barrier()
     if sampler is not None:
         t_wait = time.time()
@@ -391,7 +495,7 @@ def main():
     for i in range(2):                       # every rank (the step contains a collective): absorbs rank 0's wait above
         heads = model(resident[i % 2])
         out = post.apply_padded(heads)
-        gather_detections(out.det, out.cls, out.count, packed=out.packed)
+        gather_detections(out.det, out.cls, out.count, packed=out.packed, ready=out.nms_done)
     barrier()
 
     # ---- device-resident timing -------------------------------------------------------------
@@ -417,7 +521,7 @@ def main():
         heads = model(resident[i % 2])
         fwd_ev[i][1].record()
         out = post.apply_padded(heads)
-        gather_detections(out.det, out.cls, out.count, packed=out.packed)
+        gather_detections(out.det, out.cls, out.count, packed=out.packed, ready=out.nms_done)
         step_end[i].record()
     e1.record()
     barrier()
@@ -494,11 +598,13 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f16' if args.precision == 'fp16' else 'f32', 'data': 'synthetic',
+            'dtype': {'fp16': 'f16', 'parity': 'f16x2 (hi+lo pairs, fp32-grade)', 'fp32': 'f32'}[args.precision], 'data': 'synthetic',
             'config': {'workload': 'bs=%d %dx%d per GPU: DarkNet-53+FPNPlus forward + decode + batched NMS + mask assembly' % (B, H, W),
                        'global_batch': B * world, 'parallelism': 'dp%d' % world, 'weights': 'synthetic_state_dict(seed 0)',
                        'l2': 'two alternating resident batches; per-step activation traffic (>10 GB) >> 126 MB L2',
-                       'precision': 'fp16 storage / fp32 accumulate convs, fp32 heads + post-process' if args.precision == 'fp16' else 'fp32',
+                       'precision': {'fp16': 'fp16 storage / fp32 accumulate convs, fp32 heads + post-process',
+                                     'parity': 'fp16 hi+lo pairs on the tensor cores (3 MMAs per product), fp32 accumulate, fp32 heads + post-process',
+                                     'fp32': 'fp32 (FFMA)'}[args.precision],
                        'avg_instances_per_image': k_avg},
             'e2e': {'value': world * B * args.steps / e2e_s, 'unit': 'images/sec',
                     'h2d_bytes_per_step': int(host[0].numel() * host[0].element_size()) * world,
@@ -524,6 +630,9 @@ def main():
                          'algorithmic': '%.3f GFLOP/image x %d images per forward' % (GFLOP_PER_IMAGE, B),
                          'peak_source': peaks['source']},
         }
+        if world == 1 and not args.no_extras and args.precision == 'fp16' and H == 544 and B == BATCH:
+            del heads, out
+            line.update(measure_extras(torch, ob, model, post, resident, dev, peaks))
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sd, cpost = make_cpu_reference()

@@ -140,6 +140,11 @@ int32_t om_nms(const float* dets, int32_t n, float threshold, int64_t* keep, int
  */
 #define OM_PREC_F32 0   /* parity engine: fp32 storage, FFMA                                     */
 #define OM_PREC_F16 1   /* production engine: fp16 storage, tcgen05 tensor cores, fp32 accumulate */
+#define OM_PREC_SPLIT 2 /* parity engine on the tensor cores: every activation and weight is an fp16 pair hi + lo
+                           (hi = fp16(v), lo = fp16(v - hi): ~22 significant bits), D = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo as
+                           three tcgen05 MMAs into one fp32 TMEM accumulator.  Activations: [.., W, 2*C] halves (hi | lo along
+                           the channel axis); weights [k*k][cout_pad][2*cin] halves (hi | lo), pre-scaled by a power of two so
+                           that W_lo stays a normal fp16 number (undone by acc_scale)                                  */
 
 #define OM_OUT_ACT 0      /* padded-row NHWC activation in the engine precision                    */
 #define OM_OUT_PARTIAL 1  /* padded-row NHWC fp32 pre-activation partial sum (no bias, no act)     */
@@ -158,7 +163,8 @@ typedef struct om_conv_desc {
     int32_t out_kind;              /* OM_OUT_*                                                    */
     const void* input;             /* device, engine precision                                    */
     const void* weights;           /* device: F16 -> [k*k][cout_pad][cin] half, cout_pad = cout rounded up
-                                      to 16 (to 32 when cout < 32);  F32 -> [k*k][cin][cout] float */
+                                      to 32;  F32 -> [k*k][cin][cout rounded up to 4] float;
+                                      SPLIT -> [k*k][cout_pad][2*cin] half (hi | lo)                */
     const float* bias;             /* device [cout] or NULL                                       */
     const void* residual;          /* device, same layout/precision as an OM_OUT_ACT output, added AFTER the
                                       activation (darknet.py:15), or NULL                         */
@@ -172,6 +178,8 @@ typedef struct om_conv_desc {
      * Every tap of the stride-2 convolution is then a dense TMA box instead of a strided gather. */
     int32_t in_s2d;                /* the input (of a stride-2 layer) is parity-split                  */
     int32_t out_s2d;               /* write the OM_OUT_ACT output parity-split (no residual in place)  */
+    float acc_scale;               /* OM_PREC_SPLIT: the accumulator is multiplied by this (a power of two, the inverse of the
+                                      weight pre-scale) before up-add, bias and activation; 0 means 1  */
 } om_conv_desc;
 
 typedef struct om_conv om_conv;
@@ -188,7 +196,8 @@ void om_conv_destroy(om_conv* conv);
  * First layer (3 -> cout, 3x3, stride 1, BN folded, LeakyReLU) straight from the caller's image.
  *   image    device fp32 NCHW [batch,3,h,w]
  *   weights  device fp32 [27][cout] (tap-major: (ky*3+kx)*3+ci), bias fp32 [cout]; cout == 32
- *   output   padded-row NHWC [batch*rows, w, cout] in `precision` (parity-split when out_s2d, see om_conv_desc)
+ *   output   padded-row NHWC [batch*rows, w, cout] in `precision` (parity-split when out_s2d, see om_conv_desc);
+ *            OM_PREC_SPLIT: [batch*rows, w, 2*cout] halves (hi | lo), computed in fp32 on the CUDA cores
  */
 int32_t om_stem_conv(int32_t precision, const float* image, const float* weights, const float* bias, void* output,
                      int32_t batch, int32_t h, int32_t w, int32_t rows, int32_t cout, int32_t out_s2d, void* stream);

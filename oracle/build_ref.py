@@ -24,9 +24,24 @@ import sys
 import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-REF_ROOT = os.environ.get('ORIENMASK_REFERENCE', '/root/reference')
 OUT = os.path.join(HERE, '_ref')
 STUBS = os.path.join(OUT, 'stubs')
+# A byte-for-byte copy of the reference checkout that travels to the GPU box with the repo snapshot (git-ignored, NOT
+# gpurun-ignored; made by ship_reference() in the build container, where /root/reference exists).  Only `-m gpu` TESTS that run
+# the reference's own infer.py / test.py / nn.Module on the B200 read it; the product, smoke() and bench.py never do.
+SHIPPED = os.path.join(os.path.dirname(HERE), 'baseline', '_ref', 'reference')
+
+
+def _default_ref_root():
+    env = os.environ.get('ORIENMASK_REFERENCE')
+    if env:
+        return env
+    if os.path.isfile('/root/reference/eval/src/nms_cpu.cpp'):
+        return '/root/reference'
+    return SHIPPED
+
+
+REF_ROOT = _default_ref_root()
 
 _STUB_SOURCES = {
     'torchsummary.py': 'def summary(*a, **k):\n    pass\n',
@@ -34,8 +49,48 @@ _STUB_SOURCES = {
     'tensorboardX.py': 'class SummaryWriter:\n    pass\n',
     'pycocotools/__init__.py': '',
     'pycocotools/mask.py': '',
-    'pycocotools/coco.py': 'class COCO:\n    pass\n',
-    'pycocotools/cocoeval.py': 'class COCOeval:\n    pass\n',
+    # Stand-ins with pycocotools' call surface, enough for the reference's test.py / Tester to run to its last line on a box
+    # without the real package: ground truth and results are loaded, NO AP is computed -- every statistic is -1, which is what
+    # pycocotools itself reports when nothing can be matched.  Test infrastructure only.
+    'pycocotools/coco.py': """import json
+
+
+class COCO:
+    def __init__(self, annotation_file=None):
+        self.dataset = json.load(open(annotation_file)) if annotation_file else {'images': [], 'annotations': [], 'categories': []}
+        self.anns = list(self.dataset.get('annotations', []))
+
+    def getImgIds(self):
+        return [im['id'] for im in self.dataset.get('images', [])]
+
+    def getCatIds(self):
+        return [c['id'] for c in self.dataset.get('categories', [])]
+
+    def loadRes(self, res_file):
+        res = COCO()
+        res.dataset = dict(self.dataset)
+        res.anns = json.load(open(res_file)) if isinstance(res_file, str) else list(res_file)
+        return res
+""",
+    'pycocotools/cocoeval.py': """import numpy as np
+
+
+class COCOeval:
+    def __init__(self, coco_gt=None, coco_dt=None, iouType='segm'):
+        self.gt, self.dt, self.iouType = coco_gt, coco_dt, iouType
+        self.stats, self.eval = None, None
+
+    def evaluate(self):
+        pass
+
+    def accumulate(self):
+        k = max(1, len(self.gt.getCatIds()))
+        self.eval = {'precision': -np.ones((10, 101, k, 4, 3)), 'recall': -np.ones((10, k, 4, 3))}
+
+    def summarize(self):
+        self.stats = -np.ones(12)
+        print('pycocotools stand-in: %d %s results loaded, no AP computed' % (len(self.dt.anns), self.iouType))
+""",
     'matplotlib/__init__.py': '',                 # only the reference's infer.py itself imports it (infer.py:9)
     'matplotlib/pyplot.py': '',
 }
@@ -51,6 +106,28 @@ def write_stubs():
         os.makedirs(os.path.dirname(path), exist_ok=True)
         with open(path, 'w') as f:
             f.write(src)
+
+
+def ship_reference():
+    """Copy the reference checkout into baseline/_ref/reference (git-ignored; it ships to the GPU box with the snapshot) so that
+    the `-m gpu` drop-in tests can run the reference's own, unmodified infer.py / test.py / nn.Module there.  No-op when
+    /root/reference is absent (i.e. on the GPU box itself).  Returns the path of the copy or None."""
+    src = '/root/reference'
+    if not os.path.isfile(os.path.join(src, 'infer.py')):
+        return SHIPPED if os.path.isfile(os.path.join(SHIPPED, 'infer.py')) else None
+    import shutil
+    if os.path.isdir(SHIPPED):
+        shutil.rmtree(SHIPPED)
+    shutil.copytree(src, SHIPPED, ignore=shutil.ignore_patterns('.git', '__pycache__', '*.pyc', '*.log', 'framework.png'))
+    return SHIPPED
+
+
+def reference_root():
+    """The reference tree usable in this process (/root/reference in the build container, the shipped copy on the GPU box) or None."""
+    for cand in (os.environ.get('ORIENMASK_REFERENCE'), '/root/reference', SHIPPED):
+        if cand and os.path.isfile(os.path.join(cand, 'infer.py')):
+            return cand
+    return None
 
 
 def _find_built():

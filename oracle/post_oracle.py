@@ -227,6 +227,10 @@ class PostProcessOracle:
         out = self.finish(coord[sel], score, cls, self.pred_anchor[sel], pix)
         out['pred'] = sel[out['keep']]          # flat prediction index of every kept detection
         out['n_candidates'] = int(sel.size)
+        # for the end-to-end parity reports (tests/common.py:e2e_agreement): the pre-NMS candidate list and every score
+        out['cand'] = {'pred': sel, 'cls': cls, 'score': score, 'coord': coord[sel]}
+        out['conf'] = conf
+        out['coord_all'] = coord
         return out
 
     def __call__(self, predict):

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get('ORIENMASK_B200_LIB') or os.path.join(HERE, 'liborienm
 
 OM_MAX_SCALES = 4
 OM_MAX_ANCHORS = 16
-PREC_F32, PREC_F16 = 0, 1
+PREC_F32, PREC_F16, PREC_SPLIT = 0, 1, 2
 OUT_ACT, OUT_PARTIAL, OUT_NCHW = 0, 1, 2
 
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
@@ -37,7 +37,7 @@ class ConvDesc(ctypes.Structure):
         ('cin', c_i32), ('cout', c_i32), ('cout_stride', c_i32),
         ('ksize', c_i32), ('stride', c_i32), ('leaky', c_i32), ('out_kind', c_i32),
         ('input', c_vp), ('weights', c_vp), ('bias', c_vp), ('residual', c_vp), ('upadd', c_vp),
-        ('up_rows', c_i32), ('output', c_vp), ('in_s2d', c_i32), ('out_s2d', c_i32),
+        ('up_rows', c_i32), ('output', c_vp), ('in_s2d', c_i32), ('out_s2d', c_i32), ('acc_scale', c_f32),
     ]
 
 
@@ -122,3 +122,35 @@ def stream_ptr():
 
 def ptr(t):
     return c_vp(t.data_ptr()) if t is not None else c_vp(0)
+
+
+def pack_conv_weights(w, precision):
+    """[cout, cin, k, k] fp32 (BN already folded) -> (engine layout of om_conv_desc.weights, acc_scale).
+
+    F16: [k*k][cout_pad][cin] half.  F32: [k*k][cin][cout_pad4] float.  SPLIT: [k*k][cout_pad][2*cin] half, hi | lo of the weights
+    scaled by a power of two 2^s that puts max|w| in [2^13, 2^14): W_lo = fp16(w*2^s - W_hi) is then a normal fp16 number for
+    every weight above 2^-15 of the largest one, and acc_scale = 2^-s undoes the scale in the epilogue (exactly)."""
+    import math
+    import torch
+    cout, cin, k, _ = w.shape
+    if precision == PREC_F32:
+        cpad = (cout + 3) // 4 * 4
+        p = torch.zeros(k * k, cin, cpad, dtype=torch.float32, device=w.device)
+        p[:, :, :cout] = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout)
+        return p, 1.0
+    cpad = (cout + 31) // 32 * 32
+    wt = w.float().permute(2, 3, 0, 1).reshape(k * k, cout, cin)
+    if precision == PREC_F16:
+        p = torch.zeros(k * k, cpad, cin, dtype=torch.float16, device=w.device)
+        p[:, :cout] = wt.to(torch.float16)
+        return p, 1.0
+    amax = float(wt.abs().max())
+    s = 13 - math.floor(math.log2(amax)) if amax > 0 else 0
+    s = max(-24, min(40, s))
+    ws = wt * (2.0 ** s)
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.float()).to(torch.float16)
+    p = torch.zeros(k * k, cpad, 2 * cin, dtype=torch.float16, device=w.device)
+    p[:, :cout, :cin] = hi
+    p[:, :cout, cin:] = lo
+    return p, 2.0 ** (-s)

@@ -23,7 +23,6 @@ UNITS = [
     ('rle.cu', ['-fmad=false']),
     ('blend.cu', ['-fmad=false']),
     ('conv_f32.cu', []),
-    ('conv_tc.cu', []),
     ('conv_tc2.cu', []),
     ('conv_stem_tc.cu', []),
 ]

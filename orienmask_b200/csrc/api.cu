@@ -33,18 +33,18 @@ bool pdl_enabled() {
 
 struct om_conv {
     om_conv_desc desc;
-    void* tc_plan;
-    int tc_version;      // 2 = CTA-pair kernel (default), 1 = single-CTA kernel (ORIENMASK_B200_CONV=v1, kept for A/B measurements)
+    void* tc_plan;       // CTA-pair tcgen05 plan (OM_PREC_F16 / OM_PREC_SPLIT); null for the FFMA engine
 };
 
-extern "C" int32_t om_abi_version(void) { return 6; }
+extern "C" int32_t om_abi_version(void) { return 7; }
 extern "C" const char* om_last_error(void) { return om::error_buffer(); }
 extern "C" int64_t om_launch_count(void) { return om::g_launches; }
 extern "C" void om_launch_count_reset(void) { om::g_launches = 0; }
 
 extern "C" int32_t om_conv_create(const om_conv_desc* d, om_conv** out) {
     if (!d || !out) return om::fail(OM_ERR_INVALID, "om_conv_create: null argument");
-    if (d->precision != OM_PREC_F32 && d->precision != OM_PREC_F16) return om::fail(OM_ERR_INVALID, "unknown precision %d", d->precision);
+    if (d->precision != OM_PREC_F32 && d->precision != OM_PREC_F16 && d->precision != OM_PREC_SPLIT)
+        return om::fail(OM_ERR_INVALID, "unknown precision %d", d->precision);
     if (d->ksize != 1 && d->ksize != 3) return om::fail(OM_ERR_UNSUPPORTED, "ksize must be 1 or 3 (got %d)", d->ksize);
     if (d->stride != 1 && d->stride != 2) return om::fail(OM_ERR_UNSUPPORTED, "stride must be 1 or 2 (got %d)", d->stride);
     if (d->batch < 1 || d->in_h < 1 || d->in_w < 1 || d->out_h < 1 || d->out_w < 1 || d->cin < 1 || d->cout < 1)
@@ -66,10 +66,8 @@ extern "C" int32_t om_conv_create(const om_conv_desc* d, om_conv** out) {
     om_conv* c = new om_conv();
     c->desc = *d;
     c->tc_plan = nullptr;
-    if (d->precision == OM_PREC_F16) {
-        const char* sel = getenv("ORIENMASK_B200_CONV");
-        c->tc_version = (sel && sel[0] == 'v' && sel[1] == '1') ? 1 : 2;
-        int32_t rc = c->tc_version == 2 ? om::tc2_plan_create(*d, &c->tc_plan) : om::tc_plan_create(*d, &c->tc_plan);
+    if (d->precision != OM_PREC_F32) {
+        int32_t rc = om::tc2_plan_create(*d, &c->tc_plan);
         if (rc != OM_OK) { delete c; return rc; }
     }
     *out = c;
@@ -78,17 +76,13 @@ extern "C" int32_t om_conv_create(const om_conv_desc* d, om_conv** out) {
 
 extern "C" int32_t om_conv_run(const om_conv* c, void* stream) {
     if (!c) return om::fail(OM_ERR_INVALID, "om_conv_run: null plan");
-    if (c->desc.precision == OM_PREC_F16)
-        return c->tc_version == 2 ? om::tc2_plan_run(c->tc_plan, (cudaStream_t)stream) : om::tc_plan_run(c->tc_plan, (cudaStream_t)stream);
+    if (c->tc_plan) return om::tc2_plan_run(c->tc_plan, (cudaStream_t)stream);
     return om::f32_conv_run(c->desc, (cudaStream_t)stream);
 }
 
 extern "C" int32_t om_conv_run_to(const om_conv* c, void* output, void* stream) {
     if (!c || !output) return om::fail(OM_ERR_INVALID, "om_conv_run_to: null argument");
-    if (c->desc.precision == OM_PREC_F16) {
-        if (c->tc_version != 2) return om::fail(OM_ERR_UNSUPPORTED, "om_conv_run_to needs the CTA-pair engine");
-        return om::tc2_plan_run(c->tc_plan, (cudaStream_t)stream, output);
-    }
+    if (c->tc_plan) return om::tc2_plan_run(c->tc_plan, (cudaStream_t)stream, output);
     if (c->desc.residual) return om::fail(OM_ERR_INVALID, "om_conv_run_to: layers with a residual write in place");
     om_conv_desc d = c->desc;
     d.output = output;
@@ -97,7 +91,7 @@ extern "C" int32_t om_conv_run_to(const om_conv* c, void* output, void* stream) 
 
 extern "C" void om_conv_destroy(om_conv* c) {
     if (!c) return;
-    if (c->tc_plan) { if (c->tc_version == 2) om::tc2_plan_destroy(c->tc_plan); else om::tc_plan_destroy(c->tc_plan); }
+    if (c->tc_plan) om::tc2_plan_destroy(c->tc_plan);
     delete c;
 }
 
@@ -109,7 +103,7 @@ extern "C" int32_t om_debug_conv_timeline(void* dev_ptr) { return om::tc2_set_ti
 // block_n, tiles_n, stages, n_sub, h_stages, acc_stages, has_res (1 fp16 residual, 2 staged up-add), res_direct, smem bytes, grid,
 // CTA-pair tiles, taps, K chunks, BK, TMEM columns, cout, out_h, out_w.
 extern "C" int32_t om_debug_conv_plan_info(const om_conv* c, int32_t* info) {
-    if (!c || !info || c->desc.precision != OM_PREC_F16 || c->tc_version != 2 || !c->tc_plan)
+    if (!c || !info || !c->tc_plan)
         return om::fail(OM_ERR_INVALID, "om_debug_conv_plan_info: not a plan of the CTA-pair engine");
     om::tc2_plan_info(c->tc_plan, info);
     return OM_OK;

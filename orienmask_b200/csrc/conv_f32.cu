@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const F32Params p) {
 }
 
 // Stem: one thread per output pixel, all `COUT` channels; weights broadcast from shared memory.
-template <typename OutT, int COUT>
+// SPLIT (OM_PREC_SPLIT): the fp32 result is stored as an fp16 pair, [.., 2 * COUT] halves per pixel (hi | lo).
+template <typename OutT, int COUT, bool SPLIT = false>
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                    const float* __restrict__ bias, OutT* __restrict__ out,
                                                    int batch, int h, int wd, int rows, int out_s2d) {
@@ -152,8 +153,23 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ img
         const int Yo = n * rows + y;
         opix = (size_t)(2 * (Yo & 1) + (x & 1)) * ((size_t)batch * rows / 2 * (wd / 2)) + (size_t)(Yo >> 1) * (wd / 2) + (x >> 1);
     }
-    OutT* o = out + opix * COUT;
-    if constexpr (sizeof(OutT) == 2) {
+    OutT* o = out + opix * (SPLIT ? 2 * COUT : COUT);
+    if constexpr (SPLIT) {
+#pragma unroll
+        for (int c = 0; c < COUT; c += 8) {
+            uint4 hv, lv;
+            __half2* hh = reinterpret_cast<__half2*>(&hv);
+            __half2* lh = reinterpret_cast<__half2*>(&lv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hh[j] = __floats2half2_rn(acc[c + 2 * j], acc[c + 2 * j + 1]);
+                const float2 back = __half22float2(hh[j]);
+                lh[j] = __floats2half2_rn(acc[c + 2 * j] - back.x, acc[c + 2 * j + 1] - back.y);
+            }
+            *reinterpret_cast<uint4*>(o + c) = hv;
+            *reinterpret_cast<uint4*>(o + COUT + c) = lv;
+        }
+    } else if constexpr (sizeof(OutT) == 2) {
 #pragma unroll
         for (int c = 0; c < COUT; c += 8) {
             uint4 ov;
@@ -206,7 +222,9 @@ extern "C" int32_t om_stem_conv(int32_t precision, const float* image, const flo
         if (!(sel && sel[0] == 'f') && h % 4 == 0 && w % 32 == 0)          // default: tensor-core stem (conv_stem_tc.cu)
             return om::stem_tc_run(image, weights, bias, output, batch, h, w, rows, out_s2d, st);
         stem_kernel<__half, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d);
-    } else if (precision == OM_PREC_F32)
+    } else if (precision == OM_PREC_SPLIT)
+        stem_kernel<__half, 32, true><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d);
+    else if (precision == OM_PREC_F32)
         stem_kernel<float, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<float*>(output), batch, h, w, rows, out_s2d);
     else
         return om::fail(OM_ERR_INVALID, "om_stem_conv: unknown precision %d", precision);

@@ -7,11 +7,6 @@
 
 namespace om {
 
-// fp16 tcgen05 engine (conv_tc.cu)
-int32_t tc_plan_create(const om_conv_desc& d, void** out);
-int32_t tc_plan_run(const void* plan, cudaStream_t stream);
-void tc_plan_destroy(void* plan);
-
 // fp16 tcgen05 engine on CTA pairs, cta_group::2 (conv_tc2.cu)
 int32_t tc2_plan_create(const om_conv_desc& d, void** out);
 int32_t tc2_plan_run(const void* plan, cudaStream_t stream, void* output = nullptr);

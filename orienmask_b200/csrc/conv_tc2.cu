@@ -40,7 +40,13 @@ struct Tc2Params {
     int tiles_x, pairs_y, tiles_n;       // pair grid; linear pair id = (py * tiles_x + tx) * tiles_n + tn
     int tw, th;                          // pixel tile (tw * th <= 128)
     int taps, stride;
-    int k_chunks;                        // cin / BK
+    int k_chunks;                        // K-loop chunks per tap: cin / BK (split precision: 3 * cin / BK, see below)
+    int a_chunks;                        // BK-channel chunks of one pixel in memory: cin / BK (split precision: 2 * cin / BK, hi | lo)
+    int split_kr;                        // split precision (OM_PREC_SPLIT): cin / BK, else 0.  Activations and weights are stored as
+                                         // fp16 hi | lo halves along the channel axis and the K loop of a tap walks 3 * kr chunks:
+                                         // (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo) -- three MMAs into the same fp32 accumulator
+    float acc_scale;                     // split precision: the weights were scaled by a power of two to keep W_lo normal; undone here
+    int pix_stride, lo_off;              // split precision: fp16 elements per output pixel (2 * cout_stride) and offset of the lo half
     int block_n, half_n;                 // UMMA N and the rows of it each CTA stages
     int cout_pad;
     int halo;                            // 3x3 stride 1 with tw == 8: one halo box per chunk feeds all nine taps
@@ -304,7 +310,7 @@ struct EpiCtx {
     int warp, lane, first_pair, pair_step, num_pairs;
 };
 
-template <int KIND, int ADD, bool FLAT>
+template <int KIND, int ADD, bool FLAT, bool SPLIT>
 __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& c) {
     const int quad = c.warp & 3;
     const int grp = (c.warp - kEpiWarp0) >> 2;
@@ -348,8 +354,8 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
         uint4 rr[4] = {};
         const __half* rsrc = nullptr;
         if (ADD == 3) {
-            rsrc = reinterpret_cast<const __half*>(p.residual) + ((size_t)Y * p.out_w + x) * p.cout_stride + n0;
-            if (valid && j_first < n_chunks) ldg_res32(rr, rsrc + j_first * 32);
+            rsrc = reinterpret_cast<const __half*>(p.residual) + ((size_t)Y * p.out_w + x) * (SPLIT ? p.pix_stride : p.cout_stride) + n0;
+            if (!SPLIT && valid && j_first < n_chunks) ldg_res32(rr, rsrc + j_first * 32);
         }
         mbar_wait(&c.tmem_full[as], aphase);
         if (pair == c.first_pair) tick(6, c.warp == kEpiWarp0 && c.lane == 0);
@@ -375,6 +381,10 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
                 float f[32];
     #pragma unroll
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+                if (SPLIT) {
+    #pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] *= p.acc_scale;                        // power of two: exact
+                }
                 if (ADD == 2) {
                     const uint8_t* ubuf = c.res_buf + rb * p.res_buf_bytes;
                     if (in_tile) {
@@ -414,7 +424,24 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
                             }
                         }
                     }
-                    if (ADD == 3) {
+                    if (ADD == 3 && SPLIT) {
+                        if (valid) {                         // residual = hi + lo, both halves read by the thread that owns the pixel
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                ldg_res32(rr, rsrc + half * p.lo_off + j * 32);
+#pragma unroll
+                                for (int i = 0; i < 32; i += 8) {
+                                    const __half2* rh = reinterpret_cast<const __half2*>(&rr[i >> 3]);
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const float2 rf = __half22float2(rh[q]);
+                                        f[i + 2 * q] += rf.x; f[i + 2 * q + 1] += rf.y;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    if (ADD == 3 && !SPLIT) {
                         if (valid) {
 #pragma unroll
                             for (int i = 0; i < 32; i += 8) {
@@ -428,7 +455,26 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
                             if (j + kEpiGroups < n_chunks) ldg_res32(rr, rsrc + (j + kEpiGroups) * 32);
                         }
                     }
-                    if (valid) {
+                    if (valid && SPLIT) {                    // hi = fp16(f), lo = fp16(f - hi): the pair carries ~22 significant bits
+                        size_t opix = pix;
+                        if (p.out_s2d) opix = (size_t)(2 * (Y & 1) + (x & 1)) * (size_t)p.s2d_plane + (size_t)(Y >> 1) * (p.out_w >> 1) + (x >> 1);
+                        __half* o = reinterpret_cast<__half*>(p.output) + opix * p.pix_stride + cg;
+    #pragma unroll
+                        for (int i = 0; i < 32; i += 16) {
+                            uint32_t wh[8], wl[8];
+    #pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const __half2 h = __floats2half2_rn(f[i + 2 * q], f[i + 2 * q + 1]);
+                                const float2 hb = __half22float2(h);
+                                const __half2 l = __floats2half2_rn(f[i + 2 * q] - hb.x, f[i + 2 * q + 1] - hb.y);
+                                wh[q] = *reinterpret_cast<const uint32_t*>(&h);
+                                wl[q] = *reinterpret_cast<const uint32_t*>(&l);
+                            }
+                            st_global_256(o + i, wh);
+                            st_global_256(o + p.lo_off + i, wl);
+                        }
+                    }
+                    if (valid && !SPLIT) {
                         size_t opix = pix;
                         if (p.out_s2d) opix = (size_t)(2 * (Y & 1) + (x & 1)) * (size_t)p.s2d_plane + (size_t)(Y >> 1) * (p.out_w >> 1) + (x >> 1);
                         __half* o = reinterpret_cast<__half*>(p.output) + opix * p.cout_stride + cg;
@@ -475,7 +521,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
 }
 
 
-template <int BK>
+template <int BK, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ CUtensorMap map_res, const Tc2Params p) {
@@ -555,7 +601,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             int st = 0; uint32_t s_phase = 0;
             int hs = 0; uint32_t h_phase = 0;
             const uint32_t s_tx = 2u * (uint32_t)p.n_sub * (uint32_t)((p.halo ? 0 : p.a_box_pixels * BK * 2) + b_sub);
-            const uint32_t h_tx = 2u * (uint32_t)(p.k_chunks * p.halo_planes) * (uint32_t)(p.a_box_pixels * BK * 2);
+            const uint32_t h_tx = 2u * (uint32_t)(p.a_chunks * p.halo_planes) * (uint32_t)(p.a_box_pixels * BK * 2);
             if (p.b_resident) {                               // the whole weight tensor (this CTA's half of the rows), once
                 const uint32_t lb = mapa(smem_u32(&s_full[0]), 0);
                 if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[0], 2u * (uint32_t)(p.taps * p.k_chunks * b_sub));
@@ -577,8 +623,8 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     const uint32_t lb = mapa(smem_u32(&h_full[hs]), 0);
                     if (pair == first_pair) { pdl_wait(); tick(2, lane == 0); }
                     if (lane == 0 && rank == 0) mbar_expect_tx(&h_full[hs], h_tx);
-                    if (lane < p.k_chunks * p.halo_planes) {       // buffer order: [plane][chunk]; plane coordinates == output coordinates
-                        const int plane = lane / p.k_chunks, kc = lane - plane * p.k_chunks;
+                    if (lane < p.a_chunks * p.halo_planes) {       // buffer order: [plane][chunk]; plane coordinates == output coordinates
+                        const int plane = lane / p.a_chunks, kc = lane - plane * p.a_chunks;
                         tma_load_3d_pair(h_ring + (size_t)hs * p.h_stage_bytes + (size_t)lane * p.h_chunk_bytes, &maps_a.m[plane], lb, kc * BK, x0 - 1, y0 - 1);
                     }
                     __syncwarp();
@@ -590,6 +636,11 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     uint8_t* sb = s_ring + (size_t)st * stage_bytes;
                     const int i = g * p.n_sub + lane;                // (tap, chunk) block of this lane, tap-major
                     const int tap = i / p.k_chunks, kc = i - tap * p.k_chunks;
+                    int ka = kc, kb = kc;                            // channel chunk of the activation / weight block in memory
+                    if (SPLIT) {                                     // (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
+                        if (kc >= 2 * p.split_kr) ka = kc - 2 * p.split_kr;
+                        if (kc >= p.split_kr) kb = kc - p.split_kr;
+                    }
                     int dx = 0, dy = 0, sel = 0;
                     int tap_r = 0, tap_s = 0;
                     if (!p.halo && p.taps == 9) {
@@ -604,9 +655,9 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     if (!p.halo && pair == first_pair && g == 0) { pdl_wait(); tick(2, lane == 0); }   // first activation load
                     if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[st], s_tx);
                     if (lane < p.n_sub) {
-                        if (p.flat) tma_load_im2col_pair(sb + (size_t)lane * sub_bytes, &map_a0, lb, kc * BK, fw, fh, fo.n, tap_s, tap_r);
-                        else if (!p.halo) tma_load_3d_pair(sb + (size_t)lane * sub_bytes, &maps_a.m[sel], lb, kc * BK, x0 + dx, y0 + dy);
-                        tma_load_2d_pair(sb + (size_t)lane * sub_bytes + a_sub, &map_b, lb, kc * BK, tap * p.cout_pad + n0);
+                        if (p.flat) tma_load_im2col_pair(sb + (size_t)lane * sub_bytes, &map_a0, lb, ka * BK, fw, fh, fo.n, tap_s, tap_r);
+                        else if (!p.halo) tma_load_3d_pair(sb + (size_t)lane * sub_bytes, &maps_a.m[sel], lb, ka * BK, x0 + dx, y0 + dy);
+                        tma_load_2d_pair(sb + (size_t)lane * sub_bytes + a_sub, &map_b, lb, kb * BK, tap * p.cout_pad + n0);
                     }
                     __syncwarp();
                     if (pair == first_pair && g == 0) tick(3, lane == 0);
@@ -629,7 +680,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             const uint64_t hi_b = ((uint64_t)((8 * pixel_bytes) >> 4) << 32) | (1ull << 16) | (1ull << 46) | (kLayout << 61);
             const uint64_t hi_a = p.halo ? (((uint64_t)(((uint32_t)p.halo_pitch * pixel_bytes) >> 4) << 32) | (1ull << 16) | (1ull << 46) | (kLayout << 61)) : hi_b;
             // descriptor offset (16-byte units) of filter tap (r, s) inside the tile's halo stage
-            const uint32_t plane16 = (uint32_t)p.k_chunks * ((uint32_t)p.h_chunk_bytes >> 4);
+            const uint32_t plane16 = (uint32_t)p.a_chunks * ((uint32_t)p.h_chunk_bytes >> 4);
             auto tap_off = [&](int r, int s) -> uint32_t {
                 if (p.halo_s2) return (uint32_t)(2 * (r != 1) + (s != 1)) * plane16 + (uint32_t)((r != 0) * p.halo_pitch + (s != 0)) * (pixel_bytes >> 4);
                 return (uint32_t)(r * p.halo_pitch + s) * (pixel_bytes >> 4);
@@ -673,7 +724,8 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                         uint64_t bd = hi_b | (uint64_t)(sb16 + asub16);
                         uint64_t ad_ring = hi_a | (uint64_t)sb16;
                         for (int j = 0; j < p.n_sub; ++j) {
-                            const uint64_t ad = p.halo ? ad_tile + (uint64_t)(tap_off16 + (uint32_t)kc * hchunk16) : ad_ring;
+                            const int ka = (SPLIT && kc >= p.a_chunks) ? kc - p.a_chunks : kc;     // split: the third pass re-reads A_hi
+                            const uint64_t ad = p.halo ? ad_tile + (uint64_t)(tap_off16 + (uint32_t)ka * hchunk16) : ad_ring;
                             if (elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < BK / 16; ++k)
@@ -739,16 +791,16 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
         c.res_buf = res_buf; c.s_bias = s_bias; c.s_bias_addr = smem_u32(s_bias);
         c.warp = warp; c.lane = lane; c.first_pair = first_pair; c.pair_step = pair_step; c.num_pairs = num_pairs;
         if (p.flat) {
-            if (p.out_kind == OM_OUT_PARTIAL) epilogue_loop<1, 0, true>(p, c);
-            else if (p.res_direct) epilogue_loop<0, 3, true>(p, c);
-            else epilogue_loop<0, 0, true>(p, c);
+            if (p.out_kind == OM_OUT_PARTIAL) epilogue_loop<1, 0, true, SPLIT>(p, c);
+            else if (p.res_direct) epilogue_loop<0, 3, true, SPLIT>(p, c);
+            else epilogue_loop<0, 0, true, SPLIT>(p, c);
         }
-        else if (p.out_kind == OM_OUT_NCHW) epilogue_loop<2, 0, false>(p, c);
-        else if (p.out_kind == OM_OUT_PARTIAL) { if (p.has_res == 2) epilogue_loop<1, 2, false>(p, c); else epilogue_loop<1, 0, false>(p, c); }
-        else if (p.res_direct) epilogue_loop<0, 3, false>(p, c);
-        else if (p.has_res == 1) epilogue_loop<0, 1, false>(p, c);
-        else if (p.has_res == 2) epilogue_loop<0, 2, false>(p, c);
-        else epilogue_loop<0, 0, false>(p, c);
+        else if (p.out_kind == OM_OUT_NCHW) epilogue_loop<2, 0, false, SPLIT>(p, c);
+        else if (p.out_kind == OM_OUT_PARTIAL) { if (p.has_res == 2) epilogue_loop<1, 2, false, SPLIT>(p, c); else epilogue_loop<1, 0, false, SPLIT>(p, c); }
+        else if (p.res_direct) epilogue_loop<0, 3, false, SPLIT>(p, c);
+        else if (!SPLIT && p.has_res == 1) epilogue_loop<0, 1, false, false>(p, c);      // split precision reads its residual directly
+        else if (p.has_res == 2) epilogue_loop<0, 2, false, SPLIT>(p, c);
+        else epilogue_loop<0, 0, false, SPLIT>(p, c);
     }
 
     tick(9, threadIdx.x == 0);
@@ -874,6 +926,7 @@ struct Tc2Plan {
     CUtensorMap map_b, map_res;
     Tc2Params p;
     int bk;
+    bool split;
     int grid;
     size_t smem;
 };
@@ -903,6 +956,10 @@ int32_t tc2_set_wait_hint(unsigned int ns);
 
 static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, bool* halo_used) {
     if (d.cin % 32) return fail(OM_ERR_INVALID, "fp16 engine needs cin %% 32 == 0 (got %d)", d.cin);
+    const bool split = d.precision == OM_PREC_SPLIT;
+    const int cin_mem = split ? 2 * d.cin : d.cin;          // fp16 elements per input pixel (split precision: hi | lo)
+    if (split && d.out_kind == OM_OUT_ACT && d.cout_stride != d.cout)
+        return fail(OM_ERR_INVALID, "split precision needs a dense activation output (cout_stride == cout)");
     if (d.out_kind != OM_OUT_NCHW && (d.cout % 32 || d.cout_stride % 16 || d.cout_stride < d.cout))
         return fail(OM_ERR_INVALID, "fp16 engine needs cout %% 32 == 0 and an aligned channel pitch for NHWC outputs");
     if (d.upadd && (d.out_w % 2 || d.out_kind == OM_OUT_NCHW)) return fail(OM_ERR_INVALID, "upadd needs an even width and an NHWC output");
@@ -913,7 +970,7 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     {
         static bool hint_set = false;
         const char* wh = getenv("ORIENMASK_B200_WAIT_HINT");
-        if (!hint_set && wh) { tc2_set_wait_hint((unsigned int)atoi(wh)); }
+        if (!hint_set && wh && atoi(wh) >= 0 && atoi(wh) <= 1000000) { tc2_set_wait_hint((unsigned int)atoi(wh)); }
         hint_set = true;
     }
     Tc2Plan* plan = new Tc2Plan();
@@ -921,15 +978,16 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     Tc2Params& p = plan->p;
     const int bk = (d.cin % 64 == 0) ? 64 : 32;
     plan->bk = bk;
-    int cout_pad = (d.cout + 15) / 16 * 16;
-    if (cout_pad < 32) cout_pad = 32;
+    const int cout_pad = (d.cout + 31) / 32 * 32;       // a CTA pair splits the N tile in halves of a multiple of 16 rows
     int bn = cout_pad;
     int bn_cap = 256;
-    if (getenv("ORIENMASK_B200_BN") && d.out_w <= atoi(getenv("ORIENMASK_B200_BN_MAXW") ? getenv("ORIENMASK_B200_BN_MAXW") : "0"))
-        bn_cap = atoi(getenv("ORIENMASK_B200_BN"));        // experiment: narrower N tiles for the layers that quantise badly
+    if (getenv("ORIENMASK_B200_BN") && d.out_w <= atoi(getenv("ORIENMASK_B200_BN_MAXW") ? getenv("ORIENMASK_B200_BN_MAXW") : "0")) {
+        const int v = atoi(getenv("ORIENMASK_B200_BN"));   // experiment: narrower N tiles for the layers that quantise badly
+        if (v == 32 || v == 64 || v == 128 || v == 256) bn_cap = v;
+    }
     if (bn > bn_cap) {
         bn = bn_cap;
-        while (cout_pad % bn) bn -= 32;
+        while (bn > 32 && cout_pad % bn) bn -= 32;
     }
     if (bn % 32) { delete plan; return fail(OM_ERR_INVALID, "padded cout %d cannot be split over a CTA pair", cout_pad); }
     p.block_n = bn; p.half_n = bn / 2; p.cout_pad = cout_pad; p.tiles_n = cout_pad / bn;
@@ -956,7 +1014,7 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
         return fail(OM_ERR_INVALID, "this stride-2 layer needs in_rows == 2*out_rows (only im2col-gathered tiles are free of it)");
     }
     p.halo_s2 = d.ksize == 3 && d.stride == 2 && d.in_s2d && d.out_kind != OM_OUT_NCHW && (d.out_w % 8 == 0 || d.out_w >= 64) &&
-                !(halo_env && halo_env[0] == '0') && !getenv("ORIENMASK_B200_NO_HALO_S2");
+                !(halo_env && halo_env[0] == '0') && !getenv("ORIENMASK_B200_NO_HALO_S2") && !split;
     if (p.halo_s2) {
         // only where all weights stay resident next to two halo stages (the 32 -> 64 layer): with a weight ring the four plane
         // boxes leave too few stages and the layer gets slower than with per-tap boxes (64 -> 128 @136: 113 -> 165 us)
@@ -972,13 +1030,16 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     p.total_rows = d.batch * d.out_rows;
     const int tiles_y = p.flat ? (p.flat_total + kBlockM - 1) / kBlockM : (p.total_rows + p.th - 1) / p.th;
     p.pairs_y = (tiles_y + 1) / 2;
-    p.taps = d.ksize * d.ksize; p.stride = d.stride; p.k_chunks = d.cin / bk;
+    p.taps = d.ksize * d.ksize; p.stride = d.stride;
+    p.k_chunks = (split ? 3 : 1) * (d.cin / bk); p.a_chunks = (split ? 2 : 1) * (d.cin / bk); p.split_kr = split ? d.cin / bk : 0;
+    p.acc_scale = (split && d.acc_scale != 0.0f) ? d.acc_scale : 1.0f;
+    p.pix_stride = split ? 2 * d.cout_stride : d.cout_stride; p.lo_off = d.cout_stride;
     {
         // the fp16 residual: staged by TMA for the memory-bound layers (its DRAM latency must be covered several chunks ahead),
         // read by the epilogue threads themselves in flat mode and (experiment: ORIENMASK_B200_RESDIRECT=1) on tensor-bound tiles
         const char* rd = getenv("ORIENMASK_B200_RESDIRECT");
         const int cycles = d.ksize * d.ksize * (d.cin / bk) * (bk / 16) * (bn / 2);
-        const bool direct = p.flat || (rd && rd[0] == '1' && cycles >= 8192);
+        const bool direct = p.flat || split || (rd && rd[0] == '1' && cycles >= 8192);
         p.res_direct = (d.residual != nullptr && direct) ? 1 : 0;
         p.residual = d.residual;
         p.has_res = (d.residual != nullptr && !direct) ? 1 : 0;
@@ -994,9 +1055,12 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     p.halo_pitch = p.halo_s2 ? p.tw + 1 : p.tw + 2;
     p.a_box_pixels = p.halo_s2 ? (p.tw + 1) * (p.th + 1) : p.halo ? (p.tw + 2) * (p.th + 2) : p.tw * p.th;
     p.h_chunk_bytes = p.halo ? ((p.a_box_pixels * bk * 2 + 1023) / 1024) * 1024 : 0;
-    p.h_stage_bytes = p.h_chunk_bytes * p.k_chunks * p.halo_planes;
+    p.h_stage_bytes = p.h_chunk_bytes * p.a_chunks * p.halo_planes;
     p.h_stages = p.halo ? 2 : 0;
-    if (p.halo && getenv("ORIENMASK_B200_HSTAGES")) p.h_stages = atoi(getenv("ORIENMASK_B200_HSTAGES"));
+    if (p.halo && getenv("ORIENMASK_B200_HSTAGES")) {
+        const int v = atoi(getenv("ORIENMASK_B200_HSTAGES"));
+        if (v >= 2 && v <= 4) p.h_stages = v;
+    }
     // per-tap activation block: the tw*th-row box rounded up to the 1024-byte swizzle period (the MMA reads 128 rows; rows
     // beyond the box alias the following weight block and only feed accumulator rows the epilogue masks)
     p.a_sub_bytes = p.halo ? 0 : ((p.tw * p.th * bk * 2 + 1023) / 1024) * 1024;
@@ -1014,7 +1078,7 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     {
         const int total_b = p.taps * p.k_chunks * p.half_n * bk * 2;
         const char* br_env = getenv("ORIENMASK_B200_BRES");
-        p.b_resident = p.halo && p.tiles_n == 1 && total_b <= 96 * 1024 && !(br_env && br_env[0] == '0');
+        p.b_resident = p.halo && p.tiles_n == 1 && total_b <= 96 * 1024 && !(br_env && br_env[0] == '0') && !split;
         if (p.b_resident) {
             int hs = (kMaxSmem - fixed - total_b) / p.h_stage_bytes;
             p.h_stages = hs > 4 ? 4 : hs;
@@ -1030,14 +1094,14 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
         const int block_cycles = (bk / 16) * (bn / 2);
         const char* ns_env = getenv("ORIENMASK_B200_NSUB");
         int best = 1;
-        for (int n = 1; n <= total; ++n) {
+        for (int n = 1; n <= total && n <= 32; ++n) {     // lane j of the producer warp issues block j of a stage
             if (total % n) continue;
             const int st = ring_budget / (n * sub_bytes);
             if (st < 3 && n > 1 && !(n == total && st >= 2)) break;   // a whole tile per stage may run double-buffered
             best = n;
             if (n * block_cycles >= 1024) break;
         }
-        if (ns_env && atoi(ns_env) > 0 && total % atoi(ns_env) == 0 && ring_budget / (atoi(ns_env) * sub_bytes) >= 2) best = atoi(ns_env);
+        if (ns_env && atoi(ns_env) > 0 && atoi(ns_env) <= 32 && total % atoi(ns_env) == 0 && ring_budget / (atoi(ns_env) * sub_bytes) >= 2) best = atoi(ns_env);
         p.n_sub = best;
         p.stages = ring_budget / (best * sub_bytes);
         if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -1065,31 +1129,31 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     int32_t rc = OM_OK;
     const CUtensorMapDataType f16 = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (p.flat) {
-        rc = encode_im2col(&plan->maps.m[0], d.input, d.cin, d.cin, d.in_w, d.in_h, d.in_rows, d.batch, bk, d.ksize, d.stride, bk * 2);
+        rc = encode_im2col(&plan->maps.m[0], d.input, cin_mem, cin_mem, d.in_w, d.in_h, d.in_rows, d.batch, bk, d.ksize, d.stride, bk * 2);
         for (int i = 1; i < 4 && rc == OM_OK; ++i) plan->maps.m[i] = plan->maps.m[0];
     } else if (d.stride == 1) {
-        cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w, (cuuint64_t)d.batch * d.in_rows};
-        cuuint64_t str[2] = {(cuuint64_t)d.cin * esz, (cuuint64_t)d.in_w * d.cin * esz};
+        cuuint64_t dims[3] = {(cuuint64_t)cin_mem, (cuuint64_t)d.in_w, (cuuint64_t)d.batch * d.in_rows};
+        cuuint64_t str[2] = {(cuuint64_t)cin_mem * esz, (cuuint64_t)d.in_w * cin_mem * esz};
         cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(p.halo ? p.tw + 2 : p.tw), (cuuint32_t)(p.halo ? p.th + 2 : p.th)};
         rc = encode(&plan->maps.m[0], f16, d.input, 3, dims, str, box, bk * 2);
         for (int i = 1; i < 4 && rc == OM_OK; ++i) plan->maps.m[i] = plan->maps.m[0];
     } else {
         for (int sel = 0; sel < 4 && rc == OM_OK; ++sel) {          // sel = 2*odd_row + odd_col
             const int py = sel >> 1, px = sel & 1;
-            cuuint64_t dims[3] = {(cuuint64_t)d.cin, (cuuint64_t)d.in_w / 2, (cuuint64_t)d.batch * d.in_rows / 2};
-            cuuint64_t str[2] = {(cuuint64_t)2 * d.cin * esz, (cuuint64_t)2 * d.in_w * d.cin * esz};
+            cuuint64_t dims[3] = {(cuuint64_t)cin_mem, (cuuint64_t)d.in_w / 2, (cuuint64_t)d.batch * d.in_rows / 2};
+            cuuint64_t str[2] = {(cuuint64_t)2 * cin_mem * esz, (cuuint64_t)2 * d.in_w * cin_mem * esz};
             cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)(p.halo_s2 ? p.tw + 1 : p.tw), (cuuint32_t)(p.halo_s2 ? p.th + 1 : p.th)};
-            const char* base = reinterpret_cast<const char*>(d.input) + ((size_t)py * d.in_w + px) * d.cin * esz;
+            const char* base = reinterpret_cast<const char*>(d.input) + ((size_t)py * d.in_w + px) * cin_mem * esz;
             if (d.in_s2d) {                                   // dense parity planes: every tap is a contiguous box
-                str[0] = (cuuint64_t)d.cin * esz; str[1] = (cuuint64_t)(d.in_w / 2) * d.cin * esz;
-                base = reinterpret_cast<const char*>(d.input) + (size_t)sel * ((size_t)d.batch * d.in_rows / 2 * (d.in_w / 2)) * d.cin * esz;
+                str[0] = (cuuint64_t)cin_mem * esz; str[1] = (cuuint64_t)(d.in_w / 2) * cin_mem * esz;
+                base = reinterpret_cast<const char*>(d.input) + (size_t)sel * ((size_t)d.batch * d.in_rows / 2 * (d.in_w / 2)) * cin_mem * esz;
             }
             rc = encode(&plan->maps.m[sel], f16, base, 3, dims, str, box, bk * 2);
         }
     }
     if (rc == OM_OK) {
-        cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)p.taps * cout_pad};
-        cuuint64_t str[1] = {(cuuint64_t)d.cin * esz};
+        cuuint64_t dims[2] = {(cuuint64_t)cin_mem, (cuuint64_t)p.taps * cout_pad};
+        cuuint64_t str[1] = {(cuuint64_t)cin_mem * esz};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.half_n};
         rc = encode(&plan->map_b, f16, d.weights, 2, dims, str, box, bk * 2);
     }
@@ -1121,9 +1185,14 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
         delete plan;
         return fail(OM_ERR_INVALID, "plan out of budget: %zu bytes of shared memory, %d TMEM columns", need, cols);
     }
-    cudaError_t e = plan_dryrun() ? cudaSuccess : bk == 64
-        ? cudaFuncSetAttribute(conv_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
-        : cudaFuncSetAttribute(conv_tc2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    plan->split = split;
+    cudaError_t e = cudaSuccess;
+    if (!plan_dryrun()) {
+        if (split) e = bk == 64 ? cudaFuncSetAttribute(conv_tc2_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
+                                : cudaFuncSetAttribute(conv_tc2_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+        else e = bk == 64 ? cudaFuncSetAttribute(conv_tc2_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem)
+                          : cudaFuncSetAttribute(conv_tc2_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    }
     if (e != cudaSuccess) { delete plan; return fail(OM_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); }
     *out = plan;
     return OM_OK;
@@ -1150,10 +1219,15 @@ int32_t tc2_plan_run(const void* vp, cudaStream_t stream, void* output) {
         if (p.has_res || p.res_direct) return fail(OM_ERR_INVALID, "om_conv_run_to: layers with a residual write in place");
         p.output = output;
     }
-    if (plan->bk == 64)
-        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<64>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, p));
+    if (plan->split) {
+        if (plan->bk == 64)
+            OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<64, true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, p));
+        else
+            OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<32, true>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, p));
+    } else if (plan->bk == 64)
+        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<64, false>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, p));
     else
-        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<32>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, p));
+        OM_CUDA_TRY(launch_pdl(conv_tc2_kernel<32, false>, dim3(plan->grid), dim3(kThreads), plan->smem, stream, plan->maps, plan->map_b, plan->map_res, p));
     return check_launch("conv_tc2_kernel");
 }
 

@@ -280,11 +280,8 @@ extern "C" int32_t om_mask_rle(const om_rle_image* images, int32_t batch, int32_
     const size_t change_off = ((size_t)max_out_h * 16 + (size_t)((max_mask_w + 15) & ~15) + (size_t)max_mask_h + 15) & ~(size_t)15;
     const size_t smem = change_off + (size_t)((max_out_h + 31) / 32) * kThreads * 4;
     if (smem > 200 * 1024) return om::fail(OM_ERR_UNSUPPORTED, "om_mask_rle: sizes need %zu bytes of shared memory per CTA (max 204800)", smem);
-    static bool attr_set = false;
-    if (smem > 48 * 1024 && !attr_set) {
+    if (smem > 48 * 1024)        // per device (a process may drive several GPUs): set on every call that needs it, like allow_smem() in post.cu
         OM_CUDA_TRY(cudaFuncSetAttribute(mask_rle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_set = true;
-    }
     mask_rle_kernel<<<dim3((unsigned)max_inst, (unsigned)batch), kThreads, smem, (cudaStream_t)stream>>>(
         images, max_inst, cap, str_cap, (int)change_off, counts, n_counts, str, str_len);
     return om::check_launch("mask_rle_kernel");

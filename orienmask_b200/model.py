@@ -41,13 +41,21 @@ def _holder(root, dotted):
     return mod
 
 
+def _invalidate_after_load(module, incompatible_keys):
+    """load_state_dict post-hook (also fires when a PARENT module loads: PyTorch recurses through _load_from_state_dict and never calls
+    this module's own load_state_dict override)."""
+    module._invalidate()
+
+
 class OrienMaskYOLOFPNPlus(nn.Module):
     _plus = True          # False in OrienMaskYOLO: no skip convolutions, neck4 reads cat[up2(route8(neck8)), x4]
 
     def __init__(self, num_anchors, num_classes, pretrained=None, freeze_backbone=False, backbone_batchnorm_eval=False):
         super().__init__()
         self.num_anchors, self.num_classes = num_anchors, num_classes
-        self.precision = os.environ.get('ORIENMASK_B200_PRECISION', 'fp16')     # 'fp16' (tcgen05) | 'fp32' (parity)
+        # 'fp16' (tcgen05, production) | 'parity' (tcgen05 on fp16 hi + lo pairs, three MMAs per product: fp32-grade results on the
+        # tensor cores) | 'fp32' (FFMA on the CUDA cores, the bring-up reference of both)
+        self.precision = os.environ.get('ORIENMASK_B200_PRECISION', 'fp16')
         # replay the forward's ~95 launches as one CUDA graph (small-batch latency; outputs are overwritten by the next call)
         self.use_cuda_graph = os.environ.get('ORIENMASK_B200_GRAPH', '0') == '1'
         self._specs = conv_specs(num_anchors, num_classes, self._plus)
@@ -76,6 +84,11 @@ class OrienMaskYOLOFPNPlus(nn.Module):
         self.max_engines = max(1, int(os.environ.get('ORIENMASK_B200_MAX_ENGINES', '4')))
         self._engines = {}
         self._weights_version = 0
+        self._fingerprint = None
+        # Every forward compares a fingerprint of the live parameters / buffers with the one the packed weights were built from
+        # (see _weights_fingerprint); set to False to skip the ~0.1 ms host check when the weights are known to be frozen.
+        self.check_weights = True
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
         if pretrained is not None:
             # model/base.py:48-64: a *backbone* checkpoint (keys relative to DarkNet53: 'conv1.conv_block.0.weight', ...);
             # every key the backbone has with the same shape is taken, the others are reported and ignored
@@ -104,6 +117,20 @@ class OrienMaskYOLOFPNPlus(nn.Module):
     def _invalidate(self):
         self._engines = {}
         self._weights_version += 1
+        self._fingerprint = None
+
+    def invalidate(self):
+        """Drop the folded / packed weights: the next forward rebuilds them from the live parameters.  Needed only after an
+        update the fingerprint cannot see (``p.data.copy_(...)``: a write through a detached alias bumps no version counter)."""
+        self._invalidate()
+
+    def _weights_fingerprint(self):
+        """(version counter, storage address) of every parameter and buffer: changes on in-place updates of the tensors
+        (optimizer steps, ``p.copy_``, a parent module's ``load_state_dict`` -- which never calls this module's override),
+        on ``p.data = ...`` swaps and on device / dtype moves.  The reference always runs on the live parameters; the engine's
+        packed copies are rebuilt whenever this differs from the fingerprint they were built from."""
+        tensors = list(self.parameters()) + list(self.buffers())
+        return tuple(t._version for t in tensors) + tuple(t.data_ptr() for t in tensors)
 
     def __getstate__(self):
         # copy.deepcopy / pickle (torch.save of the whole module) take the parameters, never the buffer plans: those hold
@@ -117,6 +144,18 @@ class OrienMaskYOLOFPNPlus(nn.Module):
             raise RuntimeError('orienmask_b200 runs on CUDA (sm_100a) only; got a %s tensor and there is no CPU fallback' % x.device)
         if x.dim() != 4 or x.size(1) != 3 or x.size(2) % 32 or x.size(3) % 32:
             raise ValueError('expected [B,3,H,W] with H, W multiples of 32, got %s' % (tuple(x.shape),))
+        if self.training and not getattr(self, '_warned_training', False):
+            import warnings
+            warnings.warn('orienmask_b200 is an inference engine: BatchNorm uses running statistics even in train() mode '
+                          '(the reference would use batch statistics); call .eval()')
+            self._warned_training = True
+        if self.check_weights:
+            fp = self._weights_fingerprint()
+            if fp != self._fingerprint:
+                if self._fingerprint is not None:
+                    self._engines = {}
+                    self._weights_version += 1
+                self._fingerprint = fp
         eng = self._engine_for((int(x.size(0)), int(x.size(2)), int(x.size(3)), self.precision, x.device.index), x.device)
         return eng.run_graph(x) if self.use_cuda_graph else eng.run(x)
 
@@ -140,12 +179,13 @@ class _Engine:
     """Static buffer plan + launch schedule for one (batch, H, W, precision)."""
 
     def __init__(self, model, B, H, W, precision, device):
-        if precision not in ('fp16', 'fp32'):
-            raise ValueError("precision must be 'fp16' or 'fp32'")
+        if precision not in ('fp16', 'fp32', 'parity'):
+            raise ValueError("precision must be 'fp16', 'parity' or 'fp32'")
         self.lib = _lib.lib()
         self.B, self.H, self.W, self.device = B, H, W, device
-        self.prec = _lib.PREC_F16 if precision == 'fp16' else _lib.PREC_F32
-        self.adt = torch.float16 if precision == 'fp16' else torch.float32
+        self.prec = {'fp16': _lib.PREC_F16, 'fp32': _lib.PREC_F32, 'parity': _lib.PREC_SPLIT}[precision]
+        self.adt = torch.float32 if precision == 'fp32' else torch.float16
+        self.cmul = 2 if precision == 'parity' else 1         # halves per activation value (split precision: hi | lo)
         self.nA, self.nC = model.num_anchors, model.num_classes
         self.plus = model._plus
         self.sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in model.state_dict().items()
@@ -174,7 +214,8 @@ class _Engine:
 
     def act(self, stride, channels, dtype=None, s2d=False):
         """Padded-row NHWC buffer; s2d=True marks it parity-split (same size: four [B*rows/2, W/2, C] planes)."""
-        t = torch.zeros(self.B * self.rows(stride), self.W // stride, channels, dtype=dtype or self.adt, device=self.device)
+        t = torch.zeros(self.B * self.rows(stride), self.W // stride, channels * (self.cmul if dtype is None else 1),
+                        dtype=dtype or self.adt, device=self.device)
         self.keep.append(t)
         return dict(t=t, stride=stride, c=channels, s2d=s2d)
 
@@ -190,18 +231,10 @@ class _Engine:
         return sd[prefix + '.weight'], sd[prefix + '.bias']
 
     def pack(self, w):
-        """[cout, cin, k, k] fp32 -> engine layout (see om_conv_desc.weights)."""
-        cout, cin, k, _ = w.shape
-        if self.prec == _lib.PREC_F16:
-            cpad = max(32, (cout + 15) // 16 * 16)
-            p = torch.zeros(k * k, cpad, cin, dtype=torch.float16, device=self.device)
-            p[:, :cout] = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).to(torch.float16)
-        else:
-            cpad = (cout + 3) // 4 * 4
-            p = torch.zeros(k * k, cin, cpad, dtype=torch.float32, device=self.device)
-            p[:, :, :cout] = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout)
+        """[cout, cin, k, k] fp32 -> (engine layout, accumulator scale); see _lib.pack_conv_weights / om_conv_desc.weights."""
+        p, acc_scale = _lib.pack_conv_weights(w.to(self.device), self.prec)
         self.keep.append(p)
-        return p
+        return p, acc_scale
 
     # ---- op emission -----------------------------------------------------------------------------
     def conv(self, src, w, bias, dst, k, stride=1, leaky=True, kind=_lib.OUT_ACT, residual=None, upadd=None, nchw=None, name=None):
@@ -217,7 +250,8 @@ class _Engine:
         d.out_s2d = int(bool(dst is not None and dst.get('s2d')))
         assert not d.in_s2d or stride == 2, 'only a stride-2 layer can read a parity-split buffer'
         d.input = src['t'].data_ptr()
-        d.weights = self.pack(w).data_ptr()
+        wp, d.acc_scale = self.pack(w)
+        d.weights = wp.data_ptr()
         if bias is not None:
             b = bias.contiguous().clone()
             self.keep.append(b)
@@ -240,7 +274,7 @@ class _Engine:
         self.plans.append(('conv', handle))
         flops = 2 * d.batch * d.out_h * d.out_w * d.cout * d.cin * k * k
         self.flops += flops
-        esz = 2 if self.prec == _lib.PREC_F16 else 4
+        esz = 2 if self.prec == _lib.PREC_F16 else 4           # split precision: two halves per value
         nbytes = d.batch * d.in_h * d.in_w * d.cin * esz + w.numel() * esz
         nbytes += d.batch * d.out_h * d.out_w * d.cout * (esz if kind == _lib.OUT_ACT else 4)
         if residual is not None:

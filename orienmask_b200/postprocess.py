@@ -25,13 +25,23 @@ class PaddedDetections:
     def __init__(self, det, cls, anchor, keep, count, mask):
         self.det, self.cls, self.anchor, self.keep, self.count, self.mask = det, cls, anchor, keep, count, mask
         self.packed = None
+        self.count_host = None      # pinned copy of `count`, enqueued right after the NMS kernel (before the mask kernel)
+        self.nms_done = None        # event recorded at that point: counts and records are final, the masks are still being written
 
     def records(self):
         """[B, nms_post, 6] fp32 (cx, cy, w, h, score, cls) -- the unit the multi-GPU gather moves."""
         return torch.cat([self.det, self.cls.to(torch.float32).unsqueeze(-1)], dim=-1)
 
     def to_list(self):
-        counts = self.count.tolist()                      # the one host sync of the post-process
+        """The reference's return value (eval/orienmask_yolo_postprocess.py:124,166): per image a dict of tensors trimmed to its K
+        detections.  K has to reach the host -- the one synchronisation of the post-process -- but only the NMS kernel has to have
+        finished for it: the mask kernel (most of the post-process time) keeps running while the host slices, and the returned
+        mask tensors are ordinary stream-ordered results."""
+        if self.nms_done is not None:
+            self.nms_done.synchronize()
+            counts = self.count_host.tolist()
+        else:
+            counts = self.count.tolist()
         out = []
         for b, k in enumerate(counts):
             out.append({'bbox': self.det[b, :k], 'mask': self.mask[b, :k].view(torch.bool), 'cls': self.cls[b, :k]})
@@ -144,11 +154,16 @@ class OrienMaskYOLOPostProcess:
             _lib.check(lib.om_batched_nms(ctypes.byref(cfg), _lib.ptr(cand_count), _lib.ptr(cand_det), _lib.ptr(cand_cls),
                                           _lib.ptr(cand_pred), B, _lib.ptr(det_count), _lib.ptr(det), _lib.ptr(det_cls),
                                           _lib.ptr(det_anchor), _lib.ptr(det_keep), _lib.ptr(packed), stream), 'om_batched_nms')
+            count_host = torch.empty(B, dtype=torch.int32, pin_memory=True)
+            count_host.copy_(det_count, non_blocking=True)
+            nms_done = torch.cuda.Event()
+            nms_done.record()
             mask = torch.empty(B, self.nms_post, self.image_h, self.image_w, dtype=torch.uint8, device=dev)
             _lib.check(lib.om_mask_assemble(ctypes.byref(cfg), or_ptr, or_str, _lib.ptr(det_count), _lib.ptr(det),
                                             _lib.ptr(det_anchor), B, _lib.ptr(mask), stream), 'om_mask_assemble')
         out = PaddedDetections(det, det_cls, det_anchor, det_keep, det_count, mask)
         out.packed = packed          # [B, nms_post*6+1] rows written by the NMS kernel: what sharding.gather_detections moves
+        out.count_host, out.nms_done = count_host, nms_done
         out.candidates = dict(count=cand_count, det=cand_det, cls=cand_cls, pred=cand_pred)
         out._keepalive = (bboxes, oriens, ws)
         return out

@@ -39,8 +39,22 @@ def unpack_records(packed, K):
     return rec[..., :5].contiguous(), rec[..., 5].to(torch.int64), packed[:, K * 6].to(torch.int32)
 
 
-def gather_detections(det, cls, count, group=None, packed=None, total=None):
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
+
+
+def gather_detections(det, cls, count, group=None, packed=None, total=None, ready=None):
     """All-gather the padded detection records of every rank.
+
+    ``ready``: a CUDA event recorded when the records are final (``PaddedDetections.nms_done``: after the NMS kernel, before the
+    mask kernel).  When given, the collective is issued on a side stream that waits for that event only, so it runs under the mask
+    kernel instead of behind it on the compute stream; the compute stream joins the side stream before the result is unpacked.
 
     ``packed``: the [B_local, K*6+1] record rows the NMS kernel wrote (``PaddedDetections.packed``); when given, that buffer
     is the collective's source and nothing is re-packed.
@@ -64,8 +78,22 @@ def gather_detections(det, cls, count, group=None, packed=None, total=None):
         rows = max(sizes)
         if packed.shape[0] < rows:
             packed = torch.cat([packed, packed.new_zeros(rows - packed.shape[0], packed.shape[1])], dim=0)
-    out = torch.empty(world * rows, packed.shape[1], dtype=packed.dtype, device=packed.device)
-    dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
+    packed = packed.contiguous()
+    if ready is not None and packed.is_cuda:
+        cur = torch.cuda.current_stream(packed.device)
+        side = _side_stream(packed.device)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            out = torch.empty(world * rows, packed.shape[1], dtype=packed.dtype, device=packed.device)
+            dist.all_gather_into_tensor(out, packed, group=group)
+            done = torch.cuda.Event()
+            done.record(side)
+        packed.record_stream(side)
+        out.record_stream(cur)
+        cur.wait_event(done)
+    else:
+        out = torch.empty(world * rows, packed.shape[1], dtype=packed.dtype, device=packed.device)
+        dist.all_gather_into_tensor(out, packed, group=group)
     if total is not None and min(sizes) != rows:
         out = torch.cat([out[r * rows:r * rows + n] for r, n in enumerate(sizes)], dim=0)
     return unpack_records(out, K)

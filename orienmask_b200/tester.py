@@ -13,6 +13,7 @@ import os
 import torch
 
 from .coco_format import COCOMetrics
+from .visualizer import COCO_CAT_IDS      # the real COCO category ids (1..90 with gaps), data/dataset.py:42-49
 
 
 class Tester:
@@ -24,7 +25,7 @@ class Tester:
         self.device = torch.device(device)
         self.gt_file = gt_file
         dataset = getattr(test_loader, 'dataset', None)
-        self.coco_metrics = COCOMetrics(gt_file=gt_file, cat2label=getattr(dataset, 'CAT2LABEL', list(range(1, 81))),
+        self.coco_metrics = COCOMetrics(gt_file=gt_file, cat2label=getattr(dataset, 'CAT2LABEL', None) or list(COCO_CAT_IDS),
                                         with_mask=getattr(dataset, 'with_mask', True), save_dir=checkpoint_dir)
         self.timings = {}
 

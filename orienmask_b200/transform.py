@@ -111,9 +111,12 @@ class FastCOCOTransform:
         return self._run(image, size_divisor, pad_value, out)
 
     def _run(self, image, size_divisor, pad_value, out=None):
-        if not isinstance(image, torch.Tensor) or not image.is_cuda:
-            raise RuntimeError('orienmask_b200.FastCOCOTransform needs a CUDA tensor, got %s; there is no CPU path'
-                               % getattr(image, 'device', type(image)))
+        if not isinstance(image, torch.Tensor):
+            raise RuntimeError('orienmask_b200.FastCOCOTransform needs a torch tensor, got %s' % type(image))
+        if not image.is_cuda:
+            # data/transform.py:456-457: the reference moves the image to its device (cuda:0) first; so does this (the work itself
+            # has no CPU path -- without a CUDA device this raises)
+            image = image.to('cuda:0')
         if image.dim() != 4 or image.shape[-1] != 3:
             raise ValueError('expected [n, h, w, 3], got %s' % (tuple(image.shape),))
         if image.dtype == torch.uint8:

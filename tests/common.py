@@ -58,16 +58,19 @@ def from_padded(t, B, H):
 
 def pack_weights(w, precision):
     from orienmask_b200 import _lib
-    cout, cin, k, _ = w.shape
-    if precision == _lib.PREC_F16:
-        cpad = max(32, (cout + 15) // 16 * 16)
-        p = torch.zeros(k * k, cpad, cin, dtype=torch.float16, device=w.device)
-        p[:, :cout] = w.permute(2, 3, 0, 1).reshape(k * k, cout, cin).half()
-    else:
-        cpad = (cout + 3) // 4 * 4
-        p = torch.zeros(k * k, cin, cpad, dtype=torch.float32, device=w.device)
-        p[:, :, :cout] = w.permute(2, 3, 1, 0).reshape(k * k, cin, cout)
-    return p
+    return _lib.pack_conv_weights(w, precision)
+
+
+def split_halves(t):
+    """fp32 [..., C] -> fp16 [..., 2C]: hi | lo along the last axis (OM_PREC_SPLIT activations)."""
+    hi = t.to(torch.float16)
+    lo = (t.float() - hi.float()).to(torch.float16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def merge_halves(t):
+    c = t.shape[-1] // 2
+    return t[..., :c].float() + t[..., c:].float()
 
 
 def to_s2d(t):
@@ -95,17 +98,19 @@ def run_engine_conv(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upa
     Ho, Wo = H // stride, W // stride
     rows_o = Ho + extra_rows
     rows_i = rows_o * stride
-    adt = torch.float16 if precision == _lib.PREC_F16 else torch.float32
-    xin = to_padded(x, rows_i, adt)
+    split = precision == _lib.PREC_SPLIT
+    adt = torch.float32 if precision == _lib.PREC_F32 else torch.float16
+    xin = split_halves(to_padded(x, rows_i, torch.float32)) if split else to_padded(x, rows_i, adt)
     if in_s2d:
         xin = to_s2d(xin)
-    wp = pack_weights(w, precision)
+    wp, acc_scale = pack_weights(w, precision)
     d = _lib.ConvDesc()
     d.precision, d.batch = precision, B
     d.in_h, d.in_w, d.in_rows, d.out_h, d.out_w, d.out_rows = H, W, rows_i, Ho, Wo, rows_o
     d.cin, d.cout, d.cout_stride, d.ksize, d.stride, d.leaky, d.out_kind = cin, cout, cout, k, stride, int(leaky), kind
     d.input, d.weights = xin.data_ptr(), wp.data_ptr()
     d.in_s2d, d.out_s2d = int(in_s2d), int(out_s2d)
+    d.acc_scale = acc_scale
     keep = [xin, wp]
     if bias is not None:
         b = bias.float().contiguous()
@@ -116,10 +121,10 @@ def run_engine_conv(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upa
     elif kind == _lib.OUT_PARTIAL:
         out = torch.zeros(B * rows_o, Wo, cout, dtype=torch.float32, device=x.device)
     else:
-        out = torch.zeros(B * rows_o, Wo, cout, dtype=adt, device=x.device)
+        out = torch.zeros(B * rows_o, Wo, cout * (2 if split else 1), dtype=adt, device=x.device)
     d.output = out.data_ptr()
     if residual is not None:
-        r = to_padded(residual, rows_o, adt)
+        r = split_halves(to_padded(residual, rows_o, torch.float32)) if split else to_padded(residual, rows_o, adt)
         keep.append(r)
         d.residual = r.data_ptr()
     if upadd is not None:
@@ -138,6 +143,8 @@ def run_engine_conv(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upa
         return out
     if out_s2d:
         out = from_s2d(out)
+    if split and kind == _lib.OUT_ACT:
+        out = merge_halves(out)
     pad = out.view(B, rows_o, Wo, cout)[:, Ho:]
     assert float(pad.abs().max()) == 0.0, 'padding rows were written'
     return from_padded(out, B, Ho)
@@ -160,6 +167,92 @@ def torch_conv_ref(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upad
     if residual is not None:
         y = y + residual.double()
     return y.float()
+
+
+# ---- end-to-end agreement with explicit exceptions (SURVEY §8d iii) -------------------------------
+def _iou_centre(a, b):
+    """IoU of centre-format boxes a [4], b [n,4] (float64; only used to measure margins)."""
+    ax1, ay1, ax2, ay2 = a[0] - a[2] / 2, a[1] - a[3] / 2, a[0] + a[2] / 2, a[1] + a[3] / 2
+    bx1, by1, bx2, by2 = b[:, 0] - b[:, 2] / 2, b[:, 1] - b[:, 3] / 2, b[:, 0] + b[:, 2] / 2, b[:, 1] + b[:, 3] / 2
+    iw = np.clip(np.minimum(ax2, bx2) - np.maximum(ax1, bx1), 0, None)
+    ih = np.clip(np.minimum(ay2, by2) - np.maximum(ay1, by1), 0, None)
+    inter = iw * ih
+    return inter / (a[2] * a[3] + b[:, 2] * b[:, 3] - inter)
+
+
+def e2e_agreement(ref, padded, b, nms_pre=400, nms_post=100, nms_thr=0.5, score_noise=1e-3, iou_noise=5e-3):
+    """Detections of image `b` of an engine result (PaddedDetections) against the oracle's result `ref` for the same image
+    (PostProcessOracle.image: forward oracle heads -> post-process oracle), matched by (prediction index, class).
+
+    Returns a report: matched pairs with their worst box / score error and mask IoU, and the list of EXCEPTIONS -- (prediction,
+    class) pairs kept by only one side -- each with the margin that explains it, measured on the oracle's own scores and boxes:
+    the distance of its score to the pre-NMS top-k cut, to the post-NMS top-k cut, or of the deciding NMS pair's IoU to the
+    threshold (directly, or through another exception of the same class it overlaps: a cascade).  An exception whose margins all
+    exceed the forward noise (`score_noise`, `iou_noise`) is `explained: False` -- a real disagreement."""
+    k = int(padded.count[b].item())
+    keep = padded.keep[b, :k].long()
+    g_pred = padded.candidates['pred'][b].long()[keep].cpu().numpy()
+    g_cls = padded.cls[b, :k].cpu().numpy()
+    g_box = padded.det[b, :k].cpu().numpy()
+    g_mask = padded.mask[b, :k].cpu().numpy().astype(bool)
+    r_key = {(int(p), int(c)): i for i, (p, c) in enumerate(zip(ref['pred'], ref['cls']))}
+    g_key = {(int(p), int(c)): i for i, (p, c) in enumerate(zip(g_pred, g_cls))}
+    rep = {'reference_detections': len(r_key), 'engine_detections': len(g_key), 'matched': 0, 'max_box_err': 0.0, 'max_score_err': 0.0,
+           'min_mask_iou': 1.0, 'mean_mask_iou': 1.0, 'masks_below_0p999': 0, 'exceptions': []}
+    ious = []
+    for key, gi in g_key.items():
+        ri = r_key.get(key)
+        if ri is None:
+            continue
+        rep['matched'] += 1
+        rep['max_box_err'] = max(rep['max_box_err'], float(np.abs(ref['bbox'][ri, :4] - g_box[gi, :4]).max()))
+        rep['max_score_err'] = max(rep['max_score_err'], float(abs(ref['bbox'][ri, 4] - g_box[gi, 4])))
+        u = (ref['mask'][ri] | g_mask[gi]).sum()
+        ious.append(float((ref['mask'][ri] & g_mask[gi]).sum() / u) if u else 1.0)
+    if ious:
+        rep['min_mask_iou'], rep['mean_mask_iou'] = min(ious), float(np.mean(ious))
+        rep['masks_below_0p999'] = int(sum(i < 0.999 for i in ious))
+    # ---- exceptions and their margins (oracle-side quantities only) ----
+    cand = ref['cand']
+    conf, coord_all = ref['conf'], ref['coord_all']
+    C = conf.shape[1]
+    cut_pre = float(cand['score'].min()) if len(cand['score']) >= nms_pre else None          # score of the last candidate taken
+    kept_scores = np.sort(ref['bbox'][:, 4])[::-1]
+    cut_post = float(kept_scores[nms_post - 1]) if len(kept_scores) >= nms_post else None
+    only = [(key, 'reference') for key in r_key if key not in g_key] + [(key, 'engine') for key in g_key if key not in r_key]
+    rows = []
+    for (pred, cls), side in only:
+        score = float(conf[pred, cls])
+        box = coord_all[pred].astype(np.float64)
+        margins = {}
+        if cut_pre is not None:
+            margins['score_to_pre_nms_cut'] = abs(score - cut_pre)
+        if cut_post is not None:
+            margins['score_to_post_nms_cut'] = abs(score - cut_post)
+        same = (cand['cls'] == cls) & (cand['score'] > score - score_noise) & (cand['pred'] != pred)
+        if same.any():
+            iou = _iou_centre(box, cand['coord'][same].astype(np.float64))
+            margins['nms_iou_to_threshold'] = float(np.abs(iou - nms_thr).min())
+        rows.append({'pred': int(pred), 'cls': int(cls), 'kept_by': side, 'oracle_score': score, 'margins': margins, 'box': box})
+    for r in rows:
+        m = r['margins']
+        direct = (m.get('score_to_pre_nms_cut', 1.0) < score_noise or m.get('score_to_post_nms_cut', 1.0) < score_noise
+                  or m.get('nms_iou_to_threshold', 1.0) < iou_noise)
+        cascade = False
+        if not direct:                    # kept / dropped because another exception of its class flipped
+            for o in rows:
+                if o is not r and o['cls'] == r['cls'] and _iou_centre(r['box'], o['box'][None])[0] >= nms_thr - iou_noise:
+                    cascade = True
+        # a post-NMS top-k cut moves whenever any other exception enters or leaves the kept set
+        if not direct and not cascade and cut_post is not None and len(rows) > 1 and abs(r['oracle_score'] - cut_post) < 10 * score_noise:
+            cascade = True
+        r['explained'] = bool(direct or cascade)
+        r['how'] = 'direct' if direct else 'cascade' if cascade else 'UNEXPLAINED'
+    for r in rows:
+        r.pop('box')
+    rep['exceptions'] = rows
+    rep['unexplained'] = int(sum(not r['explained'] for r in rows))
+    return rep
 
 
 # ---- detections -> COCO format fixtures -----------------------------------------------------------

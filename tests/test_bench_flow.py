@@ -109,7 +109,7 @@ def install_stand_ins(monkeypatch):
 
         def apply_padded(self, heads):
             out = types.SimpleNamespace(det=torch.zeros(B, K, 5), cls=torch.zeros(B, K, dtype=torch.int64),
-                                        count=torch.full((B,), 3, dtype=torch.int32), packed=torch.zeros(B, K * 6 + 1))
+                                        count=torch.full((B,), 3, dtype=torch.int32), packed=torch.zeros(B, K * 6 + 1), nms_done=None)
             out.packed[:, -1] = 3.0
             out.to_list = lambda: [{'bbox': torch.zeros(3, 5), 'mask': torch.zeros(3, bench.H, bench.W, dtype=torch.bool),
                                     'cls': torch.zeros(3, dtype=torch.int64)} for _ in range(B)]

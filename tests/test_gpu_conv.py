@@ -6,7 +6,7 @@ from tests.common import run_engine_conv, torch_conv_ref
 
 pytestmark = pytest.mark.gpu
 
-F32, F16 = 0, 1
+F32, F16, SPLIT = 0, 1, 2
 ACT, PARTIAL, NCHW = 0, 1, 2
 
 # (B, cin, cout, H, W, k, stride, kind, residual, upadd)
@@ -73,6 +73,44 @@ def test_tcgen05_engine(case):
     assert torch.allclose(got, ref, atol=tol, rtol=4e-3), err
 
 
+def _split_check(got, ref):
+    """fp32-grade: every product is carried by fp16 hi + lo pairs (~22 bits) and accumulated in fp32 on the tensor cores."""
+    err = float((got - ref).abs().max())
+    rel = float((got - ref).norm() / ref.norm())
+    assert torch.allclose(got, ref, atol=2e-4, rtol=1e-4) and rel < 1e-5, (err, rel)
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_split_precision_engine(case):
+    """OM_PREC_SPLIT (the tensor-core parity mode) against fp64 torch on the UNROUNDED fp32 operands, at the fp32 engine's tolerance."""
+    B, cin, cout, H, W, k, stride, kind, _, _ = case
+    x, w, b, res, up = _data(case)
+    leaky = kind == ACT
+    got = run_engine_conv(x, w, b, stride, leaky, kind, res, up, precision=SPLIT)
+    _split_check(got, torch_conv_ref(x, w, b, stride, leaky, kind, res, up))
+
+
+def test_split_precision_weight_scale_and_small_values():
+    """Weights far below fp16's normal range (1e-6) and activations spanning 1e-3 .. 1e3: the power-of-two weight scale keeps W_lo
+    normal, and the hi + lo activation pair keeps small values next to large ones."""
+    g = torch.Generator().manual_seed(21)
+    x = (torch.randn(2, 64, 17, 17, generator=g) * torch.logspace(-3, 3, 64).view(1, 64, 1, 1)).cuda()
+    w = (torch.randn(128, 64, 3, 3, generator=g) * 1e-6).cuda()
+    b = (torch.randn(128, generator=g) * 1e-4).cuda()
+    got = run_engine_conv(x, w, b, 1, True, ACT, precision=SPLIT)
+    ref = torch_conv_ref(x, w, b, 1, True, ACT)
+    assert float((got - ref).norm() / ref.norm()) < 1e-5
+
+
+@pytest.mark.parametrize('case', [c for c in CASES if c[9]] + [(2, 128, 128, 24, 16, 1, 1, ACT, False, True), (1, 64, 256, 14, 34, 1, 1, PARTIAL, False, True)])
+def test_split_precision_upadd_staged_by_tma(case):
+    B, cin, cout, H, W, k, stride, kind, _, _ = case
+    x, w, b, res, up = _data(case, seed=3)
+    leaky = kind == ACT
+    got = run_engine_conv(x, w, b, stride, leaky, kind, res, up, precision=SPLIT, extra_rows=2)
+    _split_check(got, torch_conv_ref(x, w, b, stride, leaky, kind, res, up))
+
+
 @pytest.mark.parametrize('case', [c for c in CASES if c[9]] + [(2, 128, 128, 24, 16, 1, 1, ACT, False, True), (1, 64, 256, 14, 34, 1, 1, PARTIAL, False, True)])
 def test_tcgen05_engine_upadd_staged_by_tma(case):
     """rows_per_image(out) == 2 * rows_per_image(partial): the up-add source tile is staged by TMA (model geometry)."""
@@ -85,7 +123,20 @@ def test_tcgen05_engine_upadd_staged_by_tma(case):
     assert torch.allclose(got, ref, atol=tol, rtol=4e-3), float((got - ref).abs().max())
 
 
-@pytest.mark.parametrize('precision', [F32, F16])
+@pytest.mark.parametrize('cout', [75, 18, 255])
+def test_head_channel_counts_pad_to_32(cout):
+    """NCHW heads of any width: 20 classes -> 3 * 25 = 75 channels -> an N = 96 pair tile (48 weight rows per CTA)."""
+    g = torch.Generator().manual_seed(cout)
+    x = torch.randn(2, 256, 12, 20, generator=g).cuda()
+    w = (torch.randn(cout, 256, 1, 1, generator=g) / 16).cuda()
+    b = torch.randn(cout, generator=g).cuda()
+    for prec, quant in ((F16, True), (SPLIT, False)):
+        got = run_engine_conv(x, w, b, 1, False, NCHW, precision=prec)
+        ref = torch_conv_ref(x, w, b, 1, False, NCHW, quantize=quant)
+        assert torch.allclose(got, ref, atol=2e-3 if quant else 2e-4, rtol=4e-3 if quant else 1e-4), (prec, float((got - ref).abs().max()))
+
+
+@pytest.mark.parametrize('precision', [F32, F16, SPLIT])
 def test_parity_split_layouts(precision):
     """in_s2d (stride-2 layer reading a parity-split input) and out_s2d (layer writing one), both engines."""
     g = torch.Generator().manual_seed(11)

@@ -36,6 +36,19 @@ def test_forward_fp32_small_golden():
         assert np.abs(orien.cpu().numpy() - g['orien_%d' % i]).max() < 5e-4
 
 
+def test_forward_parity_small_golden():
+    """The tensor-core parity mode (fp16 hi + lo pairs, three MMAs per product) against the same reference heads, at the fp32
+    engine's tolerance (SURVEY §8d staged protocol (i): inside the reference's own reorder noise)."""
+    from orienmask_b200.synthetic import synthetic_images
+    g = np.load(GOLDEN + '/small_fwd_post.npz')
+    out = _model('parity')(synthetic_images(2, 64, 96, seed=1).cuda())
+    for i, (bbox, orien) in enumerate(out):
+        assert bbox.dtype == torch.float32 and orien.dtype == torch.float32
+        for got, ref in ((bbox, g['bbox_%d' % i]), (orien, g['orien_%d' % i])):
+            got = got.cpu().numpy()
+            assert np.abs(got - ref).max() < 5e-4 and np.linalg.norm(got - ref) / np.linalg.norm(ref) < 5e-5
+
+
 def test_forward_fp16_small_drift():
     from orienmask_b200.synthetic import synthetic_images
     g = np.load(GOLDEN + '/small_fwd_post.npz')
@@ -51,7 +64,7 @@ def test_forward_544_probe_both_engines():
     from orienmask_b200.synthetic import synthetic_images
     g = np.load(GOLDEN + '/fwd_544_probe.npz')
     x = synthetic_images(1, 544, 544, seed=1).cuda()
-    for prec, tol in (('fp32', 1e-3), ('fp16', None)):
+    for prec, tol in (('fp32', 1e-3), ('parity', 1e-3), ('fp16', None)):
         out = _model(prec)(x)
         for i, (bbox, orien) in enumerate(out):
             for got, ref in ((bbox, g['bbox_%d' % i]), (orien.contiguous(), g['orien_%d' % i])):
@@ -62,34 +75,76 @@ def test_forward_544_probe_both_engines():
                     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 0.03
 
 
-def test_end_to_end_fp32_vs_oracle_544():
-    """Config 1: image -> detections, parity engine, against the oracle forward + post-process on the host."""
+def _write_report(name, obj):
+    import json
+    import os
+    from tests.common import ROOT
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(obj, open(os.path.join(ROOT, 'gpurun_out', name), 'w'), indent=1)
+    print(json.dumps(obj))
+
+
+@pytest.mark.parametrize('precision', ['parity', 'fp32'])
+def test_end_to_end_parity_vs_oracle_544(precision):
+    """Config 1 (calibrated weights): images -> detections against the oracle forward + post-process on the host, at the NORTH-STAR
+    tolerances: every detection matched by (prediction index, class) has box and score within 1e-3 and mask IoU >= 0.999, and the
+    kept sets are identical except for the pairs LISTED in the report, each of which must be margin-limited (its oracle score within
+    the forward noise of a top-k cut, or its deciding NMS IoU within the noise of the threshold: SURVEY §8d iii -- the reference
+    differs from itself in fp64 on 4 of 100).  `parity` is the tensor-core split-precision mode; `fp32` the FFMA engine."""
     import orienmask_b200 as ob
     from orienmask_b200.synthetic import synthetic_images, synthetic_state_dict
     from oracle.forward_oracle import forward_oracle
-    x = synthetic_images(1, 544, 544, seed=1)
+    from tests.common import e2e_agreement
+    n_img = 2
+    x = synthetic_images(n_img, 544, 544, seed=1)
     ref_heads = forward_oracle(synthetic_state_dict(0), x)
-    ref = _oracle(544, 544, 0.005)([(b.numpy(), o.numpy()) for b, o in ref_heads])[0]
+    ref = _oracle(544, 544, 0.005)([(b.numpy(), o.numpy()) for b, o in ref_heads])
     post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5),
                                        device=torch.device('cuda:0'), **post_config(544, 544, 0.005))
-    got = post(_model('fp32')(x.cuda()))[0]
-    # north star: boxes/scores within 1e-3, mask IoU >= 0.999, identical kept sets.  Matching is by
-    # (cls, box, score) within 1e-3; forward reorder noise (<= 5e-4 on logits) may flip pairs whose
-    # margin is below that noise, so up to 4 unmatched rows are tolerated and reported (SURVEY §8d iii).
-    gb, gc = got['bbox'].cpu().numpy(), got['cls'].cpu().numpy()
-    matched = 0
-    ious = []
-    gm = got['mask'].cpu().numpy()
-    for i in range(len(gb)):
-        d = np.abs(ref['bbox'] - gb[i]).max(1) + (ref['cls'] != gc[i]) * 1e3
-        j = int(np.argmin(d))
-        if d[j] <= 1e-3:
-            matched += 1
-            u = (ref['mask'][j] | gm[i]).sum()
-            ious.append((ref['mask'][j] & gm[i]).sum() / max(u, 1) if u else 1.0)
-    assert len(gb) == len(ref['bbox'])
-    assert matched >= len(gb) - 4, 'only %d of %d detections matched' % (matched, len(gb))
-    assert min(ious) >= 0.99 and np.mean(np.asarray(ious) >= 0.999) >= 0.95, (min(ious), np.mean(ious))
+    padded = post.apply_padded(_model(precision)(x.cuda()))
+    reports = [e2e_agreement(ref[b], padded, b) for b in range(n_img)]
+    _write_report('parity_e2e_%s.json' % precision, reports)
+    for rep in reports:
+        assert rep['max_box_err'] <= 1e-3 and rep['max_score_err'] <= 1e-3, rep
+        assert rep['min_mask_iou'] >= 0.999, rep
+        assert rep['unexplained'] == 0 and len(rep['exceptions']) <= 8, rep['exceptions']
+        assert rep['matched'] >= rep['reference_detections'] - 4
+
+
+def test_end_to_end_plain_init_config1():
+    """Config 1, literal: default (`plain`) initialisation -- kaiming-uniform convolutions, identity BatchNorm statistics
+    (model/base.py:26-32).  Every one of the 1 456 560 scores is 0.2617 +- 5e-6, so all pairs pass conf_thresh and the
+    top-400 is decided in the 6th decimal: index sets are ill-conditioned by construction and are compared as SETS with the tie
+    policy stated -- a kept (prediction, class) pair may differ only if its oracle score is within 2e-6 (a few fp32 ulps of 0.26)
+    of the cut it sits at.  Heads, matched boxes / scores and masks are gated at the north-star tolerances."""
+    import orienmask_b200 as ob
+    from orienmask_b200.synthetic import synthetic_images
+    from oracle.forward_oracle import forward_oracle
+    from tests.common import e2e_agreement
+    torch.manual_seed(0)
+    m = ob.OrienMaskYOLOFPNPlus(3, 80)                    # the constructor applies the reference's default init
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m.precision = 'parity'
+    m = m.to('cuda:0').eval()
+    x = synthetic_images(1, 544, 544, seed=1)
+    ref_heads = forward_oracle(sd, x)
+    heads = m(x.cuda())
+    for (gb, go), (rb, ro) in zip(heads, ref_heads):
+        assert float((gb.cpu() - rb).abs().max()) < 5e-4 and float((go.cpu() - ro).abs().max()) < 5e-4
+    ref = _oracle(544, 544, 0.005)([(b.numpy(), o.numpy()) for b, o in ref_heads])[0]
+    assert ref['n_candidates'] == 400 and abs(float(ref['conf'].mean()) - 0.2617) < 2e-3
+    post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5),
+                                       device=torch.device('cuda:0'), **post_config(544, 544, 0.005))
+    padded = post.apply_padded(heads)
+    rep = e2e_agreement(ref, padded, 0, score_noise=2e-6, iou_noise=1e-4)
+    _write_report('parity_e2e_plain_init.json', rep)
+    assert rep['engine_detections'] == rep['reference_detections']
+    assert rep['max_box_err'] <= 1e-3 and rep['max_score_err'] <= 1e-3 and rep['min_mask_iou'] >= 0.999, rep
+    assert rep['unexplained'] == 0, rep['exceptions']
+    # the stage gate that IS well conditioned: the engine's post-process on the reference's own heads keeps identical sets
+    same = post.apply_padded([(b.cuda(), o.cuda()) for b, o in ref_heads])
+    rep2 = e2e_agreement(ref, same, 0)
+    assert rep2['exceptions'] == [] and rep2['min_mask_iou'] >= 0.999 and rep2['max_box_err'] <= 1e-5
 
 
 def test_end_to_end_fp16_runs_and_reports():
@@ -139,7 +194,7 @@ def test_report_forward_drift_544():
     x = synthetic_images(1, 544, 544, seed=1)
     ref = forward_oracle(synthetic_state_dict(0), x)
     report = {}
-    for prec in ('fp32', 'fp16'):
+    for prec in ('fp32', 'parity', 'fp16'):
         out = _model(prec)(x.cuda())
         rows = []
         for (gb, go), (rb, ro) in zip(out, ref):
@@ -149,7 +204,7 @@ def test_report_forward_drift_544():
                              'rel_l2': float((g - want).norm() / want.norm())})
         report[prec] = rows
         worst = max(r['rel_l2'] for r in rows)
-        assert worst < (1e-4 if prec == 'fp32' else 0.03), (prec, worst)
+        assert worst < (0.03 if prec == 'fp16' else 5e-5), (prec, worst)
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump(report, open(os.path.join(ROOT, 'gpurun_out', 'drift.json'), 'w'), indent=1)
 
@@ -160,7 +215,7 @@ def test_non_plus_model_both_engines():
     from orienmask_b200.synthetic import synthetic_images, synthetic_state_dict
     g = np.load(GOLDEN + '/yolo_small_fwd.npz')
     x = synthetic_images(2, 64, 96, seed=1).cuda()
-    for prec in ('fp32', 'fp16'):
+    for prec in ('fp32', 'parity', 'fp16'):
         m = ob.OrienMaskYOLO(3, 80)
         assert len(m.state_dict()) == 506
         m.load_state_dict(synthetic_state_dict(0, plus=False), strict=True)
@@ -169,7 +224,7 @@ def test_non_plus_model_both_engines():
         for i, (bbox, orien) in enumerate(out):
             for got, ref in ((bbox, g['bbox_%d' % i]), (orien.contiguous(), g['orien_%d' % i])):
                 got = got.cpu().numpy()
-                if prec == 'fp32':
+                if prec != 'fp16':
                     assert np.abs(got - ref).max() < 5e-4
                 else:
                     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 0.03
@@ -178,7 +233,7 @@ def test_non_plus_model_both_engines():
 def test_forward_returns_tensors_owned_by_the_caller():
     """The reference's forward returns fresh tensors; results of one call must survive the next call (both engines)."""
     from orienmask_b200.synthetic import synthetic_images
-    for prec in ('fp16', 'fp32'):
+    for prec in ('fp16', 'parity', 'fp32'):
         m = _model(prec)
         a = m(synthetic_images(2, 64, 96, seed=1).cuda())
         keep = [(b.clone(), o.clone()) for b, o in a]

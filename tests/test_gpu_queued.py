@@ -92,3 +92,39 @@ def test_post_process_two_anchors_per_scale():
     res = post([(b.cuda(), o.cuda()) for b, o in heads])
     for b in range(2):
         _compare(res[b], ref[b]['bbox'], ref[b]['cls'], ref[b]['mask'], ordered=True)
+
+
+def test_model_with_20_classes_all_engines():
+    """num_classes=20 (the reference's VOC configs): 3 * 25 = 75 head channels -> N = 96 pair tiles in the tcgen05 engines."""
+    import orienmask_b200 as ob
+    from oracle.forward_oracle import forward_oracle
+    from orienmask_b200.synthetic import synthetic_state_dict, synthetic_images
+    sd = synthetic_state_dict(0, num_classes=20)
+    x = synthetic_images(2, 96, 160, seed=7)
+    ref = forward_oracle(sd, x)
+    for prec in ('fp32', 'parity', 'fp16'):
+        m = ob.OrienMaskYOLOFPNPlus(3, 20)
+        m.load_state_dict(sd, strict=True)
+        m.precision = prec
+        out = m.to('cuda:0').eval()(x.cuda())
+        assert out[0][0].shape == (2, 75, 3, 5)
+        for (b, o), (rb, ro) in zip(out, ref):
+            for got, want in ((b, rb), (o, ro)):
+                got = got.float().cpu()
+                if prec == 'fp16':
+                    assert float((got - want).norm() / want.norm()) < 0.03
+                else:
+                    assert float((got - want).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize('shape', [(1, 640, 640), (2, 544, 640)])
+def test_parity_forward_at_other_sizes(shape):
+    from oracle.forward_oracle import forward_oracle
+    from orienmask_b200.synthetic import synthetic_state_dict, synthetic_images
+    B, H, W = shape
+    x = synthetic_images(B, H, W, seed=3)
+    ref = forward_oracle(synthetic_state_dict(0), x)
+    out = _model('parity')(x.cuda())
+    for (b, o), (rb, ro) in zip(out, ref):
+        for got, want in ((b, rb), (o, ro)):
+            assert float((got.float().cpu() - want).abs().max()) < 1e-3

@@ -1,6 +1,7 @@
 """CPU-side tests: the C-ABI library loads and exports every declared symbol, the host mirrors keep the
 reference interface, sharding logic (gloo, world size 2)."""
 import ctypes
+import types
 import functools
 import os
 import re
@@ -22,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
-    assert _lib.lib().om_abi_version() == 6
+    assert _lib.lib().om_abi_version() == 7
 
 
 def test_header_is_plain_c_and_links(tmp_path):
@@ -38,7 +39,7 @@ def test_header_is_plain_c_and_links(tmp_path):
                            '-o', exe, '-L', libdir, '-lorienmask_b200', '-Wl,-rpath,' + libdir])
     words = subprocess.check_output([exe]).decode().split()
     got = {words[i]: int(words[i + 1]) for i in range(0, len(words), 2)}
-    assert got['abi'] == 6 and got['entries'] == len(_lib.SIGNATURES)
+    assert got["abi"] == 7 and got['entries'] == len(_lib.SIGNATURES)
     assert got['sizeof(om_post_config)'] == ctypes.sizeof(_lib.PostConfig)
     assert got['sizeof(om_conv_desc)'] == ctypes.sizeof(_lib.ConvDesc)
     assert got['sizeof(om_prep_config)'] == ctypes.sizeof(_lib.PrepConfig)
@@ -66,7 +67,7 @@ def test_built_library_contains_blackwell_tensor_and_tma_code():
     build.build()
     counts = dict(sass_report.sass_counts())
     assert len(counts) >= 20
-    for name in ('conv_tc2_kernel<32>', 'conv_tc2_kernel<64>'):
+    for name in ('conv_tc2_kernel<32, false>', 'conv_tc2_kernel<64, false>', 'conv_tc2_kernel<32, true>', 'conv_tc2_kernel<64, true>'):
         c = counts[name]
         assert c['UTCHMMA'] > 100 and c['UTMALDG'] >= 5 and c['LDTM'] >= 4 and c['UTCBAR'] >= 2 and c['ACQBULK'] >= 1, (name, dict(c))
     assert counts['stem_tc_kernel']['UTCHMMA'] >= 2 and counts['stem_tc_kernel']['LDTM'] >= 1
@@ -105,8 +106,8 @@ def test_conv_descriptor_errors_are_reported_without_a_gpu():
              (dict(in_rows=16), -1, b'in_rows'), (dict(out_h=8), -1, b'geometry'), (dict(input=0), -1, b'null tensor'),
              (dict(cout_stride=32), -1, b'cout_stride'), (dict(cin=48), -1, b'cin'), (dict(batch=0), -1, b'non-positive'),
              (dict(residual=256, out_kind=_lib.OUT_NCHW), -1, b'residual'), (dict(in_s2d=1), -1, b'in_s2d'),
-             # a 20-class head (75 channels -> 80 padded): N = 80 cannot be halved over a CTA pair; loud, not wrong
-             (dict(cout=75, ksize=1, out_kind=_lib.OUT_NCHW), -1, b'cannot be split over a CTA pair')]
+             # split precision stores hi | lo halves of a dense pixel: a channel pitch wider than cout is refused
+             (dict(precision=_lib.PREC_SPLIT, cout_stride=128), -1, b'split precision needs a dense activation output')]
     for kw, code, text in cases:
         handle = _lib.c_vp()
         rc = lib.om_conv_create(desc(**kw), handle)
@@ -222,6 +223,52 @@ def test_engine_plans_are_bounded_lru(monkeypatch):
     assert m._engine_for(key(1), 'cuda:0') is a and len(built) == 3
     m.load_state_dict(m.state_dict())                                        # new weights: every packed plan is dropped
     assert not m._engines
+
+
+def test_weight_updates_drop_the_packed_weights(monkeypatch):
+    """The reference nn.Module always runs on its live parameters.  The engine's folded / packed copies must follow every update
+    PyTorch can make without calling this module's own load_state_dict: a parent's load_state_dict, in-place writes (optimizer steps,
+    EMA swaps through p.copy_), `p.data = ...` swaps.  Each forward compares a (version, address) fingerprint (model.py)."""
+    import torch.nn as nn
+    import orienmask_b200 as ob
+    from orienmask_b200 import model as mod
+    built = []
+
+    class FakeEngine:
+        def __init__(self, model, B, H, W, precision, device):
+            built.append(model._weights_version)
+
+        def run(self, x):
+            return 'ran'
+    monkeypatch.setattr(mod, '_Engine', FakeEngine)
+    m = ob.OrienMaskYOLOFPNPlus(3, 80).eval()
+    x = types.SimpleNamespace(is_cuda=True, dim=lambda: 4, size=lambda i: (1, 3, 64, 64)[i], device=types.SimpleNamespace(index=0))
+    assert m(x) == 'ran' and m(x) == 'ran' and len(built) == 1               # unchanged weights: the plan is reused
+    w = m.state_dict()['backbone.conv1.conv_block.0.weight']
+    with torch.no_grad():
+        w.mul_(2.0)                                                           # in place (what an optimizer step / EMA copy_ does)
+    m(x)
+    assert len(built) == 2
+    parent = nn.Sequential(m)
+    parent.load_state_dict(parent.state_dict())                               # recurses through _load_from_state_dict, not m.load_state_dict
+    m(x)
+    assert len(built) == 3
+    p = next(m.parameters())
+    p.data = p.data.clone()                                                   # storage swap: same version counter, new address
+    m(x)
+    assert len(built) == 4
+    m(x)
+    assert len(built) == 4
+    with torch.no_grad():
+        p.data.copy_(p.data * 3)                                              # through a detached alias: no counter, no new address ...
+    m(x)
+    assert len(built) == 4
+    m.invalidate()                                                            # ... the documented escape hatch
+    m(x)
+    assert len(built) == 5
+    m.train()
+    with pytest.warns(UserWarning, match='inference engine'):
+        m(x)
 
 
 def test_postprocess_constructor_mirrors_reference():

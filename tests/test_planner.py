@@ -34,12 +34,25 @@ for plus, B, H, W in cases:
             failures.append(((plus, B, H, W), 'implausible plan: %%s' %% bad[:3]))
     except Exception as e:                            # noqa: BLE001
         failures.append(((plus, B, H, W), str(e)[:300]))
+split_modes = {}
+for plus, B, H, W in [(True, 32, 544, 544), (True, 1, 544, 544), (True, 8, 960, 960), (True, 2, 64, 96), (True, 2, 544, 640), (False, 3, 96, 160)]:
+    try:                                              # the split-precision (parity) engine: same schedule, 3x the K loop, hi | lo operands
+        eng, rows = pt.plan(plus, B, H, W, 'parity')
+        planned_split = len(rows)
+        worst_smem = max(worst_smem, max(r['smem'] for r in rows))
+        split_modes[str((B, H, W))] = collections.Counter(pt.mode(r) for r in rows)
+        bad = [r['name'] for r in rows if r['halo_s2'] or r['b_resident'] or r['has_res'] == 1 or r['acc_stages'] * r['block_n'] > 512]
+        if bad:
+            failures.append((('parity', plus, B, H, W), 'implausible plan: %%s' %% bad[:3]))
+    except Exception as e:                            # noqa: BLE001
+        failures.append((('parity', plus, B, H, W), str(e)[:300]))
 eng, rows = pt.plan(True, 32, 544, 544)
 by_name = {r['name']: r for r in rows}
 pick = lambda n: [pt.mode(by_name[n])] + [by_name[n][k] for k in ('tw', 'th', 'block_n', 'tiles_n', 'has_res', 'res_direct', 'b_resident')]
 print(json.dumps({'cases': len(cases), 'layers_planned': planned, 'failures': failures, 'worst_smem': worst_smem,
                   'launches_544': len(eng.plans), 'gflop_per_image_544': eng.flops / 32 / 1e9,
                   'modes_544': collections.Counter(pt.mode(r) for r in rows),
+                  'split_modes': split_modes,
                   'modes_960': collections.Counter(pt.mode(r) for r in pt.plan(True, 8, 960, 960)[1]),
                   'neck4.1': pick('neck4.1'), 'conv2.0': pick('backbone.conv2.0'), 'conv4.0': pick('backbone.conv4.0'),
                   'conv5.1.conv.1': pick('backbone.conv5.1.conv.1'), 'conv4.1.conv.1': pick('backbone.conv4.1.conv.1'),
@@ -62,6 +75,8 @@ def test_planner_sweep_and_north_star_plan_without_a_gpu():
     # the plan the round-1 measurements were taken with (profiles/r01_plan_bs32_544.md): a change here is a change of the tuned schedule
     assert res['modes_544'] == res['modes_960'] == {'flat': 56, 'halo': 19, 'per-tap': 18, 'halo-s2': 1}
     #                    mode, tw, th, N tile, N tiles, addend (1 TMA fp16, 2 TMA up-add), direct residual, resident weights
+    # split precision: no parity-plane halo / resident weights / TMA-staged fp16 residual (the epilogue reads hi and lo itself)
+    assert sum(res['split_modes']['(32, 544, 544)'].values()) == 94 and 'halo-s2' not in res['split_modes']['(32, 544, 544)']
     assert res['neck4.1'] == ['halo', 8, 16, 256, 1, 0, 0, 0]                    # 3x3 128->256 @136x136: a third of all FLOPs
     assert res['conv2.0'] == ['halo-s2', 8, 16, 64, 1, 0, 0, 1]                  # parity-plane halo boxes, all weights resident
     assert res['conv4.0'] == ['flat', 128, 1, 256, 1, 0, 0, 0]                   # stride 2 over 137 -> 72-row images: im2col-gathered

@@ -45,7 +45,8 @@ def install_stand_ins():
     orig_conv = mod._Engine.conv
 
     def act(self, stride, channels, dtype=None, s2d=False):
-        return dict(t=Buf(self.B * self.rows(stride), self.W // stride, channels), stride=stride, c=channels, s2d=s2d)
+        return dict(t=Buf(self.B * self.rows(stride), self.W // stride, channels * (self.cmul if dtype is None else 1)), stride=stride,
+                    c=channels, s2d=s2d)
 
     def folded(self, prefix, kind):                  # shapes only: BN folding itself is tested on the GPU
         w = self.sd[prefix + ('.conv_block.0.weight' if kind == 'cbl' else '.weight')]
@@ -57,21 +58,21 @@ def install_stand_ins():
         return orig_conv(self, src, w, Buf() if bias is not None else None, dst, *a, **kw)
 
     mod._Engine.act, mod._Engine.folded, mod._Engine.conv = act, folded, conv
-    mod._Engine.pack = lambda self, w: Buf(*w.shape)
+    mod._Engine.pack = lambda self, w: (Buf(*w.shape), 1.0)
     torch.cuda.device = lambda d: contextlib.nullcontext()
 
 
 _MODELS = {}
 
 
-def plan(plus, batch, height, width):
+def plan(plus, batch, height, width, precision='fp16'):
     """-> (engine, [dict per conv_tc2 launch]) planned in dry-run mode."""
     if plus not in _MODELS:
         m = (ob.OrienMaskYOLOFPNPlus if plus else ob.OrienMaskYOLO)(3, 80)
         meta = {k: torch.empty(v.shape, device='meta') for k, v in m.state_dict().items() if v.is_floating_point()}
         m.state_dict = lambda: meta
         _MODELS[plus] = m
-    eng = mod._Engine(_MODELS[plus], batch, height, width, precision='fp16', device='meta')
+    eng = mod._Engine(_MODELS[plus], batch, height, width, precision=precision, device='meta')
     lib = _lib.lib()
     lib.om_debug_conv_plan_info.restype = ctypes.c_int32
     lib.om_debug_conv_plan_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
@@ -98,10 +99,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--batch', type=int, default=32)
     ap.add_argument('--size', type=int, default=544)
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'parity'])
     args = ap.parse_args()
     install_stand_ins()
-    _, rows = plan(True, args.batch, args.size, args.size)
-    print('Plan of the fp16 engine, bs %d, %dx%d (planner dry run, 148 SMs; tools/plan_table.py)\n' % (args.batch, args.size, args.size))
+    _, rows = plan(True, args.batch, args.size, args.size, args.precision)
+    print('Plan of the %s engine, bs %d, %dx%d (planner dry run, 148 SMs; tools/plan_table.py)\n' % (args.precision, args.batch, args.size, args.size))
     print('| # | layer | shape | mode | tile | N tile x count | stages x blocks | halo stages | weights resident | acc | addend | smem KB | CTAs | pair tiles | waves | tile eff |')
     print('|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|')
     for i, r in enumerate(rows, 1):
