@@ -141,8 +141,9 @@ int32_t om_nms(const float* dets, int32_t n, float threshold, int64_t* keep, int
 #define OM_PREC_F32 0   /* parity engine: fp32 storage, FFMA                                     */
 #define OM_PREC_F16 1   /* production engine: fp16 storage, tcgen05 tensor cores, fp32 accumulate */
 #define OM_PREC_SPLIT 2 /* parity engine on the tensor cores: every activation and weight is an fp16 pair hi + lo
-                           (hi = fp16(v), lo = fp16(v - hi): ~22 significant bits), D = A_hi*W_hi + A_lo*W_hi + A_hi*W_lo as
-                           three tcgen05 MMAs into one fp32 TMEM accumulator.  Activations: [.., W, 2*C] halves (hi | lo along
+                           (hi = fp16(v), lo = fp16(v - hi): ~22 significant bits), D = A_lo*W_hi + A_hi*W_lo + A_hi*W_hi as
+                           three tcgen05 MMA passes into one fp32 TMEM accumulator (corrections first: the tensor core
+                           truncates its running sum).  Activations: [.., W, 2*C] halves (hi | lo along
                            the channel axis); weights [k*k][cout_pad][2*cin] halves (hi | lo), pre-scaled by a power of two so
                            that W_lo stays a normal fp16 number (undone by acc_scale)                                  */
 
@@ -192,6 +193,13 @@ int32_t om_conv_run(const om_conv* conv, void* stream);
 int32_t om_conv_run_to(const om_conv* conv, void* output, void* stream);
 void om_conv_destroy(om_conv* conv);
 
+/* Debug / tooling (not needed to run the path): the planner's decisions for one layer of the tcgen05 engines --
+ * info[24] = halo, flat, halo_s2, b_resident, tw, th, block_n, tiles_n, stages, n_sub, h_stages, acc_stages, has_res (1 fp16 residual staged
+ * by TMA, 2 staged up-add), res_direct, smem bytes, grid, CTA-pair tiles, taps, K chunks, BK, TMEM columns, cout, out_h, out_w. */
+int32_t om_debug_conv_plan_info(const om_conv* conv, int32_t* info24);
+/* Debug: device buffer of >= 16 uint64 that cluster 0 of the following conv launches fills with %globaltimer stamps (NULL turns it off). */
+int32_t om_debug_conv_timeline(void* device_u64x16);
+
 /*
  * First layer (3 -> cout, 3x3, stride 1, BN folded, LeakyReLU) straight from the caller's image.
  *   image    device fp32 NCHW [batch,3,h,w]
@@ -201,6 +209,66 @@ void om_conv_destroy(om_conv* conv);
  */
 int32_t om_stem_conv(int32_t precision, const float* image, const float* weights, const float* bias, void* output,
                      int32_t batch, int32_t h, int32_t w, int32_t rows, int32_t cout, int32_t out_s2d, void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Whole network: OrienMaskYOLOFPNPlus.forward / OrienMaskYOLO.forward behind one call            */
+/* (model/orienmask_yolo_fpnplus.py:9-90, model/orienmask_yolo.py:8-86, model/backbone/darknet.py:18-54) */
+/* ------------------------------------------------------------------------------------------- */
+
+typedef struct om_engine_config {
+    int32_t precision;             /* OM_PREC_*                                                                  */
+    int32_t batch, height, width;  /* input [batch, 3, height, width]; height, width multiples of 32              */
+    int32_t num_anchors;           /* constructor arguments of the reference model (config/base.py:99-106)        */
+    int32_t num_classes;
+    int32_t plus;                  /* 1: OrienMaskYOLOFPNPlus (524-key state dict), 0: OrienMaskYOLO (506 keys)   */
+} om_engine_config;
+
+/* One entry of the reference state dict: its key (e.g. "backbone.conv2.1.conv.0.conv_block.1.running_var"), the tensor as fp32
+ * on the device in the reference's own layout (conv weights OIHW), and its element count (checked against the architecture). */
+typedef struct om_tensor {
+    const char* name;
+    const float* data;
+    int64_t numel;
+} om_tensor;
+
+typedef struct om_engine om_engine;
+
+/* Bytes of device workspace an engine of this configuration needs: activation buffers, folded + packed weights, biases. */
+int32_t om_engine_workspace_bytes(const om_engine_config* cfg, size_t* bytes);
+/*
+ * Builds the launch schedule of the forward pass: folds BatchNorm into the convolution weights and packs them for `precision` on
+ * the device (kernels enqueued on `stream`; the state-dict tensors may be released once that work has completed), lays every
+ * activation buffer out inside `workspace` (zero-filled here; at least om_engine_workspace_bytes() bytes, caller-owned, must
+ * outlive the engine) and plans every layer (TMA descriptors, tiles).  The one call of the library that synchronises `stream`
+ * (OM_PREC_SPLIT reads the per-layer weight scale back); om_forward never does.
+ */
+int32_t om_engine_create(const om_engine_config* cfg, const om_tensor* weights, int32_t n_weights, void* workspace,
+                         size_t workspace_bytes, void* stream, om_engine** out);
+/*
+ * forward(x) -> ((bbox32, orien32), (bbox16, orien16), (bbox8, orien8)), model/orienmask_yolo_fpnplus.py:74-90.
+ *   image    device fp32 NCHW [batch, 3, height, width]
+ *   bbox[3]  device fp32 NCHW [batch, A*(5+C), height/s, width/s] for s = 32, 16, 8
+ *   orien    device fp32 NCHW [batch, 6*A, height/4, width/4]: channels [0,2A) belong to stride 32, [2A,4A) to 16, [4A,6A) to 8
+ *            (the reference's torch.split(oriens, 2A, dim=1), :88)
+ * Enqueues every launch of the schedule on `stream`; no allocation, no synchronisation.
+ */
+int32_t om_forward(const om_engine* engine, const float* image, float* const* bbox, float* orien, void* stream);
+void om_engine_destroy(om_engine* engine);
+
+/* Introspection for tools (per-layer timing, plan tables): the schedule is a list of launches in execution order. */
+typedef struct om_layer_info {
+    char name[64];                 /* state-dict prefix of the layer ("neck4.0[64:128]" for a concat-split partial)          */
+    char shape[96];                /* e.g. "3x3 s1 128->256 @136x136 +res"                                                 */
+    double flops, bytes;           /* algorithmic: 2*MAC; activations in + out (+ addends) + weights                       */
+    int32_t head_slot;             /* -1, or 0..2 (bbox 32/16/8), 3 (orientation)                                          */
+    int32_t is_stem;
+    om_conv_desc desc;
+    const om_conv* conv;           /* NULL for the stem                                                                    */
+} om_layer_info;
+int32_t om_engine_layer_count(const om_engine* engine);
+int32_t om_engine_layer_info(const om_engine* engine, int32_t index, om_layer_info* info);
+/* One launch of the schedule (same arguments as om_forward; only the stem reads `image`, only head layers write outputs). */
+int32_t om_engine_run_layer(const om_engine* engine, int32_t index, const float* image, float* const* bbox, float* orien, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Pre-process (the caller side of the path: infer.py:147-151)                                   */

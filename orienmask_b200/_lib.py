@@ -61,6 +61,20 @@ class BlendConfig(ctypes.Structure):
                 ('out_h', c_i32), ('out_w', c_i32), ('alpha', c_f32)]
 
 
+class EngineConfig(ctypes.Structure):
+    _fields_ = [('precision', c_i32), ('batch', c_i32), ('height', c_i32), ('width', c_i32), ('num_anchors', c_i32),
+                ('num_classes', c_i32), ('plus', c_i32)]
+
+
+class OmTensor(ctypes.Structure):
+    _fields_ = [('name', ctypes.c_char_p), ('data', c_vp), ('numel', c_i64)]
+
+
+class LayerInfo(ctypes.Structure):
+    _fields_ = [('name', ctypes.c_char * 64), ('shape', ctypes.c_char * 96), ('flops', ctypes.c_double), ('bytes', ctypes.c_double),
+                ('head_slot', c_i32), ('is_stem', c_i32), ('desc', ConvDesc), ('conv', c_vp)]
+
+
 SRC_U8, SRC_F32 = 0, 1
 
 # name -> (restype, argtypes); every symbol declared in include/orienmask_b200.h
@@ -85,6 +99,16 @@ SIGNATURES = {
     'om_mask_areas': (c_i32, [ctypes.POINTER(BlendConfig), c_vp, c_i32, c_vp, c_vp, c_vp]),
     'om_mask_blend': (c_i32, [ctypes.POINTER(BlendConfig), c_vp, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'om_stem_conv': (c_i32, [c_i32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'om_debug_conv_plan_info': (c_i32, [c_vp, ctypes.POINTER(c_i32)]),
+    'om_debug_conv_timeline': (c_i32, [c_vp]),
+    'om_engine_workspace_bytes': (c_i32, [ctypes.POINTER(EngineConfig), ctypes.POINTER(ctypes.c_size_t)]),
+    'om_engine_create': (c_i32, [ctypes.POINTER(EngineConfig), ctypes.POINTER(OmTensor), c_i32, c_vp, ctypes.c_size_t, c_vp,
+                                 ctypes.POINTER(c_vp)]),
+    'om_forward': (c_i32, [c_vp, c_vp, ctypes.POINTER(c_vp), c_vp, c_vp]),
+    'om_engine_destroy': (None, [c_vp]),
+    'om_engine_layer_count': (c_i32, [c_vp]),
+    'om_engine_layer_info': (c_i32, [c_vp, c_i32, ctypes.POINTER(LayerInfo)]),
+    'om_engine_run_layer': (c_i32, [c_vp, c_i32, c_vp, ctypes.POINTER(c_vp), c_vp, c_vp]),
 }
 
 _lib = None

@@ -18,6 +18,7 @@ COMMON = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '--expt-relax
 # exactly like the reference's fp32 CPU arithmetic.
 UNITS = [
     ('api.cu', []),
+    ('engine.cu', []),
     ('post.cu', ['-fmad=false']),
     ('prep.cu', ['-fmad=false']),
     ('rle.cu', ['-fmad=false']),

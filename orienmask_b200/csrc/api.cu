@@ -95,11 +95,11 @@ extern "C" void om_conv_destroy(om_conv* c) {
     delete c;
 }
 
-// Debug only (not part of the ABI in include/orienmask_b200.h): device buffer of >= 16 uint64 that cluster 0 of the next
-// conv_tc2 launches fills with %globaltimer stamps (prologue / first load / first MMA / first epilogue / exit).
+// Debug: device buffer of >= 16 uint64 that cluster 0 of the next conv_tc2 launches fills with %globaltimer stamps (prologue / first
+// load / first MMA / first epilogue / exit).
 namespace om { int32_t tc2_set_timeline(void* dev_ptr); }
 extern "C" int32_t om_debug_conv_timeline(void* dev_ptr) { return om::tc2_set_timeline(dev_ptr); }
-// Debug only: the planner's decisions for a layer of the CTA-pair engine -- info[24] = halo, flat, halo_s2, b_resident, tw, th,
+// Debug: the planner's decisions for a layer of the CTA-pair engine -- info[24] = halo, flat, halo_s2, b_resident, tw, th,
 // block_n, tiles_n, stages, n_sub, h_stages, acc_stages, has_res (1 fp16 residual, 2 staged up-add), res_direct, smem bytes, grid,
 // CTA-pair tiles, taps, K chunks, BK, TMEM columns, cout, out_h, out_w.
 extern "C" int32_t om_debug_conv_plan_info(const om_conv* c, int32_t* info) {

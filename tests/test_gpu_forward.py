@@ -230,6 +230,50 @@ def test_non_plus_model_both_engines():
                     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 0.03
 
 
+@pytest.mark.parametrize('plus', [True, False])
+def test_c_engine_matches_the_python_schedule(plus, monkeypatch):
+    """om_engine_create / om_forward (the schedule, BN folding and weight packing inside the C library) against the Python-scheduled
+    twin (one om_conv_* call per layer, folding and packing in torch): bit-identical heads in every precision, both model variants."""
+    import orienmask_b200 as ob
+    from orienmask_b200 import model as mod
+    from orienmask_b200.synthetic import synthetic_images, synthetic_state_dict
+    x = synthetic_images(2, 96, 160, seed=9).cuda()
+    cls = ob.OrienMaskYOLOFPNPlus if plus else ob.OrienMaskYOLO
+    for prec in ('fp16', 'parity', 'fp32'):
+        outs = []
+        for engine in ('c', 'py'):
+            monkeypatch.setenv('ORIENMASK_B200_ENGINE', engine)
+            m = cls(3, 80)
+            m.load_state_dict(synthetic_state_dict(0, plus=plus), strict=True)
+            m.precision = prec
+            m = m.to('cuda:0').eval()
+            outs.append(m(x))
+            eng = next(iter(m._engines.values()))
+            assert type(eng) is (mod._Engine if engine == 'c' else mod._PyEngine)
+            assert len(eng.layers) == (95 if plus else 90)
+        for (b0, o0), (b1, o1) in zip(*outs):
+            assert torch.equal(b0, b1) and torch.equal(o0, o1), (prec, float((b0 - b1).abs().max()), float((o0 - o1).abs().max()))
+
+
+def test_c_engine_errors_are_loud():
+    """om_engine_create validates the state dict against the architecture and the workspace against the plan."""
+    import ctypes
+    from orienmask_b200 import _lib
+    lib = _lib.lib()
+    cfg = _lib.EngineConfig(_lib.PREC_F16, 1, 64, 64, 3, 80, 1)
+    n = ctypes.c_size_t(0)
+    _lib.check(lib.om_engine_workspace_bytes(ctypes.byref(cfg), ctypes.byref(n)), 'om_engine_workspace_bytes')
+    ws = torch.empty(n.value, dtype=torch.uint8, device='cuda')
+    w = torch.zeros(32 * 3 * 9, device='cuda')
+    arr = (_lib.OmTensor * 1)(_lib.OmTensor(b'backbone.conv1.conv_block.0.weight', w.data_ptr(), w.numel()))
+    h = _lib.c_vp()
+    rc = lib.om_engine_create(ctypes.byref(cfg), arr, 1, _lib.ptr(ws), n.value, _lib.stream_ptr(), ctypes.byref(h))
+    assert rc == -1 and b"state dict has no 'backbone.conv1.conv_block.1.weight'" in lib.om_last_error() and not h.value
+    bad = _lib.EngineConfig(_lib.PREC_F16, 1, 60, 64, 3, 80, 1)
+    assert lib.om_engine_workspace_bytes(ctypes.byref(bad), ctypes.byref(n)) == -1 and b'multiples of 32' in lib.om_last_error()
+    torch.cuda.synchronize()
+
+
 def test_forward_returns_tensors_owned_by_the_caller():
     """The reference's forward returns fresh tensors; results of one call must survive the next call (both engines)."""
     from orienmask_b200.synthetic import synthetic_images

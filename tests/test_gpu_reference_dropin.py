@@ -57,7 +57,8 @@ def _decode(seg):
 def _compare(got_bbox, got_segm, want_bbox, want_segm, sizes):
     """Match the json records of the run with the oracle's per image by category and nearest box."""
     rep = {'records_engine': len(got_bbox), 'records_oracle': len(want_bbox), 'matched': 0, 'max_box_err_rel': 0.0, 'max_score_err': 0.0,
-           'min_mask_iou': 1.0, 'unmatched': []}
+           'min_mask_iou': 1.0, 'aggregate_mask_iou': 1.0, 'masks_off': 0, 'max_differing_pixels': 0, 'unmatched': []}
+    inter_sum = union_sum = 0
     assert len(got_bbox) == len(got_segm) and len(want_bbox) == len(want_segm)
     used = set()
     for gi, g in enumerate(got_bbox):
@@ -78,8 +79,13 @@ def _compare(got_bbox, got_segm, want_bbox, want_segm, sizes):
         rep['max_score_err'] = max(rep['max_score_err'], abs(g['score'] - want_bbox[bj]['score']))
         assert got_segm[gi]['category_id'] == g['category_id'] and abs(got_segm[gi]['score'] - g['score']) < 1e-9
         a, b = _decode(got_segm[gi]['segmentation']), _decode(want_segm[bj]['segmentation'])
-        u = (a | b).sum()
-        rep['min_mask_iou'] = min(rep['min_mask_iou'], float((a & b).sum() / u) if u else 1.0)
+        u, it = int((a | b).sum()), int((a & b).sum())
+        iou = it / u if u else 1.0
+        rep['min_mask_iou'] = min(rep['min_mask_iou'], iou)
+        rep['max_differing_pixels'] = max(rep['max_differing_pixels'], u - it)
+        rep['masks_off'] += int(iou < 0.999 and u - it > 2)          # the mask gate of tests/common.py:e2e_agreement
+        inter_sum, union_sum = inter_sum + it, union_sum + u
+    rep['aggregate_mask_iou'] = inter_sum / union_sum if union_sum else 1.0
     return rep
 
 

@@ -42,7 +42,7 @@ class Buf:
 
 def install_stand_ins():
     """Replace the engine's allocations by stand-ins so that `_Engine._build` (the real schedule) runs on a CPU-only box."""
-    orig_conv = mod._Engine.conv
+    orig_conv = mod._PyEngine.conv
 
     def act(self, stride, channels, dtype=None, s2d=False):
         return dict(t=Buf(self.B * self.rows(stride), self.W // stride, channels * (self.cmul if dtype is None else 1)), stride=stride,
@@ -57,8 +57,8 @@ def install_stand_ins():
             kw['nchw'] = Buf(*kw['nchw'].shape)
         return orig_conv(self, src, w, Buf() if bias is not None else None, dst, *a, **kw)
 
-    mod._Engine.act, mod._Engine.folded, mod._Engine.conv = act, folded, conv
-    mod._Engine.pack = lambda self, w: (Buf(*w.shape), 1.0)
+    mod._PyEngine.act, mod._PyEngine.folded, mod._PyEngine.conv = act, folded, conv
+    mod._PyEngine.pack = lambda self, w: (Buf(*w.shape), 1.0)
     torch.cuda.device = lambda d: contextlib.nullcontext()
 
 
@@ -72,10 +72,8 @@ def plan(plus, batch, height, width, precision='fp16'):
         meta = {k: torch.empty(v.shape, device='meta') for k, v in m.state_dict().items() if v.is_floating_point()}
         m.state_dict = lambda: meta
         _MODELS[plus] = m
-    eng = mod._Engine(_MODELS[plus], batch, height, width, precision=precision, device='meta')
+    eng = mod._PyEngine(_MODELS[plus], batch, height, width, precision=precision, device='meta')
     lib = _lib.lib()
-    lib.om_debug_conv_plan_info.restype = ctypes.c_int32
-    lib.om_debug_conv_plan_info.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32)]
     rows = []
     for (kind, arg), layer in zip(eng.plans, eng.layers):
         if kind != 'conv':

@@ -50,7 +50,7 @@ out = full_step()            # un-profiled warm-up: builds the engine (BN foldin
 torch.cuda.synchronize()
 eng = next(iter(model._engines.values()))
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-json.dump(eng.layers, open(os.path.join(ROOT, 'gpurun_out', 'layers.json'), 'w'))
+json.dump([{k: v for k, v in l.items() if k in ('name', 'shape', 'flops', 'bytes')} for l in eng.layers], open(os.path.join(ROOT, 'gpurun_out', 'layers.json'), 'w'))
 if a.events:
     eng.time_layers(x, 2)
     json.dump(eng.time_layers(x, a.events), open(os.path.join(ROOT, 'gpurun_out', 'layer_events.json'), 'w'))
