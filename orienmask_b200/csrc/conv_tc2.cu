@@ -1043,6 +1043,14 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     p.taps = d.ksize * d.ksize; p.stride = d.stride;
     p.k_chunks = (split ? 3 : 1) * (d.cin / bk); p.a_chunks = (split ? 2 : 1) * (d.cin / bk); p.split_kr = split ? d.cin / bk : 0;
     p.acc_scale = (split && d.acc_scale != 0.0f) ? d.acc_scale : 1.0f;
+    if (split && !getenv("ORIENMASK_B200_NO_GAIN_FIX")) {
+        // tcgen05 truncates its fp32 running sum: every MMA into a non-empty accumulator loses a fraction of an ulp toward zero, which
+        // for a sum that grows from zero is, on average, a common gain error of -0.262 * 2^-24 per MMA step of the hi*hi pass (measured
+        // for K = 64 .. 9216, tools/split_probe.py, profiles/r02_split_probe.json: -0.258 .. -0.30 per step, the same for both
+        // tensor-core engines).  Undoing the mean halves the layer error; what remains is its element-dependent part.
+        const int steps = d.ksize * d.ksize * (d.cin / 16);
+        p.acc_scale *= 1.0f + 0.262f * (float)steps * 5.9604645e-8f;
+    }
     p.pix_stride = split ? 2 * d.cout_stride : d.cout_stride; p.lo_off = d.cout_stride;
     {
         // the fp16 residual: staged by TMA for the memory-bound layers (its DRAM latency must be covered several chunks ahead),
