@@ -119,6 +119,7 @@ class OrienMaskYOLOFPNPlus(nn.Module):
         self._engines = {}
         self._weights_version += 1
         self._fingerprint = None
+        self.__dict__['_state_tensors'] = None
 
     def invalidate(self):
         """Drop the folded / packed weights: the next forward rebuilds them from the live parameters.  Needed only after an
@@ -130,14 +131,18 @@ class OrienMaskYOLOFPNPlus(nn.Module):
         (optimizer steps, ``p.copy_``, a parent module's ``load_state_dict`` -- which never calls this module's override),
         on ``p.data = ...`` swaps and on device / dtype moves.  The reference always runs on the live parameters; the engine's
         packed copies are rebuilt whenever this differs from the fingerprint they were built from."""
-        tensors = list(self.parameters()) + list(self.buffers())
-        return tuple(t._version for t in tensors) + tuple(t.data_ptr() for t in tensors)
+        tensors = self.__dict__.get('_state_tensors')
+        if tensors is None:                      # walking 270 sub-modules costs ~0.5 ms: done once per weight version (see _invalidate)
+            tensors = self.__dict__['_state_tensors'] = list(self.parameters()) + list(self.buffers())
+        return tuple([t._version for t in tensors] + [t.data_ptr() for t in tensors])
 
     def __getstate__(self):
         # copy.deepcopy / pickle (torch.save of the whole module) take the parameters, never the buffer plans: those hold
         # native plan handles and gigabytes of activation buffers, and are rebuilt on the first forward of the copy
         state = self.__dict__.copy()
         state['_engines'] = {}
+        state['_state_tensors'] = None
+        state['_fingerprint'] = None
         return state
 
     def forward(self, x):
