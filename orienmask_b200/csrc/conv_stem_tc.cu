@@ -7,9 +7,16 @@
 // memory (coalesced), each of its 128 threads gathers the 27 taps of one pixel into a 64-byte SWIZZLE_64B
 // K-major row, one elected lane issues the MMAs, and every thread drains its accumulator row from TMEM
 // (bias + LeakyReLU, fp16) with two 32-byte stores.  Several CTAs per SM overlap gather, MMA and stores.
+// The patch is staged by TMA (cp.async.bulk.tensor.4d over the [B][3][H][W] image, box {36, 6, 3, 1} at (x0 - 1, y0 - 1): the image
+// border is the tensor map's out-of-bounds zero fill), double-buffered behind two mbarriers, one tile ahead of the gather; the
+// register-prefetched __ldg version it replaces (612 bounds-checked loads + shared-memory stores per tile) is kept as `TMA = false`.
 // The FFMA version of this layer (conv_f32.cu, kept for the fp32 parity engine) needs 864 FMAs per pixel and
 // was the single slowest launch of the forward pass (profiles/r01_layers_events_v2d.md).
+#include <cuda.h>
 #include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -54,14 +61,16 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8])
                  ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
-__global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ img, const float* __restrict__ w27,
-                                                      const float* __restrict__ bias, __half* __restrict__ out,
+template <bool TMA>
+__global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CUtensorMap map_img, const float* __restrict__ img,
+                                                      const float* __restrict__ w27, const float* __restrict__ bias, __half* __restrict__ out,
                                                       int batch, int h, int wd, int rows, int out_s2d) {
     __shared__ __align__(1024) uint8_t s_a[2][128 * 64];     // im2col rows, K-major SWIZZLE_64B (double-buffered)
     __shared__ __align__(1024) uint8_t s_b[kCout * 64];      // weights [cout][k], same layout
-    __shared__ float s_patch[3][kTileH + 2][kPatchW];
+    __shared__ __align__(128) float s_patch2[TMA ? 2 : 1][3][kTileH + 2][kPatchW];   // TMA: two stages, the box {36, 6, 3} as it lands
     __shared__ float s_bias[kCout];
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(8) uint64_t s_pfull[2];             // TMA: patch stage filled
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -80,6 +89,9 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_pfull[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_pfull[1])));
+        if (TMA) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_img));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -116,6 +128,18 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
         p_s[q] = (i / 34) * kPatchW + (i % 34);
     }
     const int itotal = (int)total;
+    // TMA: one thread asks for the whole patch of a tile; rows / columns outside the image arrive as zeros
+    constexpr uint32_t kPatchBytes = 3 * (kTileH + 2) * kPatchW * 4;
+    auto tma_patch = [&](int tile, int stage) {
+        const int n = tile / tiles_per_image;
+        const int r = tile - n * tiles_per_image;
+        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        const uint32_t bar = smem_u32(&s_pfull[stage]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kPatchBytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(smem_u32(&s_patch2[stage][0][0][0])), "l"(&map_img), "r"(bar), "r"(tx * kTileW - 1), "r"(ty * kTileH - 1), "r"(0), "r"(n) : "memory");
+    };
     auto fetch = [&](int tile, float (&regs)[kPerThread]) {
         const int n = tile / tiles_per_image;
         const int r = tile - n * tiles_per_image;
@@ -170,17 +194,29 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
     };
 
     float pre[kPerThread];
-    if ((int)blockIdx.x < itotal) fetch((int)blockIdx.x, pre);
+    if (!TMA && (int)blockIdx.x < itotal) fetch((int)blockIdx.x, pre);
+    if (TMA && tid == 0 && (int)blockIdx.x < itotal) tma_patch((int)blockIdx.x, 0);
     int buf = 0;
     int prev = -1;
+    int pstage = 0;
+    uint32_t pphase[2] = {0, 0};
     // software pipeline: the MMA of tile i is in flight while the epilogue of tile i-1 runs
     for (int tile = blockIdx.x; tile < itotal; tile += gridDim.x) {
-        // 1. stage the prefetched patch, start the next tile's loads
+        float (*s_patch)[kTileH + 2][kPatchW] = s_patch2[TMA ? pstage : 0];
+        if (TMA) {
+            // 1. the next tile's patch into the other stage (its last readers -- the gather of the previous tile -- are behind the
+            //    second __syncthreads of the previous iteration), then wait for this tile's
+            if (tid == 0 && tile + (int)gridDim.x < itotal) tma_patch(tile + (int)gridDim.x, pstage ^ 1);
+            mbar_wait(&s_pfull[pstage], pphase[pstage]);
+            pphase[pstage] ^= 1;
+        } else {
+            // 1. stage the prefetched patch, start the next tile's loads
 #pragma unroll
-        for (int q = 0; q < kPerThread; ++q)
-            if (tid + q * 128 < kPatchElems) (&s_patch[0][0][0])[p_s[q]] = pre[q];
-        if (tile + (int)gridDim.x < itotal) fetch(tile + (int)gridDim.x, pre);
-        __syncthreads();
+            for (int q = 0; q < kPerThread; ++q)
+                if (tid + q * 128 < kPatchElems) (&s_patch[0][0][0])[p_s[q]] = pre[q];
+            if (tile + (int)gridDim.x < itotal) fetch(tile + (int)gridDim.x, pre);
+            __syncthreads();
+        }
         // 2. im2col row of pixel (y0 + warp, x0 + lane): k = (ky*3 + kx)*3 + ci.  s_a[buf] was last read by the MMA of
         //    tile i-2, whose completion every thread observed in the epilogue of tile i-2.
         {
@@ -226,6 +262,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const float* __restrict__ 
         if (prev >= 0) epilogue(buf ^ 1, prev);
         prev = tile;
         buf ^= 1;
+        pstage ^= 1;
     }
     if (prev >= 0) epilogue(buf ^ 1, prev);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -246,7 +283,45 @@ int32_t stem_tc_run(const float* image, const float* weights, const float* bias,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long grid = (long long)sms * 5;               // one resident wave (96 registers x 128 threads -> 5 CTAs per SM)
     if (grid > tiles) grid = tiles;
-    OM_CUDA_TRY(launch_pdl(stem_tc_kernel, dim3((unsigned)grid), dim3(128), 0, stream, image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d));
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const char* sel = getenv("ORIENMASK_B200_STEM");
+    bool use_tma = !(sel && sel[0] == 'l');            // ORIENMASK_B200_STEM=ldg: the register-prefetch version (A/B)
+    if (use_tma) {
+        typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                          const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                          CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeTiledFn fn = nullptr;
+        if (!fn) {
+            void* ptr = nullptr;
+            cudaDriverEntryPointQueryResult q;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+                fn = reinterpret_cast<EncodeTiledFn>(ptr);
+        }
+        if (!fn) return fail(OM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+        if (reinterpret_cast<uintptr_t>(image) & 15) use_tma = false;          // TMA needs a 16-byte aligned base; the __ldg version takes anything
+        else {
+            // the caller's fp32 NCHW image as a 4-d tensor [B][3][H][W]; box = one tile's patch; out-of-bounds elements read as zero
+            cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, 3, (cuuint64_t)batch};
+            cuuint64_t str[3] = {(cuuint64_t)w * 4, (cuuint64_t)h * w * 4, (cuuint64_t)3 * h * w * 4};
+            cuuint32_t box[4] = {(cuuint32_t)kPatchW, (cuuint32_t)(kTileH + 2), 3, 1};
+            cuuint32_t ones[4] = {1, 1, 1, 1};
+            CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(image), dims, str, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(OM_ERR_CUDA, "cuTensorMapEncodeTiled(stem image) failed with CUresult %d", (int)r);
+        }
+    }
+    if (use_tma) {
+        // 58 registers and 23.8 KB of shared memory per CTA: up to 8 CTAs per SM (8 x 64 TMEM columns = the whole TMEM)
+        const char* ce = getenv("ORIENMASK_B200_STEM_CTAS");
+        const int per_sm = (ce && atoi(ce) >= 1 && atoi(ce) <= 8) ? atoi(ce) : 8;
+        grid = (long long)sms * per_sm;
+        if (grid > tiles) grid = tiles;
+    }
+    if (use_tma)
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d));
+    else
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d));
     return check_launch("stem_tc_kernel");
 }
 

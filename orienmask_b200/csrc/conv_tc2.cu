@@ -999,6 +999,27 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
         bn = bn_cap;
         while (bn > 32 && cout_pad % bn) bn -= 32;
     }
+    if (!getenv("ORIENMASK_B200_BN") && !(getenv("ORIENMASK_B200_NARROW_N") && getenv("ORIENMASK_B200_NARROW_N")[0] == '0')) {
+        // Small batches: when the layer has fewer pixel-tile pairs than the GPU has SM pairs, most SMs idle while a few grind through a
+        // 256-wide tile.  Split N further (128 / 64 columns) as long as everything still fits one wave: the same MMA work spreads over
+        // 2-4x the SMs.  Model per wave: a fixed ~3000 cycles (first loads, epilogue, exit) + K steps * N/2 tensor cycles.
+        // bs 1 at 544x544, forward + post-process: 1.45 -> 1.12 ms (A/B over a fixed cap, profiles/r02_latency_bs1_narrow_n.txt).
+        const int clusters = sm_count() / 2;
+        const long long m_pairs = (((long long)d.batch * d.out_h * d.out_w + kBlockM - 1) / kBlockM + 1) / 2;
+        if (m_pairs * (cout_pad / bn) < clusters) {
+            const long long steps = (long long)d.ksize * d.ksize * (d.cin / 16) * (split ? 3 : 1);
+            long long best_t = -1;
+            int best_bn = bn;
+            for (int cand = bn; cand >= 64; cand >>= 1) {
+                if (cout_pad % cand || cand % 32) continue;
+                const long long pairs = m_pairs * (cout_pad / cand);
+                const long long waves = (pairs + clusters - 1) / clusters;
+                const long long t = waves * (3000 + steps * (cand / 2));
+                if (best_t < 0 || t < best_t) { best_t = t; best_bn = cand; }
+            }
+            bn = best_bn;
+        }
+    }
     if (bn % 32) { delete plan; return fail(OM_ERR_INVALID, "padded cout %d cannot be split over a CTA pair", cout_pad); }
     p.block_n = bn; p.half_n = bn / 2; p.cout_pad = cout_pad; p.tiles_n = cout_pad / bn;
     const char* halo_env = getenv("ORIENMASK_B200_HALO");
