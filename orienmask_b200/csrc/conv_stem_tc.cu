@@ -7,7 +7,7 @@
 // memory (coalesced), each of its 128 threads gathers the 27 taps of one pixel into a 64-byte SWIZZLE_64B
 // K-major row, one elected lane issues the MMAs, and every thread drains its accumulator row from TMEM
 // (bias + LeakyReLU, fp16) with two 32-byte stores.  Several CTAs per SM overlap gather, MMA and stores.
-// The patch is staged by TMA (cp.async.bulk.tensor.4d over the [B][3][H][W] image, box {36, 6, 3, 1} at (x0 - 1, y0 - 1): the image
+// The patch is staged by TMA (cp.async.bulk.tensor.4d over the [B][3][H][W] image, box {40, 6, 3, 1} at (x0 - 4, y0 - 1): the image
 // border is the tensor map's out-of-bounds zero fill), double-buffered behind two mbarriers, one tile ahead of the gather; the
 // register-prefetched __ldg version it replaces (612 bounds-checked loads + shared-memory stores per tile) is kept as `TMA = false`.
 // The FFMA version of this layer (conv_f32.cu, kept for the fp32 parity engine) needs 864 FMAs per pixel and
@@ -23,7 +23,8 @@
 namespace {
 
 constexpr int kTileW = 32, kTileH = 4;       // 128 pixels: warp = tile row, lane = column
-constexpr int kPatchW = 36;                  // 34 used columns, padded
+constexpr int kPatchW = 40;                  // 34 used columns (x0 - 1 .. x0 + 32) inside a box that starts at x0 - 4
+constexpr int kPatchX = 3;                   // ... because a TMA box must start on a 16-byte boundary of the innermost dimension
 constexpr int kCout = 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,13 +62,15 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8])
                  ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
+struct __align__(128) PatchStage { float v[3][kTileH + 2][kPatchW]; };      // sizeof rounds up to a multiple of 128: a TMA destination
+
 template <bool TMA>
 __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CUtensorMap map_img, const float* __restrict__ img,
                                                       const float* __restrict__ w27, const float* __restrict__ bias, __half* __restrict__ out,
                                                       int batch, int h, int wd, int rows, int out_s2d) {
     __shared__ __align__(1024) uint8_t s_a[2][128 * 64];     // im2col rows, K-major SWIZZLE_64B (double-buffered)
     __shared__ __align__(1024) uint8_t s_b[kCout * 64];      // weights [cout][k], same layout
-    __shared__ __align__(128) float s_patch2[TMA ? 2 : 1][3][kTileH + 2][kPatchW];   // TMA: two stages, the box {36, 6, 3} as it lands
+    __shared__ PatchStage s_patch2[TMA ? 2 : 1];             // TMA: two stages, each the box {36, 6, 3} as it lands (128-byte aligned)
     __shared__ float s_bias[kCout];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ __align__(8) uint64_t s_pfull[2];             // TMA: patch stage filled
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
         p_y[q] = i < kPatchElems ? py - 1 : -(1 << 20);                 // out-of-range slot -> never valid
         p_x[q] = px - 1;
         p_off[q] = (ci * h + py - 1) * wd + px - 1;
-        p_s[q] = (i / 34) * kPatchW + (i % 34);
+        p_s[q] = (i / 34) * kPatchW + (i % 34) + kPatchX;
     }
     const int itotal = (int)total;
     // TMA: one thread asks for the whole patch of a tile; rows / columns outside the image arrive as zeros
@@ -138,7 +141,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kPatchBytes) : "memory");
         asm volatile(
             "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(smem_u32(&s_patch2[stage][0][0][0])), "l"(&map_img), "r"(bar), "r"(tx * kTileW - 1), "r"(ty * kTileH - 1), "r"(0), "r"(n) : "memory");
+            ::"r"(smem_u32(&s_patch2[stage].v[0][0][0])), "l"(&map_img), "r"(bar), "r"(tx * kTileW - (kPatchX + 1)), "r"(ty * kTileH - 1), "r"(0), "r"(n) : "memory");
     };
     auto fetch = [&](int tile, float (&regs)[kPerThread]) {
         const int n = tile / tiles_per_image;
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
     uint32_t pphase[2] = {0, 0};
     // software pipeline: the MMA of tile i is in flight while the epilogue of tile i-1 runs
     for (int tile = blockIdx.x; tile < itotal; tile += gridDim.x) {
-        float (*s_patch)[kTileH + 2][kPatchW] = s_patch2[TMA ? pstage : 0];
+        float (*s_patch)[kTileH + 2][kPatchW] = s_patch2[TMA ? pstage : 0].v;
         if (TMA) {
             // 1. the next tile's patch into the other stage (its last readers -- the gather of the previous tile -- are behind the
             //    second __syncthreads of the previous iteration), then wait for this tile's
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                    for (int ci = 0; ci < 3; ++ci) v[(ky * 3 + kx) * 3 + ci] = s_patch[ci][warp + ky][lane + kx];
+                    for (int ci = 0; ci < 3; ++ci) v[(ky * 3 + kx) * 3 + ci] = s_patch[ci][warp + ky][lane + kx + kPatchX];
 #pragma unroll
             for (int k = 27; k < 32; ++k) v[k] = 0.0f;
 #pragma unroll
