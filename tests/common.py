@@ -169,6 +169,65 @@ def torch_conv_ref(x, w, bias, stride=1, leaky=True, kind=0, residual=None, upad
     return y.float()
 
 
+# ---- trained-like head tensors: piecewise orientation fields with sharp instance boundaries --------
+def trained_like_heads(batch, height, width, seed, num_classes=80, per_image=10):
+    """Head tensors shaped like the model output whose ORIENTATION maps look like a trained OrienMask's: inside an instance every pixel's
+    offset points at the instance centre (eval/orienmask_yolo_postprocess.py:141-166: pix = orien * grid_anchor / 2 + base lands on the
+    centre), outside it is zero -- so a mask boundary is a discontinuity of the field, not a shallow level set of a smooth random one.
+    Instances are non-overlapping ellipses laid out on a jittered grid; each gets the anchor closest to its size, a confident
+    objectness / class logit at its centre cell and the box regression that reproduces its box.  Returns (heads, instances)."""
+    g = np.random.default_rng(seed)
+    anchors = np.asarray(ANCHORS, dtype=np.float64)
+    heads = []
+    for s in (32, 16, 8):
+        nH, nW = height // s, width // s
+        bbox = np.full((batch, 3, 5 + num_classes, nH, nW), -6.0, dtype=np.float32)
+        bbox[:, :, :4] = 0.0
+        bbox[:, :, 4] = -9.0
+        heads.append([bbox, np.zeros((batch, 6, height // 4, width // 4), dtype=np.float32)])
+    cols = int(np.ceil(np.sqrt(per_image)))
+    rows = int(np.ceil(per_image / cols))
+    yy, xx = np.mgrid[0:height // 4, 0:width // 4]
+    py, px = 4.0 * yy + 1.5, 4.0 * xx + 1.5                      # full-resolution position of every low-resolution orientation sample
+    instances = []
+    for b in range(batch):
+        used = set()
+        for k in range(per_image):
+            cell_h, cell_w = height / rows, width / cols
+            r, c = divmod(k, cols)
+            w = g.uniform(0.35, 0.8) * cell_w
+            h = g.uniform(0.35, 0.8) * cell_h
+            cx = (c + 0.5) * cell_w + g.uniform(-0.08, 0.08) * cell_w
+            cy = (r + 0.5) * cell_h + g.uniform(-0.08, 0.08) * cell_h
+            a = int(np.argmin(np.abs(np.log(anchors[:, 0] / w)) + np.abs(np.log(anchors[:, 1] / h))))
+            si = [i for i, m in enumerate(ANCHOR_MASK) if a in m][0]
+            aj = ANCHOR_MASK[si].index(a)
+            if (si, aj, r, c) in used:
+                continue
+            used.add((si, aj, r, c))
+            s = (32, 16, 8)[si]
+            nH, nW = height // s, width // s
+            gx, gy = cx / s, cy / s
+            ix, iy = int(gx), int(gy)
+            cls = int(g.integers(0, num_classes))
+            bbox = heads[si][0]
+            fx, fy = min(max(gx - ix, 0.02), 0.98), min(max(gy - iy, 0.02), 0.98)
+            bbox[b, aj, 0, iy, ix] = np.log(fx / (1 - fx))
+            bbox[b, aj, 1, iy, ix] = np.log(fy / (1 - fy))
+            bbox[b, aj, 2, iy, ix] = np.log(w / anchors[a, 0])
+            bbox[b, aj, 3, iy, ix] = np.log(h / anchors[a, 1])
+            bbox[b, aj, 4, iy, ix] = g.uniform(3.0, 7.0)
+            bbox[b, aj, 5 + cls, iy, ix] = g.uniform(3.0, 7.0)
+            inside = ((px - cx) / (w / 2)) ** 2 + ((py - cy) / (h / 2)) ** 2 < 1.0
+            ga_x, ga_y = anchors[a, 0] / width * nW, anchors[a, 1] / height * nH          # grid_anchors (:21-27)
+            orien = heads[si][1]
+            orien[b, 2 * aj][inside] = ((cx - px[inside]) / width * nW) * 2.0 / ga_x
+            orien[b, 2 * aj + 1][inside] = ((cy - py[inside]) / height * nH) * 2.0 / ga_y
+            instances.append(dict(image=b, cx=cx, cy=cy, w=w, h=h, anchor=a, cls=cls))
+    out = tuple((torch.from_numpy(bb.reshape(batch, -1, bb.shape[-2], bb.shape[-1]).copy()), torch.from_numpy(oo)) for bb, oo in heads)
+    return out, instances
+
+
 # ---- end-to-end agreement with explicit exceptions (SURVEY §8d iii) -------------------------------
 def _iou_centre(a, b):
     """IoU of centre-format boxes a [4], b [n,4] (float64; only used to measure margins)."""

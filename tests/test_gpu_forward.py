@@ -317,6 +317,41 @@ def test_forward_returns_tensors_owned_by_the_caller():
             assert x.data_ptr() != nx.data_ptr() and not torch.equal(x, nx)
 
 
+def test_fp16_engine_error_on_trained_like_heads():
+    """What the fp16 engine's error does to masks when the orientation field looks like a TRAINED network's.
+
+    On the synthetic random weights the orientation maps are smooth random fields and every mask boundary is a shallow level set of
+    them, so fp16 storage noise (head rel-L2 ~1e-3) moves boundaries by whole pixels: mean IoU 0.99 -- and smoothing the INPUT does not
+    help (tools/fp16_emulation.py: a CPU emulation of the engine's rounding points reproduces 0.971 / 0.9905 on noise images and reads
+    0.969 / 0.993 on low-pass images; the limit is fp16 storage itself).  A trained OrienMask is different in kind: inside an instance
+    the field points at the centre, outside it does not, and the mask boundary is that discontinuity.  This test transplants the ACTUAL
+    error field of the fp16 engine (engine heads minus fp32 oracle heads, same weights and images) onto such heads
+    (tests/common.py:trained_like_heads) and runs the post-process on both: boxes / scores move by the head error, kept sets do not
+    change, masks stay at IoU >= 0.999."""
+    import orienmask_b200 as ob
+    from orienmask_b200.synthetic import synthetic_images, synthetic_state_dict
+    from oracle.forward_oracle import forward_oracle
+    from tests.common import e2e_agreement, trained_like_heads
+    x = synthetic_images(2, 544, 544, seed=1)
+    ref_heads = forward_oracle(synthetic_state_dict(0), x)
+    eng_heads = _model('fp16')(x.cuda())
+    err = [((b.cpu() - rb), (o.cpu() - ro)) for (b, o), (rb, ro) in zip(eng_heads, ref_heads)]
+    rel = max(float(e.norm() / r.norm()) for pair_e, pair_r in zip(err, ref_heads) for e, r in zip(pair_e, pair_r))
+    assert 1e-4 < rel < 0.03                                         # it IS the fp16 error field (parity mode would read ~1e-5)
+    clean, instances = trained_like_heads(2, 544, 544, seed=3)
+    noisy = [(b + eb, o + eo) for (b, o), (eb, eo) in zip(clean, err)]
+    ref = _oracle(544, 544, 0.005)([(b.numpy(), o.numpy()) for b, o in clean])
+    post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5),
+                                       device=torch.device('cuda:0'), **post_config(544, 544, 0.005))
+    padded = post.apply_padded([(b.cuda(), o.cuda()) for b, o in noisy])
+    reports = [e2e_agreement(ref[b], padded, b) for b in range(2)]
+    _write_report('fp16_error_on_trained_like_heads.json', {'head_error_rel_l2': rel, 'instances': len(instances), 'images': reports})
+    for rep in reports:
+        assert rep['reference_detections'] == rep['engine_detections'] == rep['matched'] == 10 and rep['exceptions'] == [], rep
+        assert rep['max_box_err'] <= 1e-2 and rep['max_score_err'] <= 1e-2, rep
+        assert rep['aggregate_mask_iou'] >= 0.999 and rep['min_mask_iou'] >= 0.998, rep
+
+
 def test_report_fp16_detection_agreement_544():
     """What the fp16 production engine changes at the OUTPUT of the path: detections of two 544x544 images against the oracle
     (fp32 forward + post-process on the host), matched by class and box.  Writes gpurun_out/fp16_agreement.json; the gate is
@@ -352,6 +387,9 @@ def test_report_fp16_detection_agreement_544():
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'fp16_agreement.json'), 'w'), indent=1)
     print(json.dumps(rows))
+    # gates = what the CPU emulation of the engine's rounding points predicts for fp16 storage on these weights (tools/fp16_emulation.py:
+    # 98-100 of 100 matched, score error 3-6e-4, box error 2-8e-3, mask IoU mean 0.990-0.994 / min 0.956-0.973)
     for row in rows:
-        assert row['matched'] >= 0.7 * row['reference_detections'], row
-        assert row['max_score_err'] < 2e-2 and row['mean_mask_iou'] > 0.95, row
+        assert row['matched'] >= 0.95 * row['reference_detections'], row
+        assert row['max_score_err'] < 2e-3 and row['max_box_err'] <= 5e-3, row
+        assert row['mean_mask_iou'] > 0.985 and row['min_mask_iou'] > 0.95, row
