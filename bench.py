@@ -52,12 +52,13 @@ def measured_peaks():
 def measured_traffic():
     """DRAM bytes (read + write) of the conv-engine launches of one bs-32 step from the committed ncu pass
     (tools/traffic_report.py -> profiles/r01_traffic.json); None when no capture is committed."""
-    path = os.path.join(ROOT, 'profiles', 'r01_traffic.json')
-    try:
-        f = json.load(open(path))['conv_engine']
-        return {'bytes': f['dram_read'] + f['dram_write'], 'launches': f['launches']}
-    except Exception:
-        return None
+    for name in ('r02_traffic.json', 'r01_traffic.json'):
+        try:
+            f = json.load(open(os.path.join(ROOT, 'profiles', name)))['conv_engine']
+            return {'bytes': f['dram_read'] + f['dram_write'], 'launches': f['launches'], 'file': 'profiles/' + name}
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -622,9 +623,9 @@ def main():
                          'frac': achieved / peaks['tflops'], 'traffic': traffic['bytes'] if traffic else None,
                          'traffic_algorithmic': algo_bytes,
                          'traffic_note': ('ncu dram__bytes_read+write summed over the %d conv-engine launches of one step '
-                                          '(profiles/r01_traffic.json); traffic_algorithmic = the un-fused per-layer in + out + weight bytes of the same launches '
+                                          '(%s); traffic_algorithmic = the un-fused per-layer in + out + weight bytes of the same launches '
                                           '(measured < algorithmic: consecutive layers hit in the 126 MB L2)'
-                                          % traffic['launches']) if traffic else None,
+                                          % (traffic['launches'], traffic['file'])) if traffic else None,
                          'kernel': 'conv engine = the model forward: 94 conv_tc2_kernel launches (tcgen05 cta_group::2) + stem_tc_kernel, '
                                    '%.3f ms of %.3f ms per step' % (fwd_ms, total_ms / args.steps),
                          'algorithmic': '%.3f GFLOP/image x %d images per forward' % (GFLOP_PER_IMAGE, B),

@@ -71,7 +71,19 @@ typedef struct om_post_config {
     float orien_thresh;
     int32_t nms_pre;                            /* <= 1024                                        */
     int32_t nms_post;                           /* <= nms_pre                                     */
+    int32_t nms_semantics;                      /* OM_NMS_CPU (default, 0) or OM_NMS_CUDA         */
 } om_post_config;
+
+/* The reference ships TWO native NMS variants that differ at exact ties with the threshold and in result order:
+ *   OM_NMS_CPU   eval/src/nms_cpu.cpp:4-63   IoU >= threshold suppresses, areas (x2-x1)*(y2-y1) from the corners, survivors returned as
+ *                ascending original indices -- what the reference runs on CPU tensors, and the variant this repo's oracle is pinned to
+ *                (the compiled reference file itself, oracle/_ref);
+ *   OM_NMS_CUDA  eval/src/nms_kernel.cu:13-23,58-62,136-139   IoU > threshold suppresses, areas w*h, survivors returned in
+ *                score-descending order -- what the reference runs on CUDA tensors (eval/function.py:70-74,98-101).  That file does
+ *                not build against torch >= 1.11 (THC), so this mode is checked against a restatement only (oracle/nms_oracle.c);
+ *                pairs within an ulp of the threshold may round differently from a binary of the original (FMA contraction unknown). */
+#define OM_NMS_CPU 0
+#define OM_NMS_CUDA 1
 
 /* Bytes of device scratch om_decode_select needs for `batch` images: 16 bytes per (prediction, class) pair and image
  * (candidate keys + flat indices, edge list) plus the radix state -- every pair may clear conf_thresh. */
@@ -126,6 +138,8 @@ int32_t om_mask_assemble(const om_post_config* cfg, const float* const* orien, c
  *   keep [n]   device int64, out: surviving indices in ascending order (nms_cpu.cpp:62); *keep_count device int32
  */
 int32_t om_nms(const float* dets, int32_t n, float threshold, int64_t* keep, int32_t* keep_count, void* stream);
+/* Same with the variant chosen: OM_NMS_CPU (= om_nms) or OM_NMS_CUDA (keep is then in score-descending order). */
+int32_t om_nms_ex(const float* dets, int32_t n, float threshold, int32_t semantics, int64_t* keep, int32_t* keep_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Convolution engine                                                                            */

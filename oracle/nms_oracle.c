@@ -66,3 +66,42 @@ int32_t om_oracle_nms(const float* dets, int32_t n, float threshold, int64_t* ke
     free(x1); free(order); free(dead);
     return k;
 }
+
+/*
+ * The reference's OTHER native variant, eval/src/nms_kernel.cu (what it runs on CUDA tensors):
+ *   - IoU from centre-format boxes: corners cx -/+ w/2, areas Sa = w * h directly            (:13-23)
+ *   - boxes visited in score-descending order (scores.sort(0, descending=true), :88-90)
+ *   - a later box is suppressed by a kept earlier one iff IoU > threshold (strict)           (:58)
+ *   - result = kept boxes in that score-descending order (order_t.index(keep), :136-139)
+ * The file cannot be compiled against torch >= 1.11 (THC headers), so unlike om_oracle_nms this restatement is NOT pinned against a
+ * binary of the original; single-rounded fp32 like the rest (the original's FMA contraction is unknown).
+ */
+int32_t om_oracle_nms_cuda(const float* dets, int32_t n, float threshold, int64_t* keep) {
+    if (n <= 0) return 0;
+    om_key* order = (om_key*)malloc(sizeof(om_key) * (size_t)n);
+    uint8_t* dead = (uint8_t*)calloc((size_t)n, 1);
+    for (int32_t i = 0; i < n; ++i) { order[i].s = dets[5 * (size_t)i + 4]; order[i].i = i; }
+    qsort(order, (size_t)n, sizeof(om_key), cmp_desc);
+    int32_t k = 0;
+    for (int32_t a = 0; a < n; ++a) {
+        int32_t i = order[a].i;
+        if (dead[i]) continue;
+        keep[k++] = i;
+        const float* p = dets + 5 * (size_t)i;
+        for (int32_t b = a + 1; b < n; ++b) {
+            int32_t j = order[b].i;
+            if (dead[j]) continue;
+            const float* q = dets + 5 * (size_t)j;
+            float l1 = p[0] - p[2] / 2, l2 = q[0] - q[2] / 2, r1 = p[0] + p[2] / 2, r2 = q[0] + q[2] / 2;
+            float t1 = p[1] - p[3] / 2, t2 = q[1] - q[3] / 2, b1 = p[1] + p[3] / 2, b2 = q[1] + q[3] / 2;
+            float left = l1 > l2 ? l1 : l2, right = r1 < r2 ? r1 : r2, top = t1 > t2 ? t1 : t2, bottom = b1 < b2 ? b1 : b2;
+            float w = right - left; if (w < 0.f) w = 0.f;
+            float h = bottom - top; if (h < 0.f) h = 0.f;
+            float inter = w * h;
+            float sa = p[2] * p[3], sb = q[2] * q[3];
+            if (inter / (sa + sb - inter) > threshold) dead[j] = 1;
+        }
+    }
+    free(order); free(dead);
+    return k;
+}

@@ -44,19 +44,23 @@ def _lib():
         _LIB = ctypes.CDLL(build_c_oracle())
         _LIB.om_oracle_nms.restype = ctypes.c_int32
         _LIB.om_oracle_nms.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]
+        _LIB.om_oracle_nms_cuda.restype = ctypes.c_int32
+        _LIB.om_oracle_nms_cuda.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]
     return _LIB
 
 
-def nms_oracle(dets, threshold):
-    """Greedy NMS, eval/src/nms_cpu.cpp:4-63 semantics. dets [n,5] fp32 -> ascending kept indices."""
+def nms_oracle(dets, threshold, semantics='cpu'):
+    """Greedy NMS. semantics='cpu': eval/src/nms_cpu.cpp:4-63 (>=, ascending kept indices); 'cuda': eval/src/nms_kernel.cu (>, areas
+    w*h, kept indices in score-descending order).  dets [n,5] fp32."""
     dets = np.ascontiguousarray(dets, dtype=f32)
     n = dets.shape[0]
     keep = np.empty(max(n, 1), dtype=np.int64)
-    k = _lib().om_oracle_nms(dets.ctypes.data, n, ctypes.c_float(threshold), keep.ctypes.data)
+    fn = _lib().om_oracle_nms_cuda if semantics == 'cuda' else _lib().om_oracle_nms
+    k = fn(dets.ctypes.data, n, ctypes.c_float(threshold), keep.ctypes.data)
     return keep[:k].copy()
 
 
-def batched_nms_oracle(dets, cats, threshold=0.5):
+def batched_nms_oracle(dets, cats, threshold=0.5, semantics='cpu'):
     """eval/function.py:77-103 with normalized=True: centres shifted by cls*(1.5+0.5) in fp32."""
     if dets.shape[0] == 0:
         return np.zeros(0, dtype=np.int64)
@@ -64,7 +68,7 @@ def batched_nms_oracle(dets, cats, threshold=0.5):
     off = cats.astype(f32) * f32(2.0)
     shifted[:, 0] = shifted[:, 0] + off
     shifted[:, 1] = shifted[:, 1] + off
-    return nms_oracle(shifted, threshold)
+    return nms_oracle(shifted, threshold, semantics)
 
 
 def _threads(fn, items):
@@ -121,7 +125,8 @@ class PostProcessOracle:
     """Restatement of OrienMaskYOLOPostProcess (:8-166) on numpy arrays, one image at a time."""
 
     def __init__(self, grid_size, image_size, anchors, anchor_mask, num_classes,
-                 conf_thresh=0.05, nms_threshold=0.5, nms_pre=400, nms_post=100, orien_thresh=0.3):
+                 conf_thresh=0.05, nms_threshold=0.5, nms_pre=400, nms_post=100, orien_thresh=0.3, nms_semantics='cpu'):
+        self.nms_semantics = nms_semantics
         self.grid = [(int(g[0]), int(g[1])) for g in grid_size]            # (nH, nW) per scale
         if isinstance(image_size, (list, tuple)):
             self.H, self.W = int(image_size[0]), int(image_size[1])
@@ -195,7 +200,7 @@ class PostProcessOracle:
     # -- :146-166 ---------------------------------------------------------------------------
     def finish(self, coord, score, cls, anchor, pix):
         dets = np.concatenate([coord, score[:, None]], 1).astype(f32)
-        keep = batched_nms_oracle(dets, cls, self.nms_threshold)
+        keep = batched_nms_oracle(dets, cls, self.nms_threshold, self.nms_semantics)
         if keep.size > self.nms_post:
             s = dets[keep, 4]
             top = np.lexsort((keep, -s.astype(np.float64)))[:self.nms_post]

@@ -14,6 +14,7 @@ OM_MAX_SCALES = 4
 OM_MAX_ANCHORS = 16
 PREC_F32, PREC_F16, PREC_SPLIT = 0, 1, 2
 OUT_ACT, OUT_PARTIAL, OUT_NCHW = 0, 1, 2
+NMS_CPU, NMS_CUDA = 0, 1
 
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
@@ -25,7 +26,7 @@ class PostConfig(ctypes.Structure):
         ('anchors_per_scale', c_i32 * OM_MAX_SCALES), ('anchor_index', (c_i32 * 4) * OM_MAX_SCALES),
         ('total_anchors', c_i32), ('anchor_w', c_f32 * OM_MAX_ANCHORS), ('anchor_h', c_f32 * OM_MAX_ANCHORS),
         ('conf_thresh', c_f32), ('nms_thresh', c_f32), ('orien_thresh', c_f32),
-        ('nms_pre', c_i32), ('nms_post', c_i32),
+        ('nms_pre', c_i32), ('nms_post', c_i32), ('nms_semantics', c_i32),
     ]
 
 
@@ -90,6 +91,7 @@ SIGNATURES = {
     'om_mask_assemble': (c_i32, [ctypes.POINTER(PostConfig), ctypes.POINTER(c_vp), ctypes.POINTER(c_i64),
                                  c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     'om_nms': (c_i32, [c_vp, c_i32, c_f32, c_vp, c_vp, c_vp]),
+    'om_nms_ex': (c_i32, [c_vp, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp]),
     'om_conv_create': (c_i32, [ctypes.POINTER(ConvDesc), ctypes.POINTER(c_vp)]),
     'om_conv_run': (c_i32, [c_vp, c_vp]),
     'om_conv_run_to': (c_i32, [c_vp, c_vp, c_vp]),

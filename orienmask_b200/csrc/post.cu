@@ -397,6 +397,8 @@ struct NmsArgs {
     const int* counts;        // [batch] or null -> n
     int n, cap, NP, nms_post;
     float thr;
+    int mode;                 // OM_NMS_CPU: nms_cpu.cpp (>= suppresses, areas from corners, ascending-index result);
+                              // OM_NMS_CUDA: nms_kernel.cu (> suppresses, areas w*h, score-descending result)
     // batched outputs
     int* det_count; float* det; long long* det_cls; int* det_anchor; int* det_keep;
     float* records;                 // optional [batch, nms_post*6 + 1]: (cx, cy, w, h, score, cls) per slot, then the count -- the row a rank all-gathers
@@ -474,7 +476,8 @@ __global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
         const float hw = dets[p * 5 + 2] / 2.0f, hh = dets[p * 5 + 3] / 2.0f;
         const float x1 = x - hw, y1 = y - hh, x2 = x + hw, y2 = y + hh;
         gx1[r] = x1; gy1[r] = y1; gx2[r] = x2; gy2[r] = y2;
-        gar[r] = (x2 - x1) * (y2 - y1);
+        gar[r] = a.mode == OM_NMS_CUDA ? dets[p * 5 + 2] * dets[p * 5 + 3]          // nms_kernel.cu:20-21: Sa = a[2] * a[3]
+                                       : (x2 - x1) * (y2 - y1);                      // nms_cpu.cpp:22
         kept_rank[r] = 0; kept_pos[r] = 0;
     }
     __syncthreads();
@@ -503,7 +506,7 @@ __global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
                     // neither of which reaches a positive threshold -- skip the IEEE division
                     if (inter == 0.0f && a.thr > 0.0f) continue;
                     const float ovr = inter / (ia + gar[j] - inter);
-                    if (j > r && ovr >= a.thr) bits |= 1u << bb;
+                    if (j > r && (a.mode == OM_NMS_CUDA ? ovr > a.thr : ovr >= a.thr)) bits |= 1u << bb;   // nms_kernel.cu:58 / nms_cpu.cpp:59
                 }
             }
             mask[r * nw + wd] = bits;
@@ -544,8 +547,10 @@ __global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
     __syncthreads();
 
     int total = compact_slots(kept_rank, n, slot, chunk_off);
-    const bool topk = BATCHED && total > a.nms_post;
-    if (!topk) {                                   // ascending original index (nms_cpu.cpp:62)
+    // result order: score-descending ranks after a post-NMS top-k (postprocess.py:150-154) and always under nms_kernel.cu semantics
+    // (:136-139, order_t.index(keep)); ascending original index otherwise (nms_cpu.cpp:62)
+    const bool topk = (BATCHED && total > a.nms_post) || a.mode == OM_NMS_CUDA;
+    if (!topk) {
         for (int r = threadIdx.x; r < n; r += blockDim.x)
             if (kept_rank[r]) kept_pos[(int)(skey[r] & 0xffffffffu)] = 1;
         total = compact_slots(kept_pos, n, slot, chunk_off);
@@ -582,8 +587,10 @@ __global__ void __launch_bounds__(512) nms_kernel(NmsArgs a, PostDev d) {
         }
     } else {
         if (threadIdx.x == 0) *a.keep_count = n_out;
-        for (int e = threadIdx.x; e < n; e += blockDim.x)
-            if (kept_pos[e]) a.keep[slot[e]] = e;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            if (topk) { if (kept_rank[e]) a.keep[slot[e]] = (long long)(skey[e] & 0xffffffffu); }
+            else if (kept_pos[e]) a.keep[slot[e]] = e;
+        }
     }
 }
 
@@ -856,6 +863,7 @@ extern "C" int32_t om_batched_nms(const om_post_config* cfg, const int32_t* cand
     NmsArgs a{};
     a.dets = cand_det; a.cls = cand_cls; a.pred = cand_pred; a.counts = cand_count;
     a.n = 0; a.cap = d.nms_pre; a.NP = d.NP; a.nms_post = d.nms_post; a.thr = d.nms_thresh;
+    a.mode = cfg->nms_semantics == OM_NMS_CUDA ? OM_NMS_CUDA : OM_NMS_CPU;
     a.det_count = det_count; a.det = det; a.det_cls = reinterpret_cast<long long*>(det_cls);
     a.det_anchor = det_anchor; a.det_keep = det_keep; a.records = records;
     const size_t smem = nms_smem_bytes(a.NP, a.cap);
@@ -865,14 +873,19 @@ extern "C" int32_t om_batched_nms(const om_post_config* cfg, const int32_t* cand
 }
 
 extern "C" int32_t om_nms(const float* dets, int32_t n, float threshold, int64_t* keep, int32_t* keep_count, void* stream) {
+    return om_nms_ex(dets, n, threshold, OM_NMS_CPU, keep, keep_count, stream);
+}
+
+extern "C" int32_t om_nms_ex(const float* dets, int32_t n, float threshold, int32_t semantics, int64_t* keep, int32_t* keep_count, void* stream) {
     if (n < 0 || n > 1024) return om::fail(OM_ERR_INVALID, "om_nms: n=%d outside [0, 1024]", n);
+    if (semantics != OM_NMS_CPU && semantics != OM_NMS_CUDA) return om::fail(OM_ERR_INVALID, "om_nms: unknown semantics %d", semantics);
     if (!keep_count || (n > 0 && (!dets || !keep))) return om::fail(OM_ERR_INVALID, "om_nms: null argument");
     if (n == 0) {
         OM_CUDA_TRY(cudaMemsetAsync(keep_count, 0, sizeof(int32_t), (cudaStream_t)stream));
         return OM_OK;
     }
     NmsArgs a{};
-    a.dets = dets; a.n = n; a.cap = n; a.NP = next_pow2(n); a.nms_post = n; a.thr = threshold;
+    a.dets = dets; a.n = n; a.cap = n; a.NP = next_pow2(n); a.nms_post = n; a.thr = threshold; a.mode = semantics;
     a.keep = reinterpret_cast<long long*>(keep); a.keep_count = keep_count;
     PostDev d;
     memset(&d, 0, sizeof(d));

@@ -60,7 +60,7 @@ class OrienMaskYOLOPostProcess:
         self.conf_thresh, self.nms_pre, self.nms_post = float(conf_thresh), int(nms_pre), int(nms_post)
         self.orien_thresh = float(orien_thresh)
         self.nms = nms_func if nms_func is not None else batched_nms
-        self.nms_thresh = self._resolve_nms(self.nms)
+        self.nms_thresh, self.nms_semantics = self._resolve_nms(self.nms)
         if len(self.grid_size) > _lib.OM_MAX_SCALES or len(self.anchors) > _lib.OM_MAX_ANCHORS:
             raise ValueError('at most %d scales and %d anchors are supported' % (_lib.OM_MAX_SCALES, _lib.OM_MAX_ANCHORS))
         cfg = _lib.PostConfig()
@@ -77,6 +77,7 @@ class OrienMaskYOLOPostProcess:
             cfg.anchor_w[a], cfg.anchor_h[a] = w, h
         cfg.conf_thresh, cfg.nms_thresh, cfg.orien_thresh = self.conf_thresh, self.nms_thresh, self.orien_thresh
         cfg.nms_pre, cfg.nms_post = self.nms_pre, self.nms_post
+        cfg.nms_semantics = self.nms_semantics
         self._cfg = cfg
 
     @staticmethod
@@ -87,7 +88,8 @@ class OrienMaskYOLOPostProcess:
         if isinstance(func, functools.partial):
             base, kw = func.func, dict(func.keywords)
         if base is batched_nms and kw.get('normalized', True):
-            return float(kw.get('threshold', 0.5))
+            from .function import _mode
+            return float(kw.get('threshold', 0.5)), _mode(kw.get('semantics'))
         raise NotImplementedError(
             'orienmask_b200 fuses class-wise NMS into the batched kernel; nms_func must be '
             'orienmask_b200.function.batched_nms (optionally functools.partial with threshold=...), got %r' % (func,))

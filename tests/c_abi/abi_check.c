@@ -15,7 +15,7 @@ int main(void) {
     typedef void (*fn)(void);
     fn entry[] = {(fn)om_abi_version, (fn)om_last_error, (fn)om_launch_count, (fn)om_launch_count_reset,
                   (fn)om_post_workspace_bytes, (fn)om_decode_select, (fn)om_batched_nms, (fn)om_mask_assemble,
-                  (fn)om_nms, (fn)om_conv_create, (fn)om_conv_run, (fn)om_conv_run_to, (fn)om_conv_destroy,
+                  (fn)om_nms, (fn)om_nms_ex, (fn)om_conv_create, (fn)om_conv_run, (fn)om_conv_run_to, (fn)om_conv_destroy,
                   (fn)om_stem_conv, (fn)om_preprocess, (fn)om_mask_rle, (fn)om_mask_areas, (fn)om_mask_blend,
                   (fn)om_debug_conv_plan_info, (fn)om_debug_conv_timeline, (fn)om_engine_workspace_bytes, (fn)om_engine_create,
                   (fn)om_forward, (fn)om_engine_destroy, (fn)om_engine_layer_count, (fn)om_engine_layer_info, (fn)om_engine_run_layer};

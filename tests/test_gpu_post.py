@@ -173,3 +173,37 @@ def test_nms_kernel_writes_the_gather_records():
     assert torch.equal(out.packed, pack_records(out.det, out.cls, out.count))
     det, cls, cnt = unpack_records(out.packed, post.nms_post)
     assert torch.equal(det, out.det) and torch.equal(cls, out.cls) and torch.equal(cnt, out.count)
+
+
+def test_nms_cuda_semantics_mode():
+    """OM_NMS_CUDA (eval/src/nms_kernel.cu: '>' suppression, w*h areas, score-descending result) through nms(), batched_nms() and the
+    whole post-process, against the oracle's restatement of that file; exact-threshold ties separate the two variants."""
+    import orienmask_b200 as ob
+    from oracle.post_oracle import nms_oracle, batched_nms_oracle
+    g = torch.Generator().manual_seed(7)
+    for n in (1, 33, 400, 1000):
+        dets = torch.cat([torch.rand(n, 2, generator=g), torch.rand(n, 2, generator=g) * 0.3 + 0.02, torch.rand(n, 1, generator=g)], 1)
+        cats = torch.randint(0, 4, (n,), generator=g)
+        _, _, keep = ob.nms(dets.cuda(), cats.cuda(), 0.5, semantics='cuda')
+        assert np.array_equal(keep.cpu().numpy(), nms_oracle(dets.numpy(), 0.5, semantics='cuda')), n
+        d, c, keep = ob.batched_nms(dets.cuda(), cats.cuda(), threshold=0.5, semantics='cuda')
+        ref = batched_nms_oracle(dets.numpy(), cats.numpy(), 0.5, semantics='cuda')
+        assert np.array_equal(keep.cpu().numpy(), ref) and torch.equal(d.cpu(), dets[keep.cpu()])
+    # an exact tie with the threshold: two unit squares overlapping by one third -> IoU = (1/3) / (2 - 1/3) = 0.2 exactly representable? use 0.5:
+    # boxes [0,0,1,1] and [0.5... ] -> choose w=h=1 boxes shifted by 1/3 in x: inter 2/3, union 4/3 -> IoU exactly 0.5
+    tie = torch.tensor([[0.5, 0.5, 1.0, 1.0, 0.9], [0.5 + 1.0 / 3.0, 0.5, 1.0, 1.0, 0.8]])
+    iou_ref = nms_oracle(tie.numpy(), 0.5, semantics='cuda'), nms_oracle(tie.numpy(), 0.5, semantics='cpu')
+    _, _, k_cuda = ob.nms(tie.cuda(), torch.zeros(2, dtype=torch.long).cuda(), 0.5, semantics='cuda')
+    _, _, k_cpu = ob.nms(tie.cuda(), torch.zeros(2, dtype=torch.long).cuda(), 0.5, semantics='cpu')
+    assert np.array_equal(k_cuda.cpu().numpy(), iou_ref[0]) and np.array_equal(k_cpu.cpu().numpy(), iou_ref[1])
+    # whole post-process
+    import functools
+    heads = synthetic_heads(2, 64, 96, seed=5)
+    cfg = post_config(64, 96, 0.005)
+    post = ob.OrienMaskYOLOPostProcess(nms_func=functools.partial(ob.batched_nms, threshold=0.5, semantics='cuda'), device=torch.device('cuda:0'), **cfg)
+    from oracle.post_oracle import PostProcessOracle
+    ref = PostProcessOracle(cfg['grid_size'], cfg['image_size'], cfg['anchors'], cfg['anchor_mask'], 80, conf_thresh=0.005, nms_semantics='cuda')(
+        [(b.numpy(), o.numpy()) for b, o in heads])
+    res = post([(b.cuda(), o.cuda()) for b, o in heads])
+    for b in range(2):
+        _compare(res[b], ref[b]['bbox'], ref[b]['cls'], ref[b]['mask'], ordered=True)

@@ -123,7 +123,7 @@ def _gate(rep, what):
     assert rep['records_engine'] == rep['records_oracle'], rep
     assert rep['matched'] >= rep['records_oracle'] - 4 and len(rep['unmatched']) <= 4, rep      # margin-limited kept-set flips, listed
     assert rep['max_box_err_rel'] <= 1e-3 and rep['max_score_err'] <= 1e-3, rep
-    assert rep['aggregate_mask_iou'] >= 0.999 and rep['min_mask_iou'] >= 0.995 and rep['masks_off'] <= 0.1 * rep['matched'], rep
+    assert rep['aggregate_mask_iou'] >= 0.9995 and rep['min_mask_iou'] >= 0.995 and rep['masks_off'] <= 2, rep
 
 
 def _run_infer(tmp_path, precision):
