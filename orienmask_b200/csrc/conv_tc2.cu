@@ -1124,6 +1124,13 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
             if (p.h_stages < 2) p.b_resident = 0, p.h_stages = 2;
         }
     }
+    if (split && p.halo && p.h_stages == 2 && !(getenv("ORIENMASK_B200_HSTAGES")) &&
+        kMaxSmem - fixed - 2 * p.h_stage_bytes < 4 * sub_bytes && kMaxSmem - fixed - p.h_stage_bytes >= 4 * sub_bytes) {
+        // split precision doubles the halo (hi | lo chunks): two halo stages of a 128-channel layer leave room for two weight blocks only,
+        // and the MMA warp then waits on a barrier round trip per block (ncu, 3x3 128->256 @136x136: tensor pipe 50 % active).  One halo
+        // stage + a deep weight ring keeps the tensor pipe fed; the price is one exposed halo load per tile (~2 us of ~28 us).
+        p.h_stages = 1;
+    }
     const int ring_budget = kMaxSmem - fixed - p.h_stages * p.h_stage_bytes;
     if (ring_budget < 2 * sub_bytes) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
     // blocks per stage: enough MMA cycles behind each barrier round trip (>= ~1024 tensor cycles; one block issues

@@ -7,7 +7,7 @@ if [[ $what == *tests* ]]; then
   for f in test_gpu_conv test_gpu_post test_gpu_forward test_prep test_coco_format test_visualizer test_gpu_eager_bar test_gpu_reference_dropin; do
     timeout 1500 python -m pytest tests/$f.py -q -m gpu --timeout 1200 > gpurun_out/$f.log 2>&1; echo "$f: $(tail -1 gpurun_out/$f.log)"; grep -E "^(FAILED|ERROR)" gpurun_out/$f.log | head
   done
-  ORIENMASK_B200_QUEUED=1 timeout 900 python -m pytest tests/test_gpu_queued.py -q -m gpu > gpurun_out/test_gpu_queued.log 2>&1; echo "queued: $(tail -1 gpurun_out/test_gpu_queued.log)"
+  timeout 900 python -m pytest tests/test_gpu_shapes.py -q -m gpu > gpurun_out/test_gpu_shapes.log 2>&1; echo "shapes: $(tail -1 gpurun_out/test_gpu_shapes.log)"
 fi
 if [[ $what == *bench* ]]; then
   timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -3 gpurun_out/bench.err
