@@ -26,6 +26,7 @@ UNITS = [
     ('conv_f32.cu', []),
     ('conv_tc2.cu', []),
     ('conv_stem_tc.cu', []),
+    ('dark_block.cu', []),
 ]
 
 

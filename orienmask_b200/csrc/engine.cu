@@ -45,6 +45,9 @@ struct Layer {
     bool is_stem = false;
     const float* stem_w = nullptr;
     const float* stem_b = nullptr;
+    bool is_block = false;      // fused DarkNet block (dark_block.cu): desc.input = x, desc.output = out, the two weight sets below
+    const void* blk_w1 = nullptr; const void* blk_w2 = nullptr;
+    const float* blk_b1 = nullptr; const float* blk_b2 = nullptr;
     double flops = 0, bytes = 0;
     char shape[96];
 };
@@ -253,6 +256,35 @@ struct om_engine {
         layers.push_back(L);
     }
 
+    void layers_pop_conv() {
+        if (layers.empty()) return;
+        if (layers.back().conv) om_conv_destroy(layers.back().conv);
+        layers.pop_back();
+    }
+
+    // Fused residual block x -> x + conv3x3(conv1x1(x)) with C squeezed channels, output into `dst` (never in place: neighbouring tiles
+    // read each other's x halo)
+    void block(const std::string& prefix, const Buf& x, int c, const Buf& dst) {
+        if (rc != OM_OK) return;
+        Layer L;
+        L.name = prefix + " (fused block)";
+        L.is_block = true;
+        om_conv_desc& d = L.desc;
+        memset(&d, 0, sizeof(d));
+        d.precision = cfg.precision; d.batch = cfg.batch;
+        d.in_h = d.out_h = cfg.height / x.stride; d.in_w = d.out_w = cfg.width / x.stride; d.in_rows = d.out_rows = rows(x.stride);
+        d.cin = d.cout = 2 * c; d.ksize = 3; d.stride = 1; d.leaky = 1; d.out_kind = OM_OUT_ACT; d.cout_stride = 2 * c;
+        d.input = x.ptr; d.output = dst.ptr; d.residual = x.ptr; d.out_s2d = dst.s2d ? 1 : 0;
+        float sc;
+        if (!weights(prefix + ".conv.0", true, c, 2 * c, 0, 2 * c, 1, true, &L.blk_w1, &L.blk_b1, &sc, OM_PREC_F16) && !sizing) return;
+        if (!weights(prefix + ".conv.1", true, 2 * c, c, 0, c, 3, true, &L.blk_w2, &L.blk_b2, &sc, OM_PREC_F16) && !sizing) return;
+        const double px = (double)d.batch * d.out_h * d.out_w;
+        L.flops = 2.0 * px * (2.0 * c * c + 9.0 * c * 2 * c);
+        L.bytes = px * (2 * c) * 2 * 2 + (2.0 * c * c + 18.0 * c * c) * 2;        // x read once, output written once, weights
+        snprintf(L.shape, sizeof(L.shape), "1x1 %d->%d + 3x3 %d->%d @%dx%d +res fused", 2 * c, c, c, 2 * c, d.out_h, d.out_w);
+        layers.push_back(L);
+    }
+
     void cbl(const std::string& prefix, const Buf& src, int cin, int cout, const Buf& dst, int k, int stride = 1, const Buf* residual = nullptr) {
         conv(prefix, prefix, true, src, cin, 0, cin, cout, &dst, k, stride, true, OM_OUT_ACT, residual, nullptr, true, -1);
     }
@@ -318,7 +350,13 @@ struct om_engine {
                 cbl(blk + ".conv.0", x, 2 * c, c, y, 1);
                 if (i == 0 && b == n) {                          // feeds only conv3.0 (stride 2): written parity-split
                     Buf xs = act(st, 2 * c, false, true);
-                    cbl(blk + ".conv.1", y, c, 2 * c, xs, 3, 1, &x);
+                    if (cfg.precision == OM_PREC_F16 && om::dark_block_supported(2 * c, c, cfg.width / st, rows(st))) {
+                        // the whole block in one launch (dark_block.cu): the 1x1 was emitted above as a separate layer -- replace it
+                        layers_pop_conv();
+                        block(blk, x, c, xs);
+                    } else {
+                        cbl(blk + ".conv.1", y, c, 2 * c, xs, 3, 1, &x);
+                    }
                     x = xs;
                 } else {
                     cbl(blk + ".conv.1", y, c, 2 * c, x, 3, 1, &x);   // in place: x += leaky(conv(y))
@@ -447,6 +485,9 @@ static int32_t run_layer(const om_engine* e, const Layer& L, const float* image,
         return om_stem_conv(e->cfg.precision, image, L.stem_w, L.stem_b, L.desc.output, e->cfg.batch, e->cfg.height, e->cfg.width, L.desc.in_rows, 32,
                             1, st);
     }
+    if (L.is_block)
+        return om::dark_block_run(L.desc.input, L.blk_w1, L.blk_b1, L.blk_w2, L.blk_b2, L.desc.output, e->cfg.batch, L.desc.out_h, L.desc.out_w,
+                                  L.desc.out_rows, L.desc.out_s2d, st);
     if (L.head_slot >= 0) {
         void* dst = L.head_slot < 3 ? (bbox ? (void*)bbox[L.head_slot] : nullptr) : (void*)orien;
         if (!dst) return om::fail(OM_ERR_INVALID, "om_forward: null output pointer for head %d", L.head_slot);
