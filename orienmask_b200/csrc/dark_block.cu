@@ -20,9 +20,11 @@
 // the result is bit-identical to them -- tests/test_gpu_forward.py::test_c_engine_matches_the_python_schedule compares the C engine (this
 // kernel) with the Python-scheduled twin (two conv_tc2 launches) head for head.
 //
-// One CTA = one tile at a time, phases in sequence; overlap comes from two co-resident CTAs per SM (100 KB of shared memory, 128 TMEM
-// columns, 256 threads each) and from the x halo of the next tile being in flight during the current one.  Only C = 32 fits this
-// form: with C = 64 (stage conv3) the resident W2 alone is 147 KB ("Next kernel step").
+// A tile runs its phases in sequence on a STREAM of 256 threads (8 warps); one CTA per SM carries kStreams = 3 independent streams that
+// share the resident weights (40 KB) and own their x stages (2 x 23 KB), y tile (12 KB), 128 TMEM columns, mbarriers and a named barrier
+// each -- the phases of different tiles overlap across streams, and the x halo of a stream's next tile is in flight during its current
+// one.  (Two separate CTAs of one stream each -- the first version -- duplicate the weights: 100 KB per CTA, 2 per SM: 242 us; three
+// streams: see DESIGN.md.)  Only C = 32 fits this form: with C = 64 (stage conv3) the resident W2 alone is 147 KB.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -38,12 +40,15 @@ constexpr int kC = 32;                       // squeezed channels; the block's i
 constexpr int kTW = 8, kTH = 16;             // output tile (128 pixels = one M = 128 MMA)
 constexpr int kHW = kTW + 2, kHH = kTH + 2;  // halo 10 x 18 = 180 pixels
 constexpr int kHalo = kHW * kHH;
-constexpr int kThreads = 256;
+constexpr int kStreams = 3;                  // independent tile pipelines per CTA
+constexpr int kStreamThreads = 256;
+constexpr int kThreads = kStreams * kStreamThreads;
 constexpr int kXStage = ((kHalo * 128 + 1023) / 1024) * 1024;      // 23552 B
 constexpr int kYBytes = ((kHalo * 64 + 1023) / 1024) * 1024;       // 12288 B
 constexpr int kW1Bytes = kC * 128;                                 // [32 rows (cout)][64 k] fp16, SWIZZLE_128B
 constexpr int kW2Bytes = 9 * 2 * kC * 64;                          // [9][64 rows (cout)][32 k] fp16, SWIZZLE_64B
-constexpr int kSmem = 1024 + 2 * kXStage + kYBytes + kW1Bytes + kW2Bytes + 1024;
+constexpr int kStreamBytes = 2 * kXStage + kYBytes;
+constexpr int kSmem = 1024 + kStreams * kStreamBytes + kW1Bytes + kW2Bytes + 1024;
 
 struct BlockParams {
     int tiles_x, tiles_y;
@@ -102,45 +107,52 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8])
                  ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__device__ __forceinline__ void stream_sync(int stream) {                 // named barrier of one stream (0 is __syncthreads)
+    asm volatile("bar.sync %0, %1;" ::"r"(stream + 1), "r"(kStreamThreads) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* s_x = smem;                                 // [2][kXStage]   x halo, SWIZZLE_128B rows of 128 B
-    uint8_t* s_y = s_x + 2 * kXStage;                    // [kYBytes]      y halo, SWIZZLE_64B rows of 64 B
-    uint8_t* s_w1 = s_y + kYBytes;                       // [32][128 B]
+    const int stream = threadIdx.x / kStreamThreads;
+    uint8_t* s_x = smem + stream * kStreamBytes;         // [2][kXStage]   x halo, SWIZZLE_128B rows of 128 B   (per stream)
+    uint8_t* s_y = s_x + 2 * kXStage;                    // [kYBytes]      y halo, SWIZZLE_64B rows of 64 B     (per stream)
+    uint8_t* s_w1 = smem + kStreams * kStreamBytes;      // [32][128 B]                                         (shared)
     uint8_t* s_w2 = s_w1 + kW1Bytes;                     // [9][64][64 B]
     float* s_b1 = reinterpret_cast<float*>(s_w2 + kW2Bytes);     // [32]
     float* s_b2 = s_b1 + kC;                                      // [64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_b2 + 2 * kC);  // x_full[2], d1, d2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t* bars_all = reinterpret_cast<uint64_t*>(s_b2 + 2 * kC);  // per stream: x_full[2], d1, d2
+    uint64_t* bars = bars_all + 4 * stream;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars_all + 4 * kStreams);
+    const int tid = threadIdx.x % kStreamThreads, warp = tid >> 5, lane = tid & 31;    // position inside the stream
 
     // ---- prologue (overlaps the previous layer's tail under PDL): weights (not produced by the previous layer), barriers, TMEM ----
-    for (int i = tid; i < kC * 8; i += kThreads) {                       // W1: row n, 16-byte chunk c
+    for (int i = threadIdx.x; i < kC * 8; i += kThreads) {               // W1: row n, 16-byte chunk c
         const int n = i >> 3, c = i & 7;
         *reinterpret_cast<uint4*>(s_w1 + n * 128 + ((c ^ (n & 7)) << 4)) = __ldg(reinterpret_cast<const uint4*>(p.w1 + n * 64 + c * 8));
     }
-    for (int i = tid; i < 9 * 2 * kC * 4; i += kThreads) {               // W2: row R = tap * 64 + n, chunk c
+    for (int i = threadIdx.x; i < 9 * 2 * kC * 4; i += kThreads) {       // W2: row R = tap * 64 + n, chunk c
         const int R = i >> 2, c = i & 3;
         *reinterpret_cast<uint4*>(s_w2 + R * 64 + ((c ^ ((R >> 1) & 3)) << 4)) = __ldg(reinterpret_cast<const uint4*>(p.w2 + R * 32 + c * 8));
     }
-    if (tid < kC) s_b1[tid] = p.b1[tid];
-    if (tid < 2 * kC) s_b2[tid] = p.b2[tid];
-    if (tid == 0) {
-        for (int i = 0; i < 4; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[i])));
+    if (threadIdx.x < kC) s_b1[threadIdx.x] = p.b1[threadIdx.x];
+    if (threadIdx.x < 2 * kC) s_b2[threadIdx.x] = p.b2[threadIdx.x];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4 * kStreams; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars_all[i])));
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    if (threadIdx.x < 32) {                              // 128 columns per stream, allocated as one power of two
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the weight tiles above are read by the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem = tmem_base + (uint32_t)(stream * 128);
     uint64_t* x_full = bars;
     uint64_t* bar_d1 = bars + 2;
     uint64_t* bar_d2 = bars + 3;
@@ -161,15 +173,16 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
     const uint64_t w1desc = desc_sw128(smem_u32(s_w1));
     const uint32_t quad = warp & 3, half = warp >> 2;
 
-    if (tid == 0 && (int)blockIdx.x < total) load_x((int)blockIdx.x, 0);
+    const int first = (int)blockIdx.x * kStreams + stream, step = (int)gridDim.x * kStreams;
+    if (tid == 0 && first < total) load_x(first, 0);
     int stage = 0;
     uint32_t xphase[2] = {0, 0}, dphase = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (int tile = first; tile < total; tile += step) {
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         const int x0 = tx * kTW, y0 = ty * kTH;
         // the next tile's halo into the other stage: its last readers (epilogue 2 of the previous tile) are behind the barrier that ended
         // the previous iteration
-        if (tid == 0 && tile + (int)gridDim.x < total) load_x(tile + (int)gridDim.x, stage ^ 1);
+        if (tid == 0 && tile + step < total) load_x(tile + step, stage ^ 1);
         mbar_wait(&x_full[stage], xphase[stage]);
         xphase[stage] ^= 1;
         const uint32_t xs = smem_u32(s_x + stage * kXStage);
@@ -218,7 +231,7 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes of y -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
+        stream_sync(stream);
         // ---- MMA 2: nine taps over the y halo (shifted descriptors), resident W2 -> TMEM columns 64..127 ----
         if (warp == 0) {
             if (elect_one()) {
@@ -280,12 +293,12 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();                               // x[stage], y and both accumulators are free again
+        stream_sync(stream);                           // x[stage], y and both accumulators of this stream are free again
         stage ^= 1;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem) : "memory");
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
 }  // namespace
@@ -332,9 +345,9 @@ int32_t dark_block_run(const void* x, const void* w1, const float* b1, const voi
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long grid = (long long)sms * 2;
+    long long grid = sms;                                    // one CTA of kStreams tile streams per SM
     const long long tiles = (long long)p.tiles_x * p.tiles_y;
-    if (grid > tiles) grid = tiles;
+    if (grid * kStreams > tiles) grid = (tiles + kStreams - 1) / kStreams;
     OM_CUDA_TRY(launch_pdl(dark_block_kernel, dim3((unsigned)grid), dim3(kThreads), (size_t)kSmem, stream, map, p));
     return check_launch("dark_block_kernel");
 }
