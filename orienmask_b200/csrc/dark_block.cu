@@ -68,11 +68,17 @@ __device__ __forceinline__ bool elect_one() {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    while (true) {
-        uint32_t ok;
+    {
+        uint32_t ok;                                   // fast path: no clock reads when the phase has already completed
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    const long long t0 = clock64();
+    while (true) {                                     // suspend-time hint: the hardware parks the warp instead of re-issuing the poll
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
         if (ok) return;
         if (clock64() - t0 > 4000000000ll) __trap();
     }
@@ -176,31 +182,36 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
     const int first = (int)blockIdx.x * kStreams + stream, step = (int)gridDim.x * kStreams;
     if (tid == 0 && first < total) load_x(first, 0);
     int stage = 0;
-    uint32_t xphase[2] = {0, 0}, dphase = 0;
+    uint32_t xphase[2] = {0, 0}, d1phase = 0, d2phase = 0;
+    // MMA 1 of a tile: y_halo = x_halo * W1^T (rows 0..127 -> TMEM columns 0..31, rows 128..255 -> columns 32..63).  Issued by warp 0 as
+    // soon as the accumulator is free -- for the NEXT tile that is right after MMA 2 of the current one was issued, so it runs on the
+    // tensor pipe under epilogue 2 and its completion latency is off the critical path (ncu: the wait for it was 10 % of all warp time).
+    auto mma1 = [&](int st) {
+        mbar_wait(&x_full[st], xphase[st]);            // whole warp (the epilogues wait on the same phase later: already complete then)
+        if (elect_one()) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t xa = smem_u32(s_x + st * kXStage);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint64_t ad = desc_sw128(xa + h * 128 * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma(tmem + (uint32_t)(h * kC), ad + (uint64_t)(2 * k), w1desc + (uint64_t)(2 * k), idesc1, k != 0);
+            }
+            umma_commit(bar_d1);
+        }
+        __syncwarp();
+    };
+    if (warp == 0 && first < total) mma1(0);
     for (int tile = first; tile < total; tile += step) {
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         const int x0 = tx * kTW, y0 = ty * kTH;
         // the next tile's halo into the other stage: its last readers (epilogue 2 of the previous tile) are behind the barrier that ended
         // the previous iteration
         if (tid == 0 && tile + step < total) load_x(tile + step, stage ^ 1);
-        mbar_wait(&x_full[stage], xphase[stage]);
+        mbar_wait(&x_full[stage], xphase[stage]);      // (the residual of epilogue 2 reads x with ordinary loads)
         xphase[stage] ^= 1;
-        const uint32_t xs = smem_u32(s_x + stage * kXStage);
-        // ---- MMA 1: y_halo = x_halo * W1^T (rows 0..127 -> TMEM columns 0..31, rows 128..255 -> columns 32..63) ----
-        if (warp == 0) {
-            if (elect_one()) {
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint64_t ad = desc_sw128(xs + h * 128 * 128);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) umma(tmem + (uint32_t)(h * kC), ad + (uint64_t)(2 * k), w1desc + (uint64_t)(2 * k), idesc1, k != 0);
-                }
-                umma_commit(bar_d1);
-            }
-            __syncwarp();
-        }
-        mbar_wait(bar_d1, dphase);
+        mbar_wait(bar_d1, d1phase);                    // MMA 1 of this tile was issued one tile ago
+        d1phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- epilogue 1: halo pixel r = half * 128 + quad * 32 + lane -> 64 bytes of y in the SWIZZLE_64B halo tile ----
         {
@@ -247,9 +258,11 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
                 umma_commit(bar_d2);
             }
             __syncwarp();
+            // epilogue 1 of this tile has drained accumulator 1 (the barrier above): start the next tile's MMA 1 behind MMA 2
+            if (tile + step < total) { const uint32_t save = xphase[stage ^ 1]; mma1(stage ^ 1); xphase[stage ^ 1] = save; }
         }
-        mbar_wait(bar_d2, dphase);
-        dphase ^= 1;
+        mbar_wait(bar_d2, d2phase);
+        d2phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- epilogue 2: output pixel m = quad * 32 + lane, channels half * 32 .. + 31: + b2, LeakyReLU, + x, fp16, store ----
         {
