@@ -40,14 +40,21 @@ constexpr int kC = 32;                       // squeezed channels; the block's i
 constexpr int kTW = 8, kTH = 16;             // output tile (128 pixels = one M = 128 MMA)
 constexpr int kHW = kTW + 2, kHH = kTH + 2;  // halo 10 x 18 = 180 pixels
 constexpr int kHalo = kHW * kHH;
-constexpr int kStreams = 3;                  // independent tile pipelines per CTA
+#ifndef OM_BLOCK_STREAMS
+#define OM_BLOCK_STREAMS 3
+#endif
+#ifndef OM_BLOCK_XSTAGES
+#define OM_BLOCK_XSTAGES 2
+#endif
+constexpr int kStreams = OM_BLOCK_STREAMS;   // independent tile pipelines per CTA
+constexpr int kXStages = OM_BLOCK_XSTAGES;   // x halo stages per stream (1: the next halo is requested after epilogue 2)
 constexpr int kStreamThreads = 256;
 constexpr int kThreads = kStreams * kStreamThreads;
 constexpr int kXStage = ((kHalo * 128 + 1023) / 1024) * 1024;      // 23552 B
 constexpr int kYBytes = ((kHalo * 64 + 1023) / 1024) * 1024;       // 12288 B
 constexpr int kW1Bytes = kC * 128;                                 // [32 rows (cout)][64 k] fp16, SWIZZLE_128B
 constexpr int kW2Bytes = 9 * 2 * kC * 64;                          // [9][64 rows (cout)][32 k] fp16, SWIZZLE_64B
-constexpr int kStreamBytes = 2 * kXStage + kYBytes;
+constexpr int kStreamBytes = kXStages * kXStage + kYBytes;
 constexpr int kSmem = 1024 + kStreams * kStreamBytes + kW1Bytes + kW2Bytes + 1024;
 
 struct BlockParams {
@@ -123,7 +130,7 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stream = threadIdx.x / kStreamThreads;
     uint8_t* s_x = smem + stream * kStreamBytes;         // [2][kXStage]   x halo, SWIZZLE_128B rows of 128 B   (per stream)
-    uint8_t* s_y = s_x + 2 * kXStage;                    // [kYBytes]      y halo, SWIZZLE_64B rows of 64 B     (per stream)
+    uint8_t* s_y = s_x + kXStages * kXStage;             // [kYBytes]      y halo, SWIZZLE_64B rows of 64 B     (per stream)
     uint8_t* s_w1 = smem + kStreams * kStreamBytes;      // [32][128 B]                                         (shared)
     uint8_t* s_w2 = s_w1 + kW1Bytes;                     // [9][64][64 B]
     float* s_b1 = reinterpret_cast<float*>(s_w2 + kW2Bytes);     // [32]
@@ -151,6 +158,7 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
     }
     if (threadIdx.x < 32) {                              // 128 columns per stream, allocated as one power of two
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        static_assert(kStreams * 128 <= 512, "128 TMEM columns per stream");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // the weight tiles above are read by the tensor core
@@ -201,16 +209,17 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
         }
         __syncwarp();
     };
-    if (warp == 0 && first < total) mma1(0);
+    if (kXStages == 2 && warp == 0 && first < total) mma1(0);
     for (int tile = first; tile < total; tile += step) {
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         const int x0 = tx * kTW, y0 = ty * kTH;
         // the next tile's halo into the other stage: its last readers (epilogue 2 of the previous tile) are behind the barrier that ended
         // the previous iteration
-        if (tid == 0 && tile + step < total) load_x(tile + step, stage ^ 1);
+        if (kXStages == 2 && tid == 0 && tile + step < total) load_x(tile + step, stage ^ 1);
         mbar_wait(&x_full[stage], xphase[stage]);      // (the residual of epilogue 2 reads x with ordinary loads)
         xphase[stage] ^= 1;
-        mbar_wait(bar_d1, d1phase);                    // MMA 1 of this tile was issued one tile ago
+        if (kXStages == 1 && warp == 0) mma1(0);       // one stage: MMA 1 cannot run ahead of its halo
+        mbar_wait(bar_d1, d1phase);                    // two stages: MMA 1 of this tile was issued one tile ago
         d1phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- epilogue 1: halo pixel r = half * 128 + quad * 32 + lane -> 64 bytes of y in the SWIZZLE_64B halo tile ----
@@ -259,7 +268,7 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
             }
             __syncwarp();
             // epilogue 1 of this tile has drained accumulator 1 (the barrier above): start the next tile's MMA 1 behind MMA 2
-            if (tile + step < total) { const uint32_t save = xphase[stage ^ 1]; mma1(stage ^ 1); xphase[stage ^ 1] = save; }
+            if (kXStages == 2 && tile + step < total) mma1(stage ^ 1);
         }
         mbar_wait(bar_d2, d2phase);
         d2phase ^= 1;
@@ -307,7 +316,8 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         stream_sync(stream);                           // x[stage], y and both accumulators of this stream are free again
-        stage ^= 1;
+        if (kXStages == 2) stage ^= 1;
+        else if (tid == 0 && tile + step < total) load_x(tile + step, 0);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

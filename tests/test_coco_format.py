@@ -39,6 +39,25 @@ def test_rle_known_answers():
     assert co.rle_from_string(b'357K').tolist() == [3, 5, 7, 0]
 
 
+def test_rle_run_lengths_match_an_independent_implementation():
+    """pycocotools is in neither the reference tree nor this image, so the codec restatement (oracle/coco_oracle.py) has no binary to
+    be pinned against.  The run-length half of it does have an independent third-party implementation here: transformers' SAM
+    post-processing `_mask_to_rle` ("in the format expected by pycoco tools": column-major runs, the first one counting zeros), a port
+    of segment-anything's amg.py.  Pinned against it on blob masks, all-zero / all-one masks and speckle; the string compression
+    (rleToString) stays pinned by known answers and round trips only."""
+    sam = pytest.importorskip('transformers.models.sam.image_processing_sam')
+    from oracle import coco_oracle
+    rng = np.random.default_rng(3)
+    masks = np.concatenate([blob_masks(8, 37, 53, seed=9), rng.random((4, 37, 53)) < 0.3,
+                            np.zeros((1, 37, 53), bool), np.ones((1, 37, 53), bool)])
+    want = sam._mask_to_rle(torch.from_numpy(masks))
+    for m, w in zip(masks, want):
+        got = coco_oracle.rle_encode(m.astype(np.uint8))
+        assert w['size'] == [37, 53] and [int(v) for v in got] == [int(v) for v in w['counts']]
+        # and through the string codec and back
+        assert np.array_equal(coco_oracle.rle_from_string(coco_oracle.rle_to_string(got)), got)
+
+
 def test_rle_round_trips():
     rng = np.random.default_rng(0)
     for _ in range(50):
