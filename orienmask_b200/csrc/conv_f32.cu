@@ -222,8 +222,12 @@ extern "C" int32_t om_stem_conv(int32_t precision, const float* image, const flo
         if (!(sel && sel[0] == 'f') && h % 4 == 0 && w % 32 == 0)          // default: tensor-core stem (conv_stem_tc.cu)
             return om::stem_tc_run(image, weights, bias, output, batch, h, w, rows, out_s2d, st);
         stem_kernel<__half, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d);
-    } else if (precision == OM_PREC_SPLIT)
+    } else if (precision == OM_PREC_SPLIT) {
+        const char* sel = getenv("ORIENMASK_B200_STEM");
+        if (!(sel && sel[0] == 'f') && h % 4 == 0 && w % 32 == 0 && (reinterpret_cast<uintptr_t>(image) & 15) == 0)   // tensor cores, hi + lo pairs
+            return om::stem_tc_run(image, weights, bias, output, batch, h, w, rows, out_s2d, st, 1);
         stem_kernel<__half, 32, true><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d);
+    }
     else if (precision == OM_PREC_F32)
         stem_kernel<float, 32><<<blocks, 256, 0, st>>>(image, weights, bias, reinterpret_cast<float*>(output), batch, h, w, rows, out_s2d);
     else

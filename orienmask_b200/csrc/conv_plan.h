@@ -16,7 +16,7 @@ void tc2_plan_info(const void* plan, int32_t* info24);
 
 // tensor-core first layer (conv_stem_tc.cu)
 int32_t stem_tc_run(const float* image, const float* weights, const float* bias, void* output, int batch, int h, int w, int rows,
-                    int out_s2d, cudaStream_t stream);
+                    int out_s2d, cudaStream_t stream, int split = 0);
 
 // fused DarkNet block, C = 32 (dark_block.cu)
 bool dark_block_supported(int cin, int cmid, int width, int rows);

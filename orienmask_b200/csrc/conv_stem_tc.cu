@@ -64,12 +64,17 @@ __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8])
 
 struct __align__(128) PatchStage { float v[3][kTileH + 2][kPatchW]; };      // sizeof rounds up to a multiple of 128: a TMA destination
 
-template <bool TMA>
+// SPLIT (OM_PREC_SPLIT, the tensor-core parity mode): image values and weights as fp16 hi + lo pairs, three MMA passes per tile
+// (A_lo * W_hi, A_hi * W_lo, A_hi * W_hi: corrections first, see conv_tc2.cu), weights pre-scaled by a power of two so that W_lo stays a
+// normal fp16 number, output written as hi | lo halves ([.., 2 * 32] per pixel).
+template <bool TMA, bool SPLIT>
 __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CUtensorMap map_img, const float* __restrict__ img,
                                                       const float* __restrict__ w27, const float* __restrict__ bias, __half* __restrict__ out,
                                                       int batch, int h, int wd, int rows, int out_s2d) {
-    __shared__ __align__(1024) uint8_t s_a[2][128 * 64];     // im2col rows, K-major SWIZZLE_64B (double-buffered)
-    __shared__ __align__(1024) uint8_t s_b[kCout * 64];      // weights [cout][k], same layout
+    constexpr int kParts = SPLIT ? 2 : 1;                    // [0] = hi (or the plain fp16 value), [1] = lo
+    __shared__ __align__(1024) uint8_t s_a[2][kParts][128 * 64];   // im2col rows, K-major SWIZZLE_64B (double-buffered)
+    __shared__ __align__(1024) uint8_t s_b[kParts][kCout * 64];    // weights [cout][k], same layout
+    __shared__ unsigned int s_amax;
     __shared__ PatchStage s_patch2[TMA ? 2 : 1];             // TMA: two stages, each the box {36, 6, 3} as it lands (128-byte aligned)
     __shared__ float s_bias[kCout];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -78,15 +83,32 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // weights: w27 is [27][32] (tap-major: (ky*3+kx)*3+ci, then cout); B[n][k] = w27[k][n], k >= 27 -> 0
+    float wscale = 1.0f, acc_scale = 1.0f;
+    if (SPLIT) {                                             // power of two that puts max|w| in [2^13, 2^14)
+        if (tid == 0) s_amax = 0u;
+        __syncthreads();
+        float m = 0.0f;
+        for (int i = tid; i < 27 * kCout; i += 128) m = fmaxf(m, fabsf(w27[i]));
+        atomicMax(&s_amax, __float_as_uint(m));
+        __syncthreads();
+        const float amax = __uint_as_float(s_amax);
+        int sh = amax > 0.0f ? 13 - (int)floorf(log2f(amax)) : 0;
+        sh = sh < -24 ? -24 : (sh > 40 ? 40 : sh);
+        wscale = exp2f((float)sh);
+        acc_scale = exp2f((float)-sh);
+    }
     for (int i = tid; i < kCout * 4; i += 128) {
         const int n = i >> 2, c = i & 3;
-        __half v[8];
+        __half v[8], l[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int k = c * 8 + e;
-            v[e] = __float2half(k < 27 ? w27[k * kCout + n] : 0.0f);
+            const float w = (k < 27 ? w27[k * kCout + n] : 0.0f) * wscale;
+            v[e] = __float2half(w);
+            l[e] = __float2half(w - __half2float(v[e]));
         }
-        *reinterpret_cast<uint4*>(s_b + swz64(n, c)) = *reinterpret_cast<const uint4*>(v);
+        *reinterpret_cast<uint4*>(s_b[0] + swz64(n, c)) = *reinterpret_cast<const uint4*>(v);
+        if (SPLIT) *reinterpret_cast<uint4*>(s_b[kParts - 1] + swz64(n, c)) = *reinterpret_cast<const uint4*>(l);
     }
     if (tid < kCout) s_bias[tid] = bias[tid];
     if (tid == 0) {
@@ -107,7 +129,8 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
     const uint32_t tmem = s_tmem;
     pdl_wait();                                        // the previous step's last kernels may still read/write our buffers
     const uint32_t idesc = (1u << 4) | ((uint32_t)(kCout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint64_t bdesc = kmajor_desc_64b(smem_u32(s_b));
+    const uint64_t bdesc = kmajor_desc_64b(smem_u32(s_b[0]));
+    const uint64_t bdesc_lo = kmajor_desc_64b(smem_u32(s_b[kParts - 1]));
 
     const int tiles_x = wd / kTileW, tiles_y = h / kTileH;
     const int tiles_per_image = tiles_x * tiles_y;
@@ -178,20 +201,28 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
         size_t opix = (size_t)Yo * wd + xo;
         if (out_s2d)                                       // parity-split output for the stride-2 consumer (om_conv_desc)
             opix = (size_t)(2 * (Yo & 1) + (xo & 1)) * ((size_t)batch * rows / 2 * (wd / 2)) + (size_t)(Yo >> 1) * (wd / 2) + (xo >> 1);
-        __half* o = out + opix * kCout;
+        __half* o = out + opix * (kParts * kCout);
 #pragma unroll
         for (int i = 0; i < 32; i += 16) {
-            uint32_t wv[8];
+            uint32_t wv[8], wl[8];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                float a = __uint_as_float(acc[i + 2 * q]) + s_bias[i + 2 * q];
-                float b = __uint_as_float(acc[i + 2 * q + 1]) + s_bias[i + 2 * q + 1];
+                float a = __uint_as_float(acc[i + 2 * q]), b = __uint_as_float(acc[i + 2 * q + 1]);
+                if (SPLIT) { a *= acc_scale; b *= acc_scale; }         // power of two: exact
+                a += s_bias[i + 2 * q];
+                b += s_bias[i + 2 * q + 1];
                 a = fmaxf(a, 0.1f * a);                        // LeakyReLU(0.1)
                 b = fmaxf(b, 0.1f * b);
                 const __half2 hv = __floats2half2_rn(a, b);
                 wv[q] = *reinterpret_cast<const uint32_t*>(&hv);
+                if (SPLIT) {
+                    const float2 back = __half22float2(hv);
+                    const __half2 lv = __floats2half2_rn(a - back.x, b - back.y);
+                    wl[q] = *reinterpret_cast<const uint32_t*>(&lv);
+                }
             }
             st_global_256(o + i, wv);
+            if (SPLIT) st_global_256(o + kCout + i, wl);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
@@ -234,11 +265,19 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
             for (int k = 27; k < 32; ++k) v[k] = 0.0f;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                uint4 q;
+                uint4 q, ql;
                 __half2* hq = reinterpret_cast<__half2*>(&q);
+                __half2* lq = reinterpret_cast<__half2*>(&ql);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) hq[e] = __floats2half2_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
-                *reinterpret_cast<uint4*>(s_a[buf] + swz64(tid, c)) = q;
+                for (int e = 0; e < 4; ++e) {
+                    hq[e] = __floats2half2_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
+                    if (SPLIT) {
+                        const float2 back = __half22float2(hq[e]);
+                        lq[e] = __floats2half2_rn(v[c * 8 + 2 * e] - back.x, v[c * 8 + 2 * e + 1] - back.y);
+                    }
+                }
+                *reinterpret_cast<uint4*>(s_a[buf][0] + swz64(tid, c)) = q;
+                if (SPLIT) *reinterpret_cast<uint4*>(s_a[buf][kParts - 1] + swz64(tid, c)) = ql;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
@@ -248,14 +287,21 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
         if (warp == 0) {
             if (elect_one()) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t adesc = kmajor_desc_64b(smem_u32(s_a[buf]));
+                const uint64_t adesc = kmajor_desc_64b(smem_u32(s_a[buf][0]));
+                const uint64_t adesc_lo = kmajor_desc_64b(smem_u32(s_a[buf][kParts - 1]));
+                // plain: one pass; split: (A_lo, W_hi), (A_hi, W_lo), (A_hi, W_hi)
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const uint32_t acc = k;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem + (uint32_t)(buf * 32)), "l"(adesc + (uint64_t)(2 * k)), "l"(bdesc + (uint64_t)(2 * k)), "r"(idesc), "r"(acc) : "memory");
+                for (int pass = SPLIT ? 0 : 2; pass < 3; ++pass) {
+                    const uint64_t ad = pass == 0 ? adesc_lo : adesc;
+                    const uint64_t bd = pass == 1 ? bdesc_lo : bdesc;
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint32_t acc = (pass == (SPLIT ? 0 : 2) && k == 0) ? 0u : 1u;
+                        asm volatile(
+                            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                            ::"r"(tmem + (uint32_t)(buf * 32)), "l"(ad + (uint64_t)(2 * k)), "l"(bd + (uint64_t)(2 * k)), "r"(idesc), "r"(acc) : "memory");
+                    }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[buf])) : "memory");
             }
@@ -278,7 +324,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
 namespace om {
 
 int32_t stem_tc_run(const float* image, const float* weights, const float* bias, void* output, int batch, int h, int w, int rows,
-                    int out_s2d, cudaStream_t stream) {
+                    int out_s2d, cudaStream_t stream, int split) {
     if (h % kTileH || w % kTileW) return fail(OM_ERR_INVALID, "tensor-core stem needs h %% 4 == 0 and w %% 32 == 0 (got %dx%d)", h, w);
     const long long tiles = (long long)batch * (h / kTileH) * (w / kTileW);
     int dev = 0, sms = 0;
@@ -317,14 +363,18 @@ int32_t stem_tc_run(const float* image, const float* weights, const float* bias,
     if (use_tma) {
         // 58 registers and 23.8 KB of shared memory per CTA: up to 8 CTAs per SM (8 x 64 TMEM columns = the whole TMEM)
         const char* ce = getenv("ORIENMASK_B200_STEM_CTAS");
-        const int per_sm = (ce && atoi(ce) >= 1 && atoi(ce) <= 8) ? atoi(ce) : 8;
+        const int per_sm = (ce && atoi(ce) >= 1 && atoi(ce) <= 8) ? atoi(ce) : (split ? 5 : 8);     // split: 42 KB of shared memory per CTA
         grid = (long long)sms * per_sm;
         if (grid > tiles) grid = tiles;
     }
-    if (use_tma)
-        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d));
+    __half* o = reinterpret_cast<__half*>(output);
+    if (split && !use_tma) return fail(OM_ERR_UNSUPPORTED, "the split-precision tensor-core stem needs a 16-byte aligned image (TMA)");
+    if (split)
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, true>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d));
+    else if (use_tma)
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d));
     else
-        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, reinterpret_cast<__half*>(output), batch, h, w, rows, out_s2d));
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<false, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d));
     return check_launch("stem_tc_kernel");
 }
 

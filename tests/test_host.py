@@ -70,8 +70,8 @@ def test_built_library_contains_blackwell_tensor_and_tma_code():
     for name in ('conv_tc2_kernel<32, false>', 'conv_tc2_kernel<64, false>', 'conv_tc2_kernel<32, true>', 'conv_tc2_kernel<64, true>'):
         c = counts[name]
         assert c['UTCHMMA'] > 100 and c['UTMALDG'] >= 5 and c['LDTM'] >= 4 and c['UTCBAR'] >= 2 and c['ACQBULK'] >= 1, (name, dict(c))
-    assert counts['stem_tc_kernel<true>']['UTCHMMA'] >= 2 and counts['stem_tc_kernel<true>']['LDTM'] >= 1
-    assert counts['stem_tc_kernel<true>']['UTMALDG'] >= 1            # the 544x544 input tiles are staged by TMA
+    assert counts['stem_tc_kernel<true, false>']['UTCHMMA'] >= 2 and counts['stem_tc_kernel<true, false>']['LDTM'] >= 1
+    assert counts['stem_tc_kernel<true, false>']['UTMALDG'] >= 1            # the 544x544 input tiles are staged by TMA
     assert all(c['HMMA'] == 0 and c['HGMMA'] == 0 for c in counts.values())
     for name in ('mask_kernel', 'conf_compact_kernel', 'select_edge_kernel', 'select_tail_kernel', 'nms_kernel<true>', 'prep_kernel<unsigned char>',
                  'mask_rle_kernel', 'mask_blend_kernel'):
