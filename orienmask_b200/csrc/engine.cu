@@ -50,7 +50,12 @@ struct Layer {
     const float* blk_b1 = nullptr; const float* blk_b2 = nullptr;
     double flops = 0, bytes = 0;
     char shape[96];
+    // small-batch branch concurrency (om_engine.lanes): stream lane of the launch, events it waits for / records
+    int lane = 0, wait_ev = -1, record_ev = -1;
 };
+
+// Events of the branch schedule: a feature the side lanes consume is ready / a side lane has finished
+enum { EV_X4 = 0, EV_N32, EV_N16, EV_N8, EV_SKIPS, EV_HEADS, EV_COUNT };
 
 // ---- weight folding / packing on the device -----------------------------------------------------------------------------------
 // One thread per (tap, cout, cin-of-the-slice) element.  Every arithmetic step is a single-rounded fp32 operation in the order the
@@ -123,6 +128,13 @@ struct om_engine {
     unsigned int* amax = nullptr;
     int cmul = 1, esz = 2;
     int32_t rc = OM_OK;
+    // Small batches (every layer far below one wave of CTAs): the box heads and the skip / partial branch of the stride-4 neck do not
+    // sit on the critical path backbone -> necks -> neck4 -> orientation head; they run on two side streams, forked and joined by
+    // events (a CUDA-graph capture of om_forward records the same fork / join).  Large batches keep one stream: concurrent 227 KB CTAs
+    // do not co-reside and the launches would only compete for SMs (DESIGN finding 14).
+    bool lanes = false;
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev[EV_COUNT] = {};
     Buf c1;                     // stem output
 
     int rows(int stride) const {
@@ -364,6 +376,7 @@ struct om_engine {
             }
             trunk = x;
             feats[i + 1] = x;
+            if (i == 1) layers.back().record_ev = EV_X4;
         }
         const Buf &x4 = feats[2], &x8 = feats[3], &x16 = feats[4], &x32 = feats[5];
         const int ks[5] = {1, 3, 1, 3, 1};
@@ -373,18 +386,21 @@ struct om_engine {
         Buf b32[2] = {act(32, 512), act(32, 1024)};
         neck_couts(512, co);
         Buf neck32 = chain("neck32", x32, 1024, 0, 1024, b32, ks, co, 5, nullptr);
+        layers.back().record_ev = EV_N32;
         Buf r32 = act(32, 256);
         cbl("route32.0", neck32, 512, 256, r32, 1);
         Buf p16 = partial("neck16.0", 768, 0, 256, 256, r32, nullptr);
         Buf b16[2] = {act(16, 256), act(16, 512)};
         neck_couts(256, co);
         Buf neck16 = chain("neck16", x16, 768, 256, 512, b16, ks, co, 5, &p16);
+        layers.back().record_ev = EV_N16;
         Buf r16 = act(16, 128);
         cbl("route16.0", neck16, 256, 128, r16, 1);
         Buf p8 = partial("neck8.0", 384, 0, 128, 128, r16, nullptr);
         Buf b8[2] = {act(8, 128), act(8, 256)};
         neck_couts(128, co);
         Buf neck8 = chain("neck8", x8, 384, 128, 256, b8, ks, co, 5, &p8);
+        layers.back().record_ev = EV_N8;
 
         const int nb = cfg.num_anchors * (5 + cfg.num_classes);
         const Buf* necks[3] = {&neck32, &neck16, &neck8};
@@ -393,7 +409,10 @@ struct om_engine {
             Buf hb = act(head_s[j], 2 * head_c[j]);
             const std::string hp = "bbox_head" + std::to_string(head_s[j]);
             cbl(hp + ".0", *necks[j], head_c[j], 2 * head_c[j], hb, 3);
+            layers.back().lane = 1; layers.back().wait_ev = EV_N32 + j;
             head(hp + ".1", hb, 2 * head_c[j], nb, j);
+            layers.back().lane = 1;
+            if (j == 2) layers.back().record_ev = EV_HEADS;
         }
 
         Buf ab4[2] = {act(4, 128), act(4, 256)};
@@ -402,12 +421,18 @@ struct om_engine {
         if (cfg.plus) {
             Buf s32 = act(32, 64), s16 = act(16, 64), s8 = act(8, 64), s4 = act(4, 64);
             cbl("skip32.0", neck32, 512, 64, s32, 1);
+            layers.back().lane = 2; layers.back().wait_ev = EV_N32;
             cbl("skip16.0", neck16, 256, 64, s16, 1);
+            layers.back().lane = 2; layers.back().wait_ev = EV_N16;
             cbl("skip8.0", neck8, 128, 64, s8, 1);
             cbl("skip4", x4, 128, 64, s4, 1);
+            layers.back().lane = 2; layers.back().wait_ev = EV_X4;
             Buf q32 = partial("neck4.0", 256, 0, 64, 128, s32, nullptr);
+            layers.back().lane = 2;
             Buf q16 = partial("neck4.0", 256, 64, 64, 128, s16, &q32);
+            layers.back().lane = 2; layers.back().record_ev = EV_SKIPS;
             Buf q8 = partial("neck4.0", 256, 128, 64, 128, s8, &q16);
+            layers.back().wait_ev = EV_SKIPS;                          // main lane: q16 and (through stream order) s4 are ready
             neck4 = chain("neck4", s4, 256, 192, 64, ab4, ks, co, 5, &q8);
         } else {                                                     // model/orienmask_yolo.py:83: neck4(cat[route8(neck8) up2, x4])
             Buf r8 = act(8, 64);
@@ -448,6 +473,10 @@ extern "C" int32_t om_engine_workspace_bytes(const om_engine_config* cfg, size_t
 
 extern "C" void om_engine_destroy(om_engine* e) {
     if (!e) return;
+    for (int i = 0; i < 2; ++i)
+        if (e->side[i]) cudaStreamDestroy(e->side[i]);
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (Layer& L : e->layers)
         if (L.conv) om_conv_destroy(L.conv);
     delete e;
@@ -475,6 +504,17 @@ extern "C" int32_t om_engine_create(const om_engine_config* cfg, const om_tensor
     e->build();
     if (e->rc != OM_OK) { rc = e->rc; om_engine_destroy(e); return rc; }
     e->sd.clear();
+    {
+        const char* le = getenv("ORIENMASK_B200_LANES");
+        const long long cells32 = (long long)cfg->batch * (cfg->height / 32) * (cfg->width / 32);
+        e->lanes = !(le && le[0] == '0') && (cells32 <= 1200 || (le && le[0] == '1'));       // up to ~bs 4 at 544x544
+        if (e->lanes) {
+            bool ok = true;
+            for (int i = 0; i < 2 && ok; ++i) ok = cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking) == cudaSuccess;
+            for (int i = 0; i < EV_COUNT && ok; ++i) ok = cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) { om_engine_destroy(e); return om::fail(OM_ERR_CUDA, "om_engine_create: cannot create the side streams / events"); }
+        }
+    }
     *out = e;
     return OM_OK;
 }
@@ -498,10 +538,27 @@ static int32_t run_layer(const om_engine* e, const Layer& L, const float* image,
 
 extern "C" int32_t om_forward(const om_engine* e, const float* image, float* const* bbox, float* orien, void* stream) {
     if (!e) return om::fail(OM_ERR_INVALID, "om_forward: null engine");
-    for (const Layer& L : e->layers) {
-        const int32_t rc = run_layer(e, L, image, bbox, orien, (cudaStream_t)stream);
-        if (rc != OM_OK) return rc;
+    if (!e->lanes) {
+        for (const Layer& L : e->layers) {
+            const int32_t rc = run_layer(e, L, image, bbox, orien, (cudaStream_t)stream);
+            if (rc != OM_OK) return rc;
+        }
+        return OM_OK;
     }
+    cudaStream_t lane[3] = {(cudaStream_t)stream, e->side[0], e->side[1]};
+    bool used[3] = {true, false, false}, recorded[EV_COUNT] = {};
+    for (const Layer& L : e->layers) {
+        cudaStream_t st = lane[L.lane];
+        if (L.wait_ev >= 0 && recorded[L.wait_ev]) OM_CUDA_TRY(cudaStreamWaitEvent(st, e->ev[L.wait_ev], 0));
+        used[L.lane] = true;
+        const int32_t rc = run_layer(e, L, image, bbox, orien, st);
+        if (rc != OM_OK) return rc;
+        if (L.record_ev >= 0) { OM_CUDA_TRY(cudaEventRecord(e->ev[L.record_ev], st)); recorded[L.record_ev] = true; }
+    }
+    // join: everything the side lanes did is ordered before whatever the caller enqueues next on `stream`
+    if (recorded[EV_HEADS]) OM_CUDA_TRY(cudaStreamWaitEvent(lane[0], e->ev[EV_HEADS], 0));
+    if (recorded[EV_SKIPS]) OM_CUDA_TRY(cudaStreamWaitEvent(lane[0], e->ev[EV_SKIPS], 0));
+    (void)used;
     return OM_OK;
 }
 
