@@ -269,10 +269,14 @@ struct om_engine {
     }
 
     void layers_pop_conv() {
-        if (layers.empty()) return;
+        if (rc != OM_OK || layers.empty()) return;
         if (layers.back().conv) om_conv_destroy(layers.back().conv);
         layers.pop_back();
     }
+
+    // lane / event tags of the layer emitted last (no-ops once an error has stopped the emission)
+    Layer scratch_layer;
+    Layer& last() { return (rc == OM_OK && !layers.empty()) ? layers.back() : scratch_layer; }
 
     // Fused residual block x -> x + conv3x3(conv1x1(x)) with C squeezed channels, output into `dst` (never in place: neighbouring tiles
     // read each other's x halo)
@@ -376,7 +380,7 @@ struct om_engine {
             }
             trunk = x;
             feats[i + 1] = x;
-            if (i == 1) layers.back().record_ev = EV_X4;
+            if (i == 1) last().record_ev = EV_X4;
         }
         const Buf &x4 = feats[2], &x8 = feats[3], &x16 = feats[4], &x32 = feats[5];
         const int ks[5] = {1, 3, 1, 3, 1};
@@ -386,21 +390,21 @@ struct om_engine {
         Buf b32[2] = {act(32, 512), act(32, 1024)};
         neck_couts(512, co);
         Buf neck32 = chain("neck32", x32, 1024, 0, 1024, b32, ks, co, 5, nullptr);
-        layers.back().record_ev = EV_N32;
+        last().record_ev = EV_N32;
         Buf r32 = act(32, 256);
         cbl("route32.0", neck32, 512, 256, r32, 1);
         Buf p16 = partial("neck16.0", 768, 0, 256, 256, r32, nullptr);
         Buf b16[2] = {act(16, 256), act(16, 512)};
         neck_couts(256, co);
         Buf neck16 = chain("neck16", x16, 768, 256, 512, b16, ks, co, 5, &p16);
-        layers.back().record_ev = EV_N16;
+        last().record_ev = EV_N16;
         Buf r16 = act(16, 128);
         cbl("route16.0", neck16, 256, 128, r16, 1);
         Buf p8 = partial("neck8.0", 384, 0, 128, 128, r16, nullptr);
         Buf b8[2] = {act(8, 128), act(8, 256)};
         neck_couts(128, co);
         Buf neck8 = chain("neck8", x8, 384, 128, 256, b8, ks, co, 5, &p8);
-        layers.back().record_ev = EV_N8;
+        last().record_ev = EV_N8;
 
         const int nb = cfg.num_anchors * (5 + cfg.num_classes);
         const Buf* necks[3] = {&neck32, &neck16, &neck8};
@@ -409,10 +413,10 @@ struct om_engine {
             Buf hb = act(head_s[j], 2 * head_c[j]);
             const std::string hp = "bbox_head" + std::to_string(head_s[j]);
             cbl(hp + ".0", *necks[j], head_c[j], 2 * head_c[j], hb, 3);
-            layers.back().lane = 1; layers.back().wait_ev = EV_N32 + j;
+            last().lane = 1; last().wait_ev = EV_N32 + j;
             head(hp + ".1", hb, 2 * head_c[j], nb, j);
-            layers.back().lane = 1;
-            if (j == 2) layers.back().record_ev = EV_HEADS;
+            last().lane = 1;
+            if (j == 2) last().record_ev = EV_HEADS;
         }
 
         Buf ab4[2] = {act(4, 128), act(4, 256)};
@@ -421,18 +425,18 @@ struct om_engine {
         if (cfg.plus) {
             Buf s32 = act(32, 64), s16 = act(16, 64), s8 = act(8, 64), s4 = act(4, 64);
             cbl("skip32.0", neck32, 512, 64, s32, 1);
-            layers.back().lane = 2; layers.back().wait_ev = EV_N32;
+            last().lane = 2; last().wait_ev = EV_N32;
             cbl("skip16.0", neck16, 256, 64, s16, 1);
-            layers.back().lane = 2; layers.back().wait_ev = EV_N16;
+            last().lane = 2; last().wait_ev = EV_N16;
             cbl("skip8.0", neck8, 128, 64, s8, 1);
             cbl("skip4", x4, 128, 64, s4, 1);
-            layers.back().lane = 2; layers.back().wait_ev = EV_X4;
+            last().lane = 2; last().wait_ev = EV_X4;
             Buf q32 = partial("neck4.0", 256, 0, 64, 128, s32, nullptr);
-            layers.back().lane = 2;
+            last().lane = 2;
             Buf q16 = partial("neck4.0", 256, 64, 64, 128, s16, &q32);
-            layers.back().lane = 2; layers.back().record_ev = EV_SKIPS;
+            last().lane = 2; last().record_ev = EV_SKIPS;
             Buf q8 = partial("neck4.0", 256, 128, 64, 128, s8, &q16);
-            layers.back().wait_ev = EV_SKIPS;                          // main lane: q16 and (through stream order) s4 are ready
+            last().wait_ev = EV_SKIPS;                          // main lane: q16 and (through stream order) s4 are ready
             neck4 = chain("neck4", s4, 256, 192, 64, ab4, ks, co, 5, &q8);
         } else {                                                     // model/orienmask_yolo.py:83: neck4(cat[route8(neck8) up2, x4])
             Buf r8 = act(8, 64);
