@@ -304,6 +304,21 @@ def test_c_engine_errors_are_loud():
     torch.cuda.synchronize()
 
 
+def test_cuda_graph_replay_matches_eager_launches():
+    """`model.use_cuda_graph = True` (ORIENMASK_B200_GRAPH=1): the forward -- at this batch size with its side-stream lanes -- captured
+    once and replayed; every replay must equal the eager launches on the same input, for changing inputs."""
+    from orienmask_b200.synthetic import synthetic_images
+    eager, graphed = _model('fp16'), _model('fp16')
+    graphed.use_cuda_graph = True
+    for seed in (1, 2, 3):
+        x = synthetic_images(1, 544, 544, seed=seed).cuda()
+        want = [(b.clone(), o.clone()) for b, o in eager(x)]
+        got = graphed(x)
+        torch.cuda.synchronize()
+        for (gb, go), (wb, wo) in zip(got, want):
+            assert torch.equal(gb, wb) and torch.equal(go, wo), seed
+
+
 def test_forward_returns_tensors_owned_by_the_caller():
     """The reference's forward returns fresh tensors; results of one call must survive the next call (both engines)."""
     from orienmask_b200.synthetic import synthetic_images
