@@ -213,6 +213,11 @@ void om_conv_destroy(om_conv* conv);
 int32_t om_debug_conv_plan_info(const om_conv* conv, int32_t* info24);
 /* Debug: device buffer of >= 16 uint64 that cluster 0 of the following conv launches fills with %globaltimer stamps (NULL turns it off). */
 int32_t om_debug_conv_timeline(void* device_u64x16);
+/* Launch trace: arm (records != NULL: a device buffer of capacity x 4 uint64, pre-filled with {~0, ~0, 0, 0} per record) or disarm.
+ * While armed every conv-engine launch takes the next record and stamps %globaltimer into it: [0] first CTA start, [1] dependencies
+ * resolved (griddepcontrol.wait returned), [2] last CTA end, [3] last CTA start.  Returns the records handed out since the previous
+ * call.  tools/timeline.py: the in-situ timeline of a pipelined forward (what ncu's serialised launch list cannot show). */
+int32_t om_debug_trace(void* records, int32_t capacity);
 
 /*
  * First layer (3 -> cout, 3x3, stride 1, BN folded, LeakyReLU) straight from the caller's image.
@@ -283,6 +288,10 @@ int32_t om_engine_layer_count(const om_engine* engine);
 int32_t om_engine_layer_info(const om_engine* engine, int32_t index, om_layer_info* info);
 /* One launch of the schedule (same arguments as om_forward; only the stem reads `image`, only head layers write outputs). */
 int32_t om_engine_run_layer(const om_engine* engine, int32_t index, const float* image, float* const* bbox, float* orien, void* stream);
+/* A sub-schedule in one call: the launches `indices[0..n)` back to back on `stream` (tools/insitu.py times the forward with and
+ * without a group of layers: what the group costs INSIDE the pipelined forward, which ncu's serialised launch list cannot say). */
+int32_t om_engine_run_layers(const om_engine* engine, const int32_t* indices, int32_t n, const float* image, float* const* bbox,
+                             float* orien, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Pre-process (the caller side of the path: infer.py:147-151)                                   */

@@ -23,6 +23,13 @@ int32_t fail(int32_t code, const char* fmt, ...) {
 
 void count_launch(int n) { g_launches += n; }
 
+static unsigned long long* g_trace_base = nullptr;
+static int g_trace_cap = 0, g_trace_used = 0;
+unsigned long long* trace_next() {
+    if (g_trace_base == nullptr || g_trace_used >= g_trace_cap) return nullptr;
+    return g_trace_base + 4 * (size_t)(g_trace_used++);
+}
+
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("ORIENMASK_B200_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -109,3 +116,14 @@ extern "C" int32_t om_debug_conv_plan_info(const om_conv* c, int32_t* info) {
     return OM_OK;
 }
 
+// Debug: arm (records != NULL) or disarm the launch trace.  `records` is a device buffer of capacity x 4 uint64 that the caller has
+// filled with {~0, ~0, 0, 0} per record; every following conv-engine launch (conv_tc2 / stem / fused block) takes the next record
+// and stamps %globaltimer into it (first CTA start, dependencies resolved, last CTA end, last CTA start).  Returns the number of
+// records handed out since the previous call.  tools/timeline.py turns this into the in-situ timeline of a forward.
+extern "C" int32_t om_debug_trace(void* records, int32_t capacity) {
+    const int32_t used = om::g_trace_used;
+    om::g_trace_base = reinterpret_cast<unsigned long long*>(records);
+    om::g_trace_cap = records ? capacity : 0;
+    om::g_trace_used = 0;
+    return used;
+}

@@ -38,9 +38,25 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Debug trace (om_debug_trace): when armed, every conv-engine launch gets the next 4 x uint64 record of a device buffer and stamps
+// %globaltimer into it: [0] first CTA start (min), [1] first "dependencies resolved" (min over CTAs of the time griddepcontrol.wait
+// returned), [2] last CTA end (max), [3] last CTA start (max).  nullptr (the normal case) costs one predicated branch per CTA.
+unsigned long long* trace_next();
+
 }  // namespace om
 
 #ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long trace_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void trace_start(unsigned long long* rec) {
+    if (rec != nullptr) { const unsigned long long t = trace_now(); atomicMin(rec, t); atomicMax(rec + 3, t); }
+}
+__device__ __forceinline__ void trace_dep(unsigned long long* rec) { if (rec != nullptr) atomicMin(rec + 1, trace_now()); }
+__device__ __forceinline__ void trace_end(unsigned long long* rec) { if (rec != nullptr) atomicMax(rec + 2, trace_now()); }
+
 // Device side of PDL: block until every prerequisite grid has completed and its writes are visible, then let the
 // next grid in the stream begin its own prologue.
 __device__ __forceinline__ void pdl_wait() {

@@ -70,7 +70,8 @@ struct __align__(128) PatchStage { float v[3][kTileH + 2][kPatchW]; };      // s
 template <bool TMA, bool SPLIT>
 __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CUtensorMap map_img, const float* __restrict__ img,
                                                       const float* __restrict__ w27, const float* __restrict__ bias, __half* __restrict__ out,
-                                                      int batch, int h, int wd, int rows, int out_s2d) {
+                                                      int batch, int h, int wd, int rows, int out_s2d, unsigned long long* trace) {
+    if (threadIdx.x == 0) trace_start(trace);
     constexpr int kParts = SPLIT ? 2 : 1;                    // [0] = hi (or the plain fp16 value), [1] = lo
     __shared__ __align__(1024) uint8_t s_a[2][kParts][128 * 64];   // im2col rows, K-major SWIZZLE_64B (double-buffered)
     __shared__ __align__(1024) uint8_t s_b[kParts][kCout * 64];    // weights [cout][k], same layout
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = s_tmem;
     pdl_wait();                                        // the previous step's last kernels may still read/write our buffers
+    if (threadIdx.x == 0) trace_dep(trace);
     const uint32_t idesc = (1u << 4) | ((uint32_t)(kCout >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t bdesc = kmajor_desc_64b(smem_u32(s_b[0]));
     const uint64_t bdesc_lo = kmajor_desc_64b(smem_u32(s_b[kParts - 1]));
@@ -316,6 +318,7 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
     if (prev >= 0) epilogue(buf ^ 1, prev);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) trace_end(trace);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
 }
 
@@ -368,13 +371,14 @@ int32_t stem_tc_run(const float* image, const float* weights, const float* bias,
         if (grid > tiles) grid = tiles;
     }
     __half* o = reinterpret_cast<__half*>(output);
+    unsigned long long* tr = trace_next();
     if (split && !use_tma) return fail(OM_ERR_UNSUPPORTED, "the split-precision tensor-core stem needs a 16-byte aligned image (TMA)");
     if (split)
-        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, true>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d));
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, true>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d, tr));
     else if (use_tma)
-        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d));
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d, tr));
     else
-        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<false, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d));
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<false, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d, tr));
     return check_launch("stem_tc_kernel");
 }
 

@@ -87,6 +87,7 @@ struct Tc2Params {
     const float* bias;
     const float* upadd;
     void* output;
+    unsigned long long* trace;           // om_debug_trace record of this launch, or nullptr
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -528,6 +529,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     const CUtensorMap& map_a0 = maps_a.m[0];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     tick(0, threadIdx.x == 0);
+    if (threadIdx.x == 0) trace_start(p.trace);
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int b_sub = p.half_n * BK * 2;                                // one (tap, chunk) block of this CTA's weight rows
     const int a_sub = p.a_sub_bytes;                                    // per-tap mode: the matching activation box (0 in halo mode)
@@ -621,7 +623,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 if (p.halo) {
                     mbar_wait(&h_empty[hs], h_phase ^ 1);
                     const uint32_t lb = mapa(smem_u32(&h_full[hs]), 0);
-                    if (pair == first_pair) { pdl_wait(); tick(2, lane == 0); }
+                    if (pair == first_pair) { pdl_wait(); tick(2, lane == 0); if (lane == 0) trace_dep(p.trace); }
                     if (lane == 0 && rank == 0) mbar_expect_tx(&h_full[hs], h_tx);
                     if (lane < p.a_chunks * p.halo_planes) {       // buffer order: [plane][chunk]; plane coordinates == output coordinates
                         const int plane = lane / p.a_chunks, kc = lane - plane * p.a_chunks;
@@ -659,7 +661,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                             sel = ((r != 1) ? 2 : 0) + ((s != 1) ? 1 : 0);       // odd row / odd column views
                         }
                     }
-                    if (!p.halo && pair == first_pair && g == 0) { pdl_wait(); tick(2, lane == 0); }   // first activation load
+                    if (!p.halo && pair == first_pair && g == 0) { pdl_wait(); tick(2, lane == 0); if (lane == 0) trace_dep(p.trace); }   // first activation load
                     if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[st], s_tx);
                     if (lane < p.n_sub) {
                         if (p.flat) tma_load_im2col_pair(sb + (size_t)lane * sub_bytes, &map_a0, lb, ka * BK, fw, fh, fo.n, tap_s, tap_r);
@@ -818,6 +820,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     __syncthreads();
     cluster_sync();                                    // nobody leaves while the peer may still touch its smem / TMEM
     tick(10, threadIdx.x == 0);
+    if (threadIdx.x == 0) trace_end(p.trace);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -1261,6 +1264,7 @@ int32_t tc2_plan_run(const void* vp, cudaStream_t stream, void* output) {
     const Tc2Plan* plan = reinterpret_cast<const Tc2Plan*>(vp);
     if (plan_dryrun()) return fail(OM_ERR_UNSUPPORTED, "plans made under ORIENMASK_B200_PLAN_DRYRUN cannot be launched");
     Tc2Params p = plan->p;
+    p.trace = trace_next();
     if (output != nullptr) {
         if (p.has_res || p.res_direct) return fail(OM_ERR_INVALID, "om_conv_run_to: layers with a residual write in place");
         p.output = output;

@@ -65,6 +65,7 @@ struct BlockParams {
     const __half* w1; const __half* w2;      // engine layout of OM_PREC_F16: [1][32][64] and [9][64][32]
     const float* b1; const float* b2;
     __half* out;
+    unsigned long long* trace;               // om_debug_trace record of this launch, or nullptr
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,6 +128,7 @@ __device__ __forceinline__ void stream_sync(int stream) {                 // nam
 __global__ void __launch_bounds__(kThreads, 1)
 dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    if (threadIdx.x == 0) trace_start(p.trace);
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int stream = threadIdx.x / kStreamThreads;
     uint8_t* s_x = smem + stream * kStreamBytes;         // [2][kXStage]   x halo, SWIZZLE_128B rows of 128 B   (per stream)
@@ -171,6 +173,7 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
     uint64_t* bar_d1 = bars + 2;
     uint64_t* bar_d2 = bars + 3;
     pdl_wait();                                                           // x is the previous layer's output
+    if (threadIdx.x == 0) trace_dep(p.trace);
 
     const int total = p.tiles_x * p.tiles_y;
     constexpr uint32_t kXBytes = kHalo * 128;
@@ -321,6 +324,7 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0) trace_end(p.trace);
     if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
@@ -364,6 +368,7 @@ int32_t dark_block_run(const void* x, const void* w1, const float* b1, const voi
     p.out_s2d = out_s2d; p.s2d_plane = (long long)batch * rows / 2 * (width / 2);
     p.w1 = reinterpret_cast<const __half*>(w1); p.w2 = reinterpret_cast<const __half*>(w2); p.b1 = b1; p.b2 = b2;
     p.out = reinterpret_cast<__half*>(out);
+    p.trace = trace_next();
     OM_CUDA_TRY(cudaFuncSetAttribute(dark_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);

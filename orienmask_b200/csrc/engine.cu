@@ -584,3 +584,14 @@ extern "C" int32_t om_engine_run_layer(const om_engine* e, int32_t index, const 
     if (!e || index < 0 || index >= (int32_t)e->layers.size()) return om::fail(OM_ERR_INVALID, "om_engine_run_layer: bad argument");
     return run_layer(e, e->layers[index], image, bbox, orien, (cudaStream_t)stream);
 }
+
+extern "C" int32_t om_engine_run_layers(const om_engine* e, const int32_t* indices, int32_t n, const float* image, float* const* bbox, float* orien,
+                                        void* stream) {
+    if (!e || !indices || n < 0) return om::fail(OM_ERR_INVALID, "om_engine_run_layers: bad argument");
+    for (int32_t i = 0; i < n; ++i) {
+        if (indices[i] < 0 || indices[i] >= (int32_t)e->layers.size()) return om::fail(OM_ERR_INVALID, "om_engine_run_layers: index %d out of range", indices[i]);
+        const int32_t rc = run_layer(e, e->layers[indices[i]], image, bbox, orien, (cudaStream_t)stream);
+        if (rc != OM_OK) return rc;
+    }
+    return OM_OK;
+}
