@@ -36,7 +36,13 @@ constexpr int kStageBytes = kStageRows * 128;
 constexpr int kMaxResBufs = 2 * kEpiGroups;   // addend staging buffers: one lane per epilogue group, up to 2 deep
 constexpr int kMaxAcc = 8;                    // accumulator stages in TMEM (narrow tiles: 512 columns / N)
 
+// n / d for 0 <= n < 2^31 as one multiply-high and a shift (the persistent loops decode tile coordinates per tile: six runtime integer
+// divisions of ~25 instructions each were 22 % of the warp instructions of the narrow memory-bound layers, ncu source view of conv2.0).
+// d >= 2: l = ceil(log2 d), mul = ceil(2^(31+l) / d) < 2^32, q = umulhi(n, mul) >> (l - 1); exact because mul * d - 2^(31+l) < 2^l.
+struct FastDiv { uint32_t mul, shift, one, d; };
+
 struct Tc2Params {
+    FastDiv d_tiles_n, d_tiles_x, d_out_rows, d_tw, d_flat_hw, d_out_w, d_k_chunks;
     int tiles_x, pairs_y, tiles_n;       // pair grid; linear pair id = (py * tiles_x + tx) * tiles_n + tn
     int tw, th;                          // pixel tile (tw * th <= 128)
     int taps, stride;
@@ -149,7 +155,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
     const unsigned int hint = g_wait_hint_ns;
     const long long t0 = clock64();
-    while (true) {
+    for (uint32_t spins = 1;; ++spins) {               // the clock is read every 64th round only: this loop was 19 % of conv2.0's instructions
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -157,7 +163,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(addr), "r"(parity), "r"(hint) : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000ll) __trap();
+        if ((spins & 63u) == 0u && clock64() - t0 > 4000000000ll) __trap();
     }
 }
 
@@ -256,13 +262,18 @@ __device__ __forceinline__ void tick(int slot, bool who) {
     }
 }
 
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+    const int q = (int)(__umulhi((uint32_t)n, f.mul) >> f.shift);
+    return f.one ? n : q;
+}
+
 struct PairCoord { int tx, py, tn; };
 __device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
     PairCoord t;
-    t.tn = pair % p.tiles_n;
-    const int r = pair / p.tiles_n;
-    t.tx = r % p.tiles_x;
-    t.py = r / p.tiles_x;
+    const int r = fdiv(pair, p.d_tiles_n);
+    t.tn = pair - r * p.tiles_n;
+    t.py = fdiv(r, p.d_tiles_x);
+    t.tx = r - t.py * p.tiles_x;
     return t;
 }
 
@@ -273,9 +284,9 @@ __device__ __forceinline__ FlatOrigin flat_origin(const Tc2Params& p, int tm) {
     int q0 = tm * kBlockM;
     if (q0 >= p.flat_total) q0 = 0;
     FlatOrigin o;
-    o.n = q0 / p.flat_hw;
+    o.n = fdiv(q0, p.d_flat_hw);
     const int rem = q0 - o.n * p.flat_hw;
-    o.y = rem / p.out_w;
+    o.y = fdiv(rem, p.d_out_w);
     o.x = rem - o.y * p.out_w;
     return o;
 }
@@ -304,6 +315,16 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     return v;
 }
 
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2: one issue slot for two IEEE fp32 operations, bit-identical to the scalar forms).
+__device__ __forceinline__ void add2(float& a, float& b, float x, float y) {
+    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 p, {%0, %1};\n\tmov.b64 q, {%2, %3};\n\tadd.rn.f32x2 p, p, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "+f"(a), "+f"(b) : "f"(x), "f"(y));
+}
+__device__ __forceinline__ void mul2(float& o0, float& o1, float a, float b, float x) {
+    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 p, {%2, %3};\n\tmov.b64 q, {%4, %4};\n\tmul.rn.f32x2 p, p, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "=f"(o0), "=f"(o1) : "f"(a), "f"(b), "f"(x));
+}
+
 struct EpiCtx {
     uint32_t tmem_base, leader_tmem_empty0, rank, s_bias_addr;
     uint64_t* tmem_full; uint64_t* res_full; uint64_t* res_empty;
@@ -317,7 +338,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
     const int grp = (c.warp - kEpiWarp0) >> 2;
     const int m = quad * 32 + c.lane;                   // accumulator row = pixel inside the tile
     const int n_chunks = p.block_n / p.chunk_cols;
-    const int my = m / p.tw, mx = m - my * p.tw;
+    const int my = fdiv(m, p.d_tw), mx = m - my * p.tw;
     const bool in_tile = m < p.tw * p.th;
     int as = 0; uint32_t aphase = 0;
     int rslot = 0; uint32_t rphase = 0;                 // this group's addend slot and its phase
@@ -341,14 +362,14 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
         const PairCoord t = decode_pair(p, pair);
         int x0 = t.tx * p.tw, y0 = (2 * t.py + (int)c.rank) * p.th;
         int Y = y0 + my, x = x0 + mx;
-        int img = Y / p.out_rows, y = Y - img * p.out_rows;
+        int img = fdiv(Y, p.d_out_rows), y = Y - img * p.out_rows;
         bool valid = in_tile && (Y < p.total_rows) && (y < p.out_h) && (x < p.out_w);
         if (FLAT) {                                     // accumulator row m = output pixel (2 * py + rank) * 128 + m in (image, y, x) order
             const int q = (2 * t.py + (int)c.rank) * kBlockM + m;
             valid = q < p.flat_total;
-            img = q / p.flat_hw;
+            img = fdiv(q, p.d_flat_hw);
             const int rem = q - img * p.flat_hw;
-            y = rem / p.out_w; x = rem - y * p.out_w;
+            y = fdiv(rem, p.d_out_w); x = rem - y * p.out_w;
             Y = img * p.out_rows + y;
         }
         const int n0 = t.tn * p.block_n;
@@ -384,7 +405,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
                 for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
                 if (SPLIT) {
     #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] *= p.acc_scale;                        // power of two: exact
+                    for (int i = 0; i < 32; i += 2) mul2(f[i], f[i + 1], f[i], f[i + 1], p.acc_scale);   // power of two (x gain fix)
                 }
                 if (ADD == 2) {
                     const uint8_t* ubuf = c.res_buf + rb * p.res_buf_bytes;
@@ -392,24 +413,28 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
     #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 u = *reinterpret_cast<const float4*>(ubuf + swz(up_row, i >> 2, 128));
-                            f[i] += u.x; f[i + 1] += u.y; f[i + 2] += u.z; f[i + 3] += u.w;
+                            add2(f[i], f[i + 1], u.x, u.y); add2(f[i + 2], f[i + 3], u.z, u.w);
                         }
                     }
                 } else if (up != nullptr) {
     #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
                         const float4 u = __ldg(reinterpret_cast<const float4*>(up + cg + i));
-                        f[i] += u.x; f[i + 1] += u.y; f[i + 2] += u.z; f[i + 3] += u.w;
+                        add2(f[i], f[i + 1], u.x, u.y); add2(f[i + 2], f[i + 3], u.z, u.w);
                     }
                 }
     #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 bv = lds_f4(c.s_bias_addr + (uint32_t)(cg + i) * 4u);          // warp-uniform: smem broadcast
-                    f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+                    add2(f[i], f[i + 1], bv.x, bv.y); add2(f[i + 2], f[i + 3], bv.z, bv.w);
                 }
                 if (p.leaky) {
     #pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.1f * f[i]);           // LeakyReLU(0.1)
+                    for (int i = 0; i < 32; i += 2) {                                       // LeakyReLU(0.1) = max(f, 0.1 f)
+                        float m0, m1;
+                        mul2(m0, m1, f[i], f[i + 1], 0.1f);
+                        f[i] = fmaxf(f[i], m0); f[i + 1] = fmaxf(f[i + 1], m1);
+                    }
                 }
                 if (KIND == 0) {
                     if (ADD == 1) {
@@ -421,7 +446,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
     #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const float2 rf = __half22float2(rh[q]);
-                                f[i + 2 * q] += rf.x; f[i + 2 * q + 1] += rf.y;
+                                add2(f[i + 2 * q], f[i + 2 * q + 1], rf.x, rf.y);
                             }
                         }
                     }
@@ -436,7 +461,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
 #pragma unroll
                                     for (int q = 0; q < 4; ++q) {
                                         const float2 rf = __half22float2(rh[q]);
-                                        f[i + 2 * q] += rf.x; f[i + 2 * q + 1] += rf.y;
+                                        add2(f[i + 2 * q], f[i + 2 * q + 1], rf.x, rf.y);
                                     }
                                 }
                             }
@@ -450,7 +475,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) {
                                     const float2 rf = __half22float2(rh[q]);
-                                    f[i + 2 * q] += rf.x; f[i + 2 * q + 1] += rf.y;
+                                    add2(f[i + 2 * q], f[i + 2 * q + 1], rf.x, rf.y);
                                 }
                             }
                             if (j + kEpiGroups < n_chunks) ldg_res32(rr, rsrc + (j + kEpiGroups) * 32);
@@ -637,7 +662,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     const uint32_t lb = mapa(smem_u32(&s_full[st]), 0);
                     uint8_t* sb = s_ring + (size_t)st * stage_bytes;
                     const int i = g * p.n_sub + lane;                // (tap, chunk) block of this lane, tap-major
-                    int tap = i / p.k_chunks, kc = i - tap * p.k_chunks;
+                    int tap = fdiv(i, p.d_k_chunks), kc = i - tap * p.k_chunks;
                     int ka = kc, kb = kc;                            // channel chunk of the activation / weight block in memory
                     if (SPLIT) {
                         // pass-major K loop: (A_lo, W_hi) over all taps, then (A_hi, W_lo), then (A_hi, W_hi).  tcgen05 accumulates
@@ -948,6 +973,17 @@ struct Tc2Plan {
 // than 8 pixels (their TMA boxes degenerate into many 128..512-byte rows and they share little halo in L2).
 // NCHW heads: the widest row segment among tiles that are at least 75 % full, so that the per-channel fp32
 // stores of a warp form few long runs without idling a large part of the epilogue lanes.
+FastDiv make_fastdiv(int d) {
+    FastDiv f = {0u, 0u, 1u, (uint32_t)d};
+    if (d <= 1) return f;
+    int l = 0;
+    while ((1ll << l) < d) ++l;
+    f.mul = (uint32_t)(((1ull << (31 + l)) + (unsigned long long)d - 1) / (unsigned long long)d);
+    f.shift = (uint32_t)(l - 1);
+    f.one = 0u;
+    return f;
+}
+
 int pick_tile_w(int w, bool widest) {
     int best = 1, best_score = -1;
     for (int tw = 1; tw <= w && tw <= kBlockM; ++tw) {
@@ -1064,8 +1100,11 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     p.total_rows = d.batch * d.out_rows;
     const int tiles_y = p.flat ? (p.flat_total + kBlockM - 1) / kBlockM : (p.total_rows + p.th - 1) / p.th;
     p.pairs_y = (tiles_y + 1) / 2;
+    p.d_tiles_n = make_fastdiv(p.tiles_n); p.d_tiles_x = make_fastdiv(p.tiles_x); p.d_out_rows = make_fastdiv(d.out_rows);
+    p.d_tw = make_fastdiv(p.tw); p.d_flat_hw = make_fastdiv(p.flat_hw); p.d_out_w = make_fastdiv(d.out_w);
     p.taps = d.ksize * d.ksize; p.stride = d.stride;
     p.k_chunks = (split ? 3 : 1) * (d.cin / bk); p.a_chunks = (split ? 2 : 1) * (d.cin / bk); p.split_kr = split ? d.cin / bk : 0;
+    p.d_k_chunks = make_fastdiv(p.k_chunks);
     p.acc_scale = (split && d.acc_scale != 0.0f) ? d.acc_scale : 1.0f;
     if (split && !getenv("ORIENMASK_B200_NO_GAIN_FIX")) {
         // tcgen05 truncates its fp32 running sum: every MMA into a non-empty accumulator loses a fraction of an ulp toward zero, which
