@@ -7,7 +7,23 @@
 
 #include "../../include/orienmask_b200.h"
 
+// n / d for 0 <= n < 2^31 as one multiply-high and a shift (the persistent kernels decode tile coordinates per tile: six runtime integer
+// divisions of ~25 instructions each were 22 % of the warp instructions of the narrow memory-bound layers, ncu source view of conv2.0).
+// d >= 2: l = ceil(log2 d), mul = ceil(2^(31+l) / d) < 2^32, q = umulhi(n, mul) >> (l - 1); exact because mul * d - 2^(31+l) < 2^l.
+struct FastDiv { uint32_t mul, shift, one, d; };
+
 namespace om {
+
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f = {0u, 0u, 1u, (uint32_t)d};
+    if (d <= 1) return f;
+    int l = 0;
+    while ((1ll << l) < d) ++l;
+    f.mul = (uint32_t)(((1ull << (31 + l)) + (unsigned long long)d - 1) / (unsigned long long)d);
+    f.shift = (uint32_t)(l - 1);
+    f.one = 0u;
+    return f;
+}
 
 char* error_buffer();                       // thread-local, 512 bytes
 int32_t fail(int32_t code, const char* fmt, ...);
@@ -46,6 +62,19 @@ unsigned long long* trace_next();
 }  // namespace om
 
 #ifdef __CUDACC__
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+    const int q = (int)(__umulhi((uint32_t)n, f.mul) >> f.shift);
+    return f.one ? n : q;
+}
+// Packed fp32 pairs (Blackwell FADD2 / FMUL2: one issue slot for two IEEE fp32 operations, bit-identical to the scalar forms).
+__device__ __forceinline__ void add2(float& a, float& b, float x, float y) {
+    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 p, {%0, %1};\n\tmov.b64 q, {%2, %3};\n\tadd.rn.f32x2 p, p, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "+f"(a), "+f"(b) : "f"(x), "f"(y));
+}
+__device__ __forceinline__ void mul2(float& o0, float& o1, float a, float b, float x) {
+    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 p, {%2, %3};\n\tmov.b64 q, {%4, %4};\n\tmul.rn.f32x2 p, p, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
+        : "=f"(o0), "=f"(o1) : "f"(a), "f"(b), "f"(x));
+}
 __device__ __forceinline__ unsigned long long trace_now() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -68,16 +68,17 @@ struct __align__(128) PatchStage { float v[3][kTileH + 2][kPatchW]; };      // s
 // (A_lo * W_hi, A_hi * W_lo, A_hi * W_hi: corrections first, see conv_tc2.cu), weights pre-scaled by a power of two so that W_lo stays a
 // normal fp16 number, output written as hi | lo halves ([.., 2 * 32] per pixel).
 template <bool TMA, bool SPLIT>
-__global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CUtensorMap map_img, const float* __restrict__ img,
+__global__ void __launch_bounds__(128, (TMA && !SPLIT) ? 8 : 1) stem_tc_kernel(const __grid_constant__ CUtensorMap map_img, const float* __restrict__ img,
                                                       const float* __restrict__ w27, const float* __restrict__ bias, __half* __restrict__ out,
-                                                      int batch, int h, int wd, int rows, int out_s2d, unsigned long long* trace) {
+                                                      int batch, int h, int wd, int rows, int out_s2d, unsigned long long* trace,
+                                                      FastDiv fd_tpi, FastDiv fd_tx) {
     if (threadIdx.x == 0) trace_start(trace);
     constexpr int kParts = SPLIT ? 2 : 1;                    // [0] = hi (or the plain fp16 value), [1] = lo
     __shared__ __align__(1024) uint8_t s_a[2][kParts][128 * 64];   // im2col rows, K-major SWIZZLE_64B (double-buffered)
     __shared__ __align__(1024) uint8_t s_b[kParts][kCout * 64];    // weights [cout][k], same layout
     __shared__ unsigned int s_amax;
     __shared__ PatchStage s_patch2[TMA ? 2 : 1];             // TMA: two stages, each the box {36, 6, 3} as it lands (128-byte aligned)
-    __shared__ float s_bias[kCout];
+    __shared__ __align__(16) float s_bias[kCout];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ __align__(8) uint64_t s_pfull[2];             // TMA: patch stage filled
     __shared__ uint32_t s_tmem;
@@ -136,6 +137,9 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
 
     const int tiles_x = wd / kTileW, tiles_y = h / kTileH;
     const int tiles_per_image = tiles_x * tiles_y;
+    // tile -> (image, tile row, tile column) by multiply-high (common.cuh): two runtime divisions per thread and tile were a quarter of
+    // the kernel's instructions
+    const FastDiv d_tpi = fd_tpi, d_tx = fd_tx;
     const long long total = (long long)batch * tiles_per_image;
     uint32_t phase[2] = {0, 0};
     constexpr int kPatchElems = 3 * (kTileH + 2) * 34;               // 612 = 4.78 per thread
@@ -159,9 +163,9 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
     // TMA: one thread asks for the whole patch of a tile; rows / columns outside the image arrive as zeros
     constexpr uint32_t kPatchBytes = 3 * (kTileH + 2) * kPatchW * 4;
     auto tma_patch = [&](int tile, int stage) {
-        const int n = tile / tiles_per_image;
+        const int n = fdiv(tile, d_tpi);
         const int r = tile - n * tiles_per_image;
-        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        const int ty = fdiv(r, d_tx), tx = r - ty * tiles_x;
         const uint32_t bar = smem_u32(&s_pfull[stage]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kPatchBytes) : "memory");
         asm volatile(
@@ -169,9 +173,9 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
             ::"r"(smem_u32(&s_patch2[stage].v[0][0][0])), "l"(&map_img), "r"(bar), "r"(tx * kTileW - (kPatchX + 1)), "r"(ty * kTileH - 1), "r"(0), "r"(n) : "memory");
     };
     auto fetch = [&](int tile, float (&regs)[kPerThread]) {
-        const int n = tile / tiles_per_image;
+        const int n = fdiv(tile, d_tpi);
         const int r = tile - n * tiles_per_image;
-        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        const int ty = fdiv(r, d_tx), tx = r - ty * tiles_x;
         const int y0 = ty * kTileH, x0 = tx * kTileW;
         const float* base = img + (size_t)n * 3 * h * wd + (size_t)y0 * wd + x0;
 #pragma unroll
@@ -182,9 +186,9 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
     };
     // epilogue of the tile whose accumulator sits in TMEM stage `buf`: this thread's pixel, 32 channels
     auto epilogue = [&](int buf, int tile) {
-        const int n = tile / tiles_per_image;
+        const int n = fdiv(tile, d_tpi);
         const int r = tile - n * tiles_per_image;
-        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        const int ty = fdiv(r, d_tx), tx = r - ty * tiles_x;
         mbar_wait(&s_bar[buf], phase[buf]);
         phase[buf] ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -210,11 +214,13 @@ __global__ void __launch_bounds__(128) stem_tc_kernel(const __grid_constant__ CU
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 float a = __uint_as_float(acc[i + 2 * q]), b = __uint_as_float(acc[i + 2 * q + 1]);
-                if (SPLIT) { a *= acc_scale; b *= acc_scale; }         // power of two: exact
-                a += s_bias[i + 2 * q];
-                b += s_bias[i + 2 * q + 1];
-                a = fmaxf(a, 0.1f * a);                        // LeakyReLU(0.1)
-                b = fmaxf(b, 0.1f * b);
+                if (SPLIT) mul2(a, b, a, b, acc_scale);                // power of two: exact
+                const float2 bv = *reinterpret_cast<const float2*>(&s_bias[i + 2 * q]);
+                add2(a, b, bv.x, bv.y);
+                float ma, mb;
+                mul2(ma, mb, a, b, 0.1f);                      // LeakyReLU(0.1) = max(v, 0.1 v)
+                a = fmaxf(a, ma);
+                b = fmaxf(b, mb);
                 const __half2 hv = __floats2half2_rn(a, b);
                 wv[q] = *reinterpret_cast<const uint32_t*>(&hv);
                 if (SPLIT) {
@@ -374,11 +380,11 @@ int32_t stem_tc_run(const float* image, const float* weights, const float* bias,
     unsigned long long* tr = trace_next();
     if (split && !use_tma) return fail(OM_ERR_UNSUPPORTED, "the split-precision tensor-core stem needs a 16-byte aligned image (TMA)");
     if (split)
-        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, true>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d, tr));
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, true>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d, tr, make_fastdiv((h / kTileH) * (w / kTileW)), make_fastdiv(w / kTileW)));
     else if (use_tma)
-        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d, tr));
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<true, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d, tr, make_fastdiv((h / kTileH) * (w / kTileW)), make_fastdiv(w / kTileW)));
     else
-        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<false, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d, tr));
+        OM_CUDA_TRY(launch_pdl(stem_tc_kernel<false, false>, dim3((unsigned)grid), dim3(128), 0, stream, map, image, weights, bias, o, batch, h, w, rows, out_s2d, tr, make_fastdiv((h / kTileH) * (w / kTileW)), make_fastdiv(w / kTileW)));
     return check_launch("stem_tc_kernel");
 }
 

@@ -36,11 +36,6 @@ constexpr int kStageBytes = kStageRows * 128;
 constexpr int kMaxResBufs = 2 * kEpiGroups;   // addend staging buffers: one lane per epilogue group, up to 2 deep
 constexpr int kMaxAcc = 8;                    // accumulator stages in TMEM (narrow tiles: 512 columns / N)
 
-// n / d for 0 <= n < 2^31 as one multiply-high and a shift (the persistent loops decode tile coordinates per tile: six runtime integer
-// divisions of ~25 instructions each were 22 % of the warp instructions of the narrow memory-bound layers, ncu source view of conv2.0).
-// d >= 2: l = ceil(log2 d), mul = ceil(2^(31+l) / d) < 2^32, q = umulhi(n, mul) >> (l - 1); exact because mul * d - 2^(31+l) < 2^l.
-struct FastDiv { uint32_t mul, shift, one, d; };
-
 struct Tc2Params {
     FastDiv d_tiles_n, d_tiles_x, d_out_rows, d_tw, d_flat_hw, d_out_w, d_k_chunks;
     int tiles_x, pairs_y, tiles_n;       // pair grid; linear pair id = (py * tiles_x + tx) * tiles_n + tn
@@ -94,6 +89,7 @@ struct Tc2Params {
     const float* upadd;
     void* output;
     unsigned long long* trace;           // om_debug_trace record of this launch, or nullptr
+    int hint_a, hint_w, hint_res, hint_out;   // L2 eviction priority of the activation / weight / residual loads and of the fp16 output stores
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -168,29 +164,59 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Operand loads of a CTA pair: data lands in the issuing CTA, completion bytes go to the LEADER's barrier.
-__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+// L2 eviction-priority policies (createpolicy): 0 none, 1 evict_first (data that is dead after this access), 2 evict_last (data
+// the next layers read again).  Every operand load / output store carries one; see the planner (l2 hints) for who gets what.
+// 0 = no hint at all (NOT the same as an explicit evict_normal policy: with that on every load the memory-bound 136x136 layers
+// measured 20 % slower, in-situ A/B) -- the wrappers below issue the plain instruction when the policy word is 0.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+    uint64_t p = 0;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
-__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void tma_load_3d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, uint64_t pol) {
+    if (pol == 0)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, uint64_t pol) {
+    if (pol == 0)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, uint64_t pol) {
+    if (pol == 0)
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol) : "memory");
 }
 // im2col-mode loads (tensor map from cuTensorMapEncodeIm2col): `pixelsPerColumn` pixels starting at input position (w, h) of
 // image n, shifted by the filter tap (ow, oh), walking x -> y -> image inside the map's bounding box with its traversal
 // stride; positions outside the image read zeros.
 __device__ __forceinline__ void tma_load_im2col_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c, int w, int h, int n,
-                                                     int ow, int oh) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)ow), "h"((uint16_t)oh) : "memory");
+                                                     int ow, int oh, uint64_t pol) {
+    if (pol == 0)
+        asm volatile(
+            "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)ow), "h"((uint16_t)oh) : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8}, %9;"
+            ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)ow), "h"((uint16_t)oh), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void tma_load_im2col(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h, int n) {
     const uint16_t z = 0;
@@ -202,6 +228,11 @@ __device__ __forceinline__ void tma_load_im2col(void* dst, const CUtensorMap* ma
 __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&w)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+}
+__device__ __forceinline__ void st_global_256_hint(void* ptr, const uint32_t (&w)[8], uint64_t pol) {
+    if (pol == 0) { st_global_256(ptr, w); return; }
+    asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
+                 ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "l"(pol) : "memory");
 }
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -262,11 +293,6 @@ __device__ __forceinline__ void tick(int slot, bool who) {
     }
 }
 
-__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
-    const int q = (int)(__umulhi((uint32_t)n, f.mul) >> f.shift);
-    return f.one ? n : q;
-}
-
 struct PairCoord { int tx, py, tn; };
 __device__ __forceinline__ PairCoord decode_pair(const Tc2Params& p, int pair) {
     PairCoord t;
@@ -304,25 +330,19 @@ __device__ __forceinline__ FlatOrigin flat_origin(const Tc2Params& p, int tm) {
 //         thread that owns the pixel, one 32-column chunk ahead (flat mode)
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void ldg_res32(uint4 (&r)[4], const __half* src) {      // 32 fp16 = 64 bytes of one pixel
+    // two 32-byte loads (LDG.256): whole sectors per lane -- with the L1 carved down to nothing, four 16-byte loads fetched every
+    // sector twice from L2
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[i].x), "=r"(r[i].y), "=r"(r[i].z), "=r"(r[i].w) : "l"(src + 8 * i) : "memory");
+    for (int i = 0; i < 4; i += 2)
+        asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[i].x), "=r"(r[i].y), "=r"(r[i].z), "=r"(r[i].w), "=r"(r[i + 1].x), "=r"(r[i + 1].y), "=r"(r[i + 1].z), "=r"(r[i + 1].w)
+                     : "l"(src + 8 * i) : "memory");
 }
 
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
-}
-
-// Packed fp32 pairs (Blackwell FADD2 / FMUL2: one issue slot for two IEEE fp32 operations, bit-identical to the scalar forms).
-__device__ __forceinline__ void add2(float& a, float& b, float x, float y) {
-    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 p, {%0, %1};\n\tmov.b64 q, {%2, %3};\n\tadd.rn.f32x2 p, p, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
-        : "+f"(a), "+f"(b) : "f"(x), "f"(y));
-}
-__device__ __forceinline__ void mul2(float& o0, float& o1, float a, float b, float x) {
-    asm("{\n\t.reg .b64 p, q;\n\tmov.b64 p, {%2, %3};\n\tmov.b64 q, {%4, %4};\n\tmul.rn.f32x2 p, p, q;\n\tmov.b64 {%0, %1}, p;\n\t}"
-        : "=f"(o0), "=f"(o1) : "f"(a), "f"(b), "f"(x));
 }
 
 struct EpiCtx {
@@ -340,6 +360,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
     const int n_chunks = p.block_n / p.chunk_cols;
     const int my = fdiv(m, p.d_tw), mx = m - my * p.tw;
     const bool in_tile = m < p.tw * p.th;
+    const uint64_t pol_out = l2_policy(p.hint_out);
     int as = 0; uint32_t aphase = 0;
     int rslot = 0; uint32_t rphase = 0;                 // this group's addend slot and its phase
     int g0 = 0;                                          // sequence number (mod kEpiGroups) of the tile's first chunk
@@ -512,7 +533,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
                                 const __half2 h = __floats2half2_rn(f[i + 2 * q], f[i + 2 * q + 1]);
                                 w[q] = *reinterpret_cast<const uint32_t*>(&h);
                             }
-                            st_global_256(o + i, w);
+                            st_global_256_hint(o + i, w, pol_out);
                         }
                     }
                 } else if (KIND == 1) {
@@ -627,6 +648,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             // across lanes instead of serialising on one thread (which bounded the layers with small boxes). =====
             int st = 0; uint32_t s_phase = 0;
             int hs = 0; uint32_t h_phase = 0;
+            const uint64_t pol_a = l2_policy(p.hint_a), pol_w = l2_policy(p.hint_w);
             const uint32_t s_tx = 2u * (uint32_t)p.n_sub * (uint32_t)((p.halo ? 0 : p.a_box_pixels * BK * 2) + b_sub);
             const uint32_t h_tx = 2u * (uint32_t)(p.a_chunks * p.halo_planes) * (uint32_t)(p.a_box_pixels * BK * 2);
             if (p.b_resident) {                               // the whole weight tensor (this CTA's half of the rows), once
@@ -634,7 +656,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[0], 2u * (uint32_t)(p.taps * p.k_chunks * b_sub));
                 if (lane < p.taps * p.k_chunks) {
                     const int tap = lane / p.k_chunks, kc = lane - tap * p.k_chunks;
-                    tma_load_2d_pair(s_ring + (size_t)lane * b_sub, &map_b, lb, kc * BK, tap * p.cout_pad + (int)rank * p.half_n);
+                    tma_load_2d_pair(s_ring + (size_t)lane * b_sub, &map_b, lb, kc * BK, tap * p.cout_pad + (int)rank * p.half_n, pol_w);
                 }
                 __syncwarp();
             }
@@ -652,7 +674,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     if (lane == 0 && rank == 0) mbar_expect_tx(&h_full[hs], h_tx);
                     if (lane < p.a_chunks * p.halo_planes) {       // buffer order: [plane][chunk]; plane coordinates == output coordinates
                         const int plane = lane / p.a_chunks, kc = lane - plane * p.a_chunks;
-                        tma_load_3d_pair(h_ring + (size_t)hs * p.h_stage_bytes + (size_t)lane * p.h_chunk_bytes, &maps_a.m[plane], lb, kc * BK, x0 - 1, y0 - 1);
+                        tma_load_3d_pair(h_ring + (size_t)hs * p.h_stage_bytes + (size_t)lane * p.h_chunk_bytes, &maps_a.m[plane], lb, kc * BK, x0 - 1, y0 - 1, pol_a);
                     }
                     __syncwarp();
                     if (++hs == p.h_stages) { hs = 0; h_phase ^= 1; }
@@ -689,9 +711,9 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     if (!p.halo && pair == first_pair && g == 0) { pdl_wait(); tick(2, lane == 0); if (lane == 0) trace_dep(p.trace); }   // first activation load
                     if (lane == 0 && rank == 0) mbar_expect_tx(&s_full[st], s_tx);
                     if (lane < p.n_sub) {
-                        if (p.flat) tma_load_im2col_pair(sb + (size_t)lane * sub_bytes, &map_a0, lb, ka * BK, fw, fh, fo.n, tap_s, tap_r);
-                        else if (!p.halo) tma_load_3d_pair(sb + (size_t)lane * sub_bytes, &maps_a.m[sel], lb, ka * BK, x0 + dx, y0 + dy);
-                        tma_load_2d_pair(sb + (size_t)lane * sub_bytes + a_sub, &map_b, lb, kb * BK, tap * p.cout_pad + n0);
+                        if (p.flat) tma_load_im2col_pair(sb + (size_t)lane * sub_bytes, &map_a0, lb, ka * BK, fw, fh, fo.n, tap_s, tap_r, pol_a);
+                        else if (!p.halo) tma_load_3d_pair(sb + (size_t)lane * sub_bytes, &maps_a.m[sel], lb, ka * BK, x0 + dx, y0 + dy, pol_a);
+                        tma_load_2d_pair(sb + (size_t)lane * sub_bytes + a_sub, &map_b, lb, kb * BK, tap * p.cout_pad + n0, pol_w);
                     }
                     __syncwarp();
                     if (pair == first_pair && g == 0) tick(3, lane == 0);
@@ -798,6 +820,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             // uses its slot k % res_depth, so the loads run res_depth chunks ahead of each group (the DRAM latency of
             // the addend was the top stall of the memory-bound residual layers with a single slot)
             pdl_wait();
+            const uint64_t pol_r = l2_policy(p.hint_res);
             int grp = 0, slot[kEpiGroups] = {}; uint32_t sphase[kEpiGroups] = {};
             const int n_chunks = p.block_n / p.chunk_cols;
             const uint32_t bytes = p.has_res == 1 ? (uint32_t)(p.tw * p.th * p.row_bytes) : (uint32_t)(p.up_bw * p.up_bh * 128);
@@ -813,7 +836,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     if (elect_one()) {
                         mbar_expect_tx(&res_full[rb], bytes);
                         if (p.flat) tma_load_im2col(res_buf + rb * p.res_buf_bytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, fo.x, fo.y, fo.n);
-                        else tma_load_3d(res_buf + rb * p.res_buf_bytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0);
+                        else tma_load_3d(res_buf + rb * p.res_buf_bytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0, pol_r);
                     }
                     __syncwarp();
                     if (++slot[grp] == p.res_depth) { slot[grp] = 0; sphase[grp] ^= 1; }
@@ -973,17 +996,6 @@ struct Tc2Plan {
 // than 8 pixels (their TMA boxes degenerate into many 128..512-byte rows and they share little halo in L2).
 // NCHW heads: the widest row segment among tiles that are at least 75 % full, so that the per-channel fp32
 // stores of a warp form few long runs without idling a large part of the epilogue lanes.
-FastDiv make_fastdiv(int d) {
-    FastDiv f = {0u, 0u, 1u, (uint32_t)d};
-    if (d <= 1) return f;
-    int l = 0;
-    while ((1ll << l) < d) ++l;
-    f.mul = (uint32_t)(((1ull << (31 + l)) + (unsigned long long)d - 1) / (unsigned long long)d);
-    f.shift = (uint32_t)(l - 1);
-    f.one = 0u;
-    return f;
-}
-
 int pick_tile_w(int w, bool widest) {
     int best = 1, best_score = -1;
     for (int tw = 1; tw <= w && tw <= kBlockM; ++tw) {
@@ -1100,11 +1112,11 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     p.total_rows = d.batch * d.out_rows;
     const int tiles_y = p.flat ? (p.flat_total + kBlockM - 1) / kBlockM : (p.total_rows + p.th - 1) / p.th;
     p.pairs_y = (tiles_y + 1) / 2;
-    p.d_tiles_n = make_fastdiv(p.tiles_n); p.d_tiles_x = make_fastdiv(p.tiles_x); p.d_out_rows = make_fastdiv(d.out_rows);
-    p.d_tw = make_fastdiv(p.tw); p.d_flat_hw = make_fastdiv(p.flat_hw); p.d_out_w = make_fastdiv(d.out_w);
+    p.d_tiles_n = om::make_fastdiv(p.tiles_n); p.d_tiles_x = om::make_fastdiv(p.tiles_x); p.d_out_rows = om::make_fastdiv(d.out_rows);
+    p.d_tw = om::make_fastdiv(p.tw); p.d_flat_hw = om::make_fastdiv(p.flat_hw); p.d_out_w = om::make_fastdiv(d.out_w);
     p.taps = d.ksize * d.ksize; p.stride = d.stride;
     p.k_chunks = (split ? 3 : 1) * (d.cin / bk); p.a_chunks = (split ? 2 : 1) * (d.cin / bk); p.split_kr = split ? d.cin / bk : 0;
-    p.d_k_chunks = make_fastdiv(p.k_chunks);
+    p.d_k_chunks = om::make_fastdiv(p.k_chunks);
     p.acc_scale = (split && d.acc_scale != 0.0f) ? d.acc_scale : 1.0f;
     if (split && !getenv("ORIENMASK_B200_NO_GAIN_FIX")) {
         // tcgen05 truncates its fp32 running sum: every MMA into a non-empty accumulator loses a fraction of an ulp toward zero, which
@@ -1212,6 +1224,18 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     p.up_rows = d.up_rows; p.bias = d.bias; p.upadd = d.upadd;
     p.cout_stride = d.cout_stride; p.output = d.output;
     p.out_s2d = d.out_s2d; p.s2d_plane = (long long)d.batch * d.out_rows / 2 * (d.out_w / 2);
+    {
+        // L2 eviction priorities (experiment: ORIENMASK_B200_L2HINT=mode)
+        const char* he = getenv("ORIENMASK_B200_L2HINT");
+        const int mode = he ? atoi(he) : 0;
+        const bool res_layer = d.residual != nullptr && d.out_kind == OM_OUT_ACT;
+        const bool squeeze = d.ksize == 1 && d.stride == 1 && d.out_kind == OM_OUT_ACT && d.cout < d.cin && d.upadd == nullptr;
+        if (mode == 1 || mode == 2) { if (res_layer) p.hint_a = 1; }
+        if (mode == 1 || mode == 3) { if (res_layer) p.hint_out = 2; if (squeeze) p.hint_a = 2; }
+        if (mode == 4) { if (res_layer) { p.hint_a = 1; p.hint_res = 1; } }
+        if (mode == 5) { p.hint_w = 2; }
+        if (mode == 6) { if (res_layer) { p.hint_a = 1; } p.hint_w = 2; }
+    }
 
     const size_t esz = 2;
     int32_t rc = OM_OK;

@@ -58,6 +58,7 @@ constexpr int kStreamBytes = kXStages * kXStage + kYBytes;
 constexpr int kSmem = 1024 + kStreams * kStreamBytes + kW1Bytes + kW2Bytes + 1024;
 
 struct BlockParams {
+    FastDiv d_tiles_x, d_rows;
     int tiles_x, tiles_y;
     int width, height, rows, total_rows;     // output == input geometry (stride 1)
     int out_s2d;
@@ -83,12 +84,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (ok) return;
     }
     const long long t0 = clock64();
-    while (true) {                                     // suspend-time hint: the hardware parks the warp instead of re-issuing the poll
+    for (uint32_t spins = 1;; ++spins) {               // suspend-time hint: the hardware parks the warp instead of re-issuing the poll
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000ll) __trap();
+        if ((spins & 63u) == 0u && clock64() - t0 > 4000000000ll) __trap();
     }
 }
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {          // K-major, 128-byte rows, dense 8-row groups
@@ -178,7 +179,7 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
     const int total = p.tiles_x * p.tiles_y;
     constexpr uint32_t kXBytes = kHalo * 128;
     auto load_x = [&](int tile, int stage) {
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        const int ty = fdiv(tile, p.d_tiles_x), tx = tile - ty * p.tiles_x;
         const uint32_t bar = smem_u32(&x_full[stage]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kXBytes) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -214,7 +215,7 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
     };
     if (kXStages == 2 && warp == 0 && first < total) mma1(0);
     for (int tile = first; tile < total; tile += step) {
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        const int ty = fdiv(tile, p.d_tiles_x), tx = tile - ty * p.tiles_x;
         const int x0 = tx * kTW, y0 = ty * kTH;
         // the next tile's halo into the other stage: its last readers (epilogue 2 of the previous tile) are behind the barrier that ended
         // the previous iteration
@@ -234,17 +235,22 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
                 if (r < kHalo) {
                     const int hy = r / kHW, hx = r - hy * kHW;
                     const int gx = x0 - 1 + hx, Y = y0 - 1 + hy;
-                    const int img = Y >= 0 ? Y / p.rows : 0;
+                    const int img = Y >= 0 ? fdiv(Y, p.d_rows) : 0;
                     const bool inside = gx >= 0 && gx < p.width && Y >= 0 && Y < p.total_rows && (Y - img * p.rows) < p.height;
                     uint32_t w[16];
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        float a = __uint_as_float(v[2 * q]) + s_b1[2 * q];
-                        float b = __uint_as_float(v[2 * q + 1]) + s_b1[2 * q + 1];
-                        a = fmaxf(a, 0.1f * a);
-                        b = fmaxf(b, 0.1f * b);
-                        const __half2 hv = inside ? __floats2half2_rn(a, b) : __floats2half2_rn(0.0f, 0.0f);
-                        w[q] = *reinterpret_cast<const uint32_t*>(&hv);
+                    for (int q = 0; q < 16; q += 2) {
+                        const float4 bv = *reinterpret_cast<const float4*>(s_b1 + 2 * q);          // warp-uniform: smem broadcast
+                        float a = __uint_as_float(v[2 * q]), b = __uint_as_float(v[2 * q + 1]);
+                        float c = __uint_as_float(v[2 * q + 2]), d = __uint_as_float(v[2 * q + 3]);
+                        add2(a, b, bv.x, bv.y); add2(c, d, bv.z, bv.w);
+                        float ma, mb, mc, md;
+                        mul2(ma, mb, a, b, 0.1f); mul2(mc, md, c, d, 0.1f);
+                        a = fmaxf(a, ma); b = fmaxf(b, mb); c = fmaxf(c, mc); d = fmaxf(d, md);
+                        const __half2 h0 = inside ? __floats2half2_rn(a, b) : __floats2half2_rn(0.0f, 0.0f);
+                        const __half2 h1 = inside ? __floats2half2_rn(c, d) : __floats2half2_rn(0.0f, 0.0f);
+                        w[q] = *reinterpret_cast<const uint32_t*>(&h0);
+                        w[q + 1] = *reinterpret_cast<const uint32_t*>(&h1);
                     }
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
@@ -283,7 +289,7 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
             uint32_t v[32];
             tmem_ld32(tmem + ((quad * 32u) << 16) + 2 * kC + half * 32, v);
             const int gx = x0 + ox, Y = y0 + oy;
-            const int img = Y / p.rows, yin = Y - img * p.rows;
+            const int img = fdiv(Y, p.d_rows), yin = Y - img * p.rows;
             const bool valid = gx < p.width && Y < p.total_rows && yin < p.height;
             const int rr = (oy + 1) * kHW + ox + 1;                       // this pixel inside the x halo
             const uint8_t* xrow = s_x + stage * kXStage + rr * 128;
@@ -302,13 +308,14 @@ dark_block_kernel(const __grid_constant__ CUtensorMap map_x, const BlockParams p
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int ch = i + c8 * 8 + 2 * q;
-                            float a = __uint_as_float(v[ch]) + s_b2[half * 32 + ch];
-                            float b = __uint_as_float(v[ch + 1]) + s_b2[half * 32 + ch + 1];
-                            a = fmaxf(a, 0.1f * a);
-                            b = fmaxf(b, 0.1f * b);
+                            const float2 bv = *reinterpret_cast<const float2*>(s_b2 + half * 32 + ch);
+                            float a = __uint_as_float(v[ch]), b = __uint_as_float(v[ch + 1]);
+                            add2(a, b, bv.x, bv.y);
+                            float ma, mb;
+                            mul2(ma, mb, a, b, 0.1f);
+                            a = fmaxf(a, ma); b = fmaxf(b, mb);
                             const float2 rf = __half22float2(rh[q]);
-                            a += rf.x;
-                            b += rf.y;
+                            add2(a, b, rf.x, rf.y);
                             const __half2 hv = __floats2half2_rn(a, b);
                             wv[c8 * 4 + q] = *reinterpret_cast<const uint32_t*>(&hv);
                         }
@@ -364,6 +371,7 @@ int32_t dark_block_run(const void* x, const void* w1, const float* b1, const voi
     BlockParams p;
     p.tiles_x = (width + kTW - 1) / kTW;
     p.tiles_y = (batch * rows + kTH - 1) / kTH;
+    p.d_tiles_x = make_fastdiv(p.tiles_x); p.d_rows = make_fastdiv(rows);
     p.width = width; p.height = height; p.rows = rows; p.total_rows = batch * rows;
     p.out_s2d = out_s2d; p.s2d_plane = (long long)batch * rows / 2 * (width / 2);
     p.w1 = reinterpret_cast<const __half*>(w1); p.w2 = reinterpret_cast<const __half*>(w2); p.b1 = b1; p.b2 = b2;
