@@ -27,6 +27,7 @@ UNITS = [
     ('conv_tc2.cu', []),
     ('conv_stem_tc.cu', []),
     ('dark_block.cu', []),
+    ('stem_fused.cu', []),
 ]
 
 

@@ -18,6 +18,11 @@ void tc2_plan_info(const void* plan, int32_t* info24);
 int32_t stem_tc_run(const float* image, const float* weights, const float* bias, void* output, int batch, int h, int w, int rows,
                     int out_s2d, cudaStream_t stream, int split = 0);
 
+// first two layers in one launch: stem 3 -> 32 + stride-2 32 -> 64 (stem_fused.cu)
+bool stem_fused_supported(int h, int w, const void* image);
+int32_t stem_fused_run(const float* image, const float* w27, const float* b1, const void* w2, const float* b2, void* out, int batch, int h,
+                       int w, int out_rows, cudaStream_t stream);
+
 // fused DarkNet block, C = 32 (dark_block.cu)
 bool dark_block_supported(int cin, int cmid, int width, int rows);
 int32_t dark_block_run(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, void* out, int batch, int height,

@@ -45,6 +45,7 @@ struct Layer {
     bool is_stem = false;
     const float* stem_w = nullptr;
     const float* stem_b = nullptr;
+    bool is_stem2 = false;      // stem + backbone.conv2.0 in one launch (stem_fused.cu): stem_w / stem_b + blk_w2 / blk_b2, desc.output = x
     bool is_block = false;      // fused DarkNet block (dark_block.cu): desc.input = x, desc.output = out, the two weight sets below
     const void* blk_w1 = nullptr; const void* blk_w2 = nullptr;
     const float* blk_b1 = nullptr; const float* blk_b2 = nullptr;
@@ -345,7 +346,7 @@ struct om_engine {
             const void* wp = nullptr; const float* bp = nullptr; float sc;
             weights("backbone.conv1", true, 32, 3, 0, 3, 3, true, &wp, &bp, &sc, OM_PREC_F32);
             L.stem_w = reinterpret_cast<const float*>(wp); L.stem_b = bp;
-            c1 = act(1, 32, false, true);
+            if (!(cfg.precision == OM_PREC_F16 && om::stem_fused_supported(H, W, nullptr))) c1 = act(1, 32, false, true);   // (fused below: never materialised)
             L.desc.precision = cfg.precision; L.desc.batch = B; L.desc.in_h = L.desc.out_h = H; L.desc.in_w = L.desc.out_w = W;
             L.desc.in_rows = L.desc.out_rows = rows(1); L.desc.cin = 3; L.desc.cout = 32; L.desc.ksize = 3; L.desc.stride = 1; L.desc.leaky = 1;
             L.desc.output = c1.ptr; L.desc.out_s2d = 1;
@@ -354,12 +355,25 @@ struct om_engine {
             snprintf(L.shape, sizeof(L.shape), "3x3 s1 3->32 @%dx%d stem", H, W);
             layers.push_back(L);
         }
+        // fp16 engine: the stem and backbone.conv2.0 run as ONE launch (stem_fused.cu) -- the stem's full-resolution output never
+        // reaches memory.  The stem layer emitted above becomes that launch once conv2.0's weights and output buffer exist.
+        const bool fuse_stem = cfg.precision == OM_PREC_F16 && om::stem_fused_supported(H, W, nullptr);
         Buf trunk = c1;
         Buf feats[6];            // by log2(stride)
         for (int i = 0; i < 5; ++i) {
             const int c = kStageChannels[i], n = kStageBlocks[i], st = 2 << i;
             const std::string stage = "backbone.conv" + std::to_string(i + 2);
             Buf x = act(st, 2 * c), y = act(st, c);
+            if (i == 0 && fuse_stem && rc == OM_OK) {
+                Layer& L = layers.back();
+                float sc;
+                if (!weights(stage + ".0", true, 2 * c, c, 0, c, 3, true, &L.blk_w2, &L.blk_b2, &sc, OM_PREC_F16) && !sizing) return;
+                L.name = "backbone.conv1 + conv2.0 (fused)"; L.is_stem = false; L.is_stem2 = true;
+                L.desc.output = x.ptr; L.desc.out_s2d = 0; L.desc.out_h = H / 2; L.desc.out_w = W / 2; L.desc.out_rows = rows(2); L.desc.cout = 2 * c;
+                L.flops += 2.0 * B * (H / 2) * (W / 2) * (2.0 * c) * c * 9;
+                L.bytes = (double)B * H * W * 3 * 4 + (double)B * (H / 2) * (W / 2) * 2 * c * 2 + (27.0 * 32 + 9.0 * 2 * c * c) * 2;
+                snprintf(L.shape, sizeof(L.shape), "3x3 s1 3->32 @%dx%d + 3x3 s2 32->64 @%dx%d fused", H, W, H / 2, W / 2);
+            } else
             cbl(stage + ".0", trunk, c, 2 * c, x, 3, 2);
             for (int b = 1; b <= n; ++b) {
                 const std::string blk = stage + "." + std::to_string(b);
@@ -528,6 +542,12 @@ static int32_t run_layer(const om_engine* e, const Layer& L, const float* image,
         if (!image) return om::fail(OM_ERR_INVALID, "om_forward: null image");
         return om_stem_conv(e->cfg.precision, image, L.stem_w, L.stem_b, L.desc.output, e->cfg.batch, e->cfg.height, e->cfg.width, L.desc.in_rows, 32,
                             1, st);
+    }
+    if (L.is_stem2) {
+        if (!image) return om::fail(OM_ERR_INVALID, "om_forward: null image");
+        if (reinterpret_cast<uintptr_t>(image) & 15) return om::fail(OM_ERR_INVALID, "om_forward: the fp16 engine needs a 16-byte aligned image");
+        return om::stem_fused_run(image, L.stem_w, L.stem_b, L.blk_w2, L.blk_b2, L.desc.output, e->cfg.batch, e->cfg.height, e->cfg.width,
+                                  L.desc.out_rows, st);
     }
     if (L.is_block)
         return om::dark_block_run(L.desc.input, L.blk_w1, L.blk_b1, L.blk_w2, L.blk_b2, L.desc.output, e->cfg.batch, L.desc.out_h, L.desc.out_w,
