@@ -218,6 +218,9 @@ int32_t om_debug_conv_timeline(void* device_u64x16);
  * resolved (griddepcontrol.wait returned), [2] last CTA end, [3] last CTA start.  Returns the records handed out since the previous
  * call.  tools/timeline.py: the in-situ timeline of a pipelined forward (what ncu's serialised launch list cannot show). */
 int32_t om_debug_trace(void* records, int32_t capacity);
+/* Phase log of the fused stem kernel: stream 0 of CTA 0 stamps %globaltimer at the phase boundaries of its first 16 tiles into
+ * [16][8] uint64 (tile start, patch arrived, im2col rows done, MMA 1 done, epilogue 1 done, MMA 2 done, epilogue 2 done). NULL disarms. */
+int32_t om_debug_phase_log(void* device_u64x128);
 
 /*
  * First layer (3 -> cout, 3x3, stride 1, BN folded, LeakyReLU) straight from the caller's image.

@@ -104,6 +104,7 @@ SIGNATURES = {
     'om_debug_conv_plan_info': (c_i32, [c_vp, ctypes.POINTER(c_i32)]),
     'om_debug_conv_timeline': (c_i32, [c_vp]),
     'om_debug_trace': (c_i32, [c_vp, c_i32]),
+    'om_debug_phase_log': (c_i32, [c_vp]),
     'om_engine_workspace_bytes': (c_i32, [ctypes.POINTER(EngineConfig), ctypes.POINTER(ctypes.c_size_t)]),
     'om_engine_create': (c_i32, [ctypes.POINTER(EngineConfig), ctypes.POINTER(OmTensor), c_i32, c_vp, ctypes.c_size_t, c_vp,
                                  ctypes.POINTER(c_vp)]),

@@ -127,3 +127,8 @@ extern "C" int32_t om_debug_trace(void* records, int32_t capacity) {
     om::g_trace_used = 0;
     return used;
 }
+
+// Debug: device buffer of 16 x 8 uint64 that stream 0 of CTA 0 of the fused stem kernel fills with %globaltimer stamps at the phase
+// boundaries of its first 16 tiles (tile start, patch arrived, im2col done, MMA 1 done, epilogue 1 done, MMA 2 done, epilogue 2 done).
+namespace om { int32_t stem_fused_set_phase_log(void* dev_ptr); }
+extern "C" int32_t om_debug_phase_log(void* device_u64x128) { return om::stem_fused_set_phase_log(device_u64x128); }

@@ -125,6 +125,12 @@ __device__ __forceinline__ void stream_sync(int stream) {                 // nam
 // 16-byte chunk c (0..3) of 64-byte row r in a SWIZZLE_64B K-major tile whose base is 1024-byte aligned
 __device__ __forceinline__ uint32_t swz64(int r, int c) { return (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)); }
 
+// Debug phase log (om_debug_phase_log): stream 0 of CTA 0 stamps %globaltimer at the phase boundaries of its first tiles.
+__device__ unsigned long long* g_phase_log = nullptr;
+__device__ __forceinline__ void phase_tick(int tile_no, int slot, bool who) {
+    if (g_phase_log != nullptr && who && tile_no < 16) g_phase_log[tile_no * 8 + slot] = trace_now();
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 stem_fused_kernel(const __grid_constant__ CUtensorMap map_img, const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -204,14 +210,19 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_img, const FusedParams
     if (tid == 0 && first < p.total) load_patch(first, 0);
     int stage = 0;
     uint32_t pphase[2] = {0, 0}, d1phase = 0, d2phase = 0;
+    const bool logger = blockIdx.x == 0 && threadIdx.x == 0;
+    int tile_no = -1;
     for (int tile = first; tile < p.total; tile += step) {
         int n, ty, tx;
         decode(tile, n, ty, tx);
+        ++tile_no;
+        phase_tick(tile_no, 0, logger);
         // the next tile's patch into the other stage: its last readers (the gather of the previous tile) are behind the barriers that
         // ended the previous iteration
         if (tid == 0 && tile + step < p.total) load_patch(tile + step, stage ^ 1);
         mbar_wait(&p_full[stage], pphase[stage]);
         pphase[stage] ^= 1;
+        phase_tick(tile_no, 1, logger);
         // ---- im2col rows.  Row r = plane * 160 + pr: the stem pixel that ends up at entry pr = jj * 9 + ii of parity plane `plane`
         // (exactly where epilogue 1 will write it, so MMA 1 row r <-> plane row r), k = (ky*3 + kx)*3 + ci.  A thread gathers a PAIR of
         // horizontally adjacent stem pixels -- the odd-column one at entry ii and the even-column one at entry ii + 1 of the same stem
@@ -264,6 +275,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_img, const FusedParams
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         stream_sync(stream);
+        phase_tick(tile_no, 2, logger);
         // ---- MMA 1: stem pixels [640 x 32] = rows [640 x 32] * W1^T -> TMEM columns g*32 .. +31 for rows g*128 .. +127 ----
         if (warp == 0) {
             if (elect_one()) {
@@ -283,6 +295,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_img, const FusedParams
         mbar_wait(bar_d1, d1phase);
         d1phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        phase_tick(tile_no, 3, logger);
         // ---- epilogue 1: row r = g*128 + quad*32 + lane = plane * 160 + pr -> 64 bytes at entry pr of its parity plane, i.e. over the
         // im2col row it came from.  plane = 2*(row odd) + (column odd); entry (jj, ii) of a plane is the stem pixel
         // (2*(y0 - 1 + jj) + row parity, 2*(x0 - 1 + ii) + column parity), y0 / x0 the tile origin in output pixels. ----
@@ -318,6 +331,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_img, const FusedParams
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         stream_sync(stream);                             // every accumulator of MMA 1 is drained, every plane is written
+        phase_tick(tile_no, 4, logger);
         // ---- MMA 2: nine taps over the four planes (shifted descriptors), resident W2 -> TMEM columns 0 .. 63 ----
         if (warp == 0) {
             if (elect_one()) {
@@ -339,6 +353,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_img, const FusedParams
         mbar_wait(bar_d2, d2phase);
         d2phase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        phase_tick(tile_no, 5, logger);
         // ---- epilogue 2: output pixel m = quad*32 + lane, channels half*32 .. +31: + b2, LeakyReLU, fp16, store ----
         {
             const int m = (int)(quad * 32) + lane;
@@ -369,6 +384,7 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_img, const FusedParams
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         stream_sync(stream);                             // patch[stage], the operand tile and the accumulators of this stream are free again
+        phase_tick(tile_no, 6, logger);
         stage ^= 1;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -380,6 +396,11 @@ stem_fused_kernel(const __grid_constant__ CUtensorMap map_img, const FusedParams
 }  // namespace
 
 namespace om {
+
+int32_t stem_fused_set_phase_log(void* dev_ptr) {
+    OM_CUDA_TRY(cudaMemcpyToSymbol(g_phase_log, &dev_ptr, sizeof(void*)));
+    return OM_OK;
+}
 
 bool stem_fused_supported(int h, int w, const void* image) {
     const char* e = getenv("ORIENMASK_B200_FUSED_STEM");

@@ -17,7 +17,7 @@ int main(void) {
                   (fn)om_post_workspace_bytes, (fn)om_decode_select, (fn)om_batched_nms, (fn)om_mask_assemble,
                   (fn)om_nms, (fn)om_nms_ex, (fn)om_conv_create, (fn)om_conv_run, (fn)om_conv_run_to, (fn)om_conv_destroy,
                   (fn)om_stem_conv, (fn)om_preprocess, (fn)om_mask_rle, (fn)om_mask_areas, (fn)om_mask_blend,
-                  (fn)om_debug_conv_plan_info, (fn)om_debug_conv_timeline, (fn)om_debug_trace, (fn)om_engine_workspace_bytes, (fn)om_engine_create,
+                  (fn)om_debug_conv_plan_info, (fn)om_debug_conv_timeline, (fn)om_debug_trace, (fn)om_debug_phase_log, (fn)om_engine_workspace_bytes, (fn)om_engine_create,
                   (fn)om_forward, (fn)om_engine_destroy, (fn)om_engine_layer_count, (fn)om_engine_layer_info, (fn)om_engine_run_layer, (fn)om_engine_run_layers};
     memset(&cfg, 0, sizeof cfg);
     rc = om_post_workspace_bytes(&cfg, 1, &bytes);
