@@ -71,6 +71,11 @@ struct Tc2Params {
     int has_res;                         // epilogue addend staged by TMA: 0 none, 1 residual (fp16, same resolution, after the
                                          // activation), 2 up-add (fp32 half-resolution partial sum, before bias and activation)
     int res_depth;                       // addend staging slots per epilogue group (1..2)
+    int res_bufs, res_bufs_log2;         // addend staging buffers (kEpiGroups * res_depth): chunk number `seq` of the CTA's chunk sequence uses
+                                         // buffer seq % res_bufs (phase (seq / res_bufs) & 1) and is consumed by epilogue group seq % kEpiGroups.
+                                         // (Tried: 64-column chunks of the tensor-bound 68x68 residual layers in TWO buffers shared by the
+                                         // four groups, to halve the staging's TMA rows -- no gain, in-situ A/B; a buffer shared across
+                                         // groups also needs an extra wait, because a parity wait is only meaningful within one phase.)
     int res_buf_bytes;                   // one staged 32-column chunk: 128 rows x 64 B (fp16 residual) or x 128 B (fp32 up-add)
     int up_bw, up_bh;                    // up-add box: tw/2 + 1 by th/2 + 1 source pixels (covers odd tile origins)
     int chunk_cols;                      // accumulator columns per staged chunk (64 fp16 / 32 fp32 / 32 narrow fp16)
@@ -362,8 +367,8 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
     const bool in_tile = m < p.tw * p.th;
     const uint64_t pol_out = l2_policy(p.hint_out);
     int as = 0; uint32_t aphase = 0;
-    int rslot = 0; uint32_t rphase = 0;                 // this group's addend slot and its phase
-    int g0 = 0;                                          // sequence number (mod kEpiGroups) of the tile's first chunk
+    int seq0 = 0;                                        // sequence number of the tile's first chunk in this CTA's chunk sequence
+    int g0 = 0;                                          // ... mod kEpiGroups
     for (int pair = c.first_pair; pair < c.num_pairs; pair += c.pair_step) {
         if (pair == c.first_pair) pdl_wait();          // while the first accumulator is still being produced
         const int j_first = (grp - g0) & (kEpiGroups - 1);
@@ -377,6 +382,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
             __syncwarp();
             if (c.lane == 0) mbar_arrive_cluster(c.leader_tmem_empty0 + (uint32_t)(as * 8));
             g0 = (g0 + n_chunks) & (kEpiGroups - 1);
+            seq0 += n_chunks;
             if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
             continue;
         }
@@ -410,8 +416,11 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
             up = p.upadd + ((size_t)(img * p.up_rows + (y >> 1)) * (p.out_w >> 1) + (x >> 1)) * p.cout;
         const int up_row = ((Y >> 1) - (y0 >> 1)) * p.up_bw + ((x >> 1) - (x0 >> 1));   // source pixel inside the staged box
         for (int j = j_first; j < n_chunks; j += kEpiGroups) {
-            const int rb = grp + kEpiGroups * rslot;
-            if (ADD == 1 || ADD == 2) mbar_wait(&c.res_full[rb], rphase);
+            const int seq = seq0 + j;
+            const int rb = seq & (p.res_bufs - 1);
+            if (ADD == 1 || ADD == 2) {
+                mbar_wait(&c.res_full[rb], (uint32_t)(seq >> p.res_bufs_log2) & 1u);
+            }
             for (int c0 = 0; c0 < p.chunk_cols; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(j * p.chunk_cols + c0), v);
@@ -558,10 +567,10 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
             if (ADD == 1 || ADD == 2) {
                 __syncwarp();
                 if (c.lane == 0) mbar_arrive(&c.res_empty[rb]);
-                if (++rslot == p.res_depth) { rslot = 0; rphase ^= 1; }
             }
         }
         g0 = (g0 + n_chunks) & (kEpiGroups - 1);
+        seq0 += n_chunks;
         if (++as == p.acc_stages) { as = 0; aphase ^= 1; }
     }
     tick(7, c.warp == kEpiWarp0 && c.lane == 0);
@@ -584,7 +593,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
     uint8_t* h_ring = smem;                                             // [h_stages][h_stage_bytes]   (halo mode only)
     uint8_t* s_ring = smem + (size_t)p.h_stages * p.h_stage_bytes;      // [stages][n_sub][A box | B block]
     uint8_t* res_buf = s_ring + (size_t)p.stages * stage_bytes;         // [2][kStageBytes] (has_res only)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(res_buf + (p.has_res ? kEpiGroups * p.res_depth * p.res_buf_bytes : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(res_buf + (p.has_res ? p.res_bufs * p.res_buf_bytes : 0));
     uint64_t* s_full = bars;                           // [stages]     (the leader's copies of the full barriers are the live ones)
     uint64_t* s_empty = bars + kMaxStages;             // [stages]
     uint64_t* h_full = bars + 2 * kMaxStages;          // [h_stages]
@@ -821,7 +830,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
             // the addend was the top stall of the memory-bound residual layers with a single slot)
             pdl_wait();
             const uint64_t pol_r = l2_policy(p.hint_res);
-            int grp = 0, slot[kEpiGroups] = {}; uint32_t sphase[kEpiGroups] = {};
+            int seq = 0;
             const int n_chunks = p.block_n / p.chunk_cols;
             const uint32_t bytes = p.has_res == 1 ? (uint32_t)(p.tw * p.th * p.row_bytes) : (uint32_t)(p.up_bw * p.up_bh * 128);
             for (int pair = first_pair; pair < num_pairs; pair += pair_step) {
@@ -831,16 +840,15 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 FlatOrigin fo = {0, 0, 0};
                 if (p.flat) fo = flat_origin(p, 2 * t.py + (int)rank);
                 for (int j = 0; j < n_chunks; ++j) {
-                    const int rb = grp + kEpiGroups * slot[grp];
-                    mbar_wait(&res_empty[rb], sphase[grp] ^ 1);
+                    const int rb = seq & (p.res_bufs - 1);
+                    mbar_wait(&res_empty[rb], ((uint32_t)(seq >> p.res_bufs_log2) & 1u) ^ 1u);
                     if (elect_one()) {
                         mbar_expect_tx(&res_full[rb], bytes);
                         if (p.flat) tma_load_im2col(res_buf + rb * p.res_buf_bytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, fo.x, fo.y, fo.n);
                         else tma_load_3d(res_buf + rb * p.res_buf_bytes, &map_res, &res_full[rb], t.tn * p.block_n + j * p.chunk_cols, x0, y0, pol_r);
                     }
                     __syncwarp();
-                    if (++slot[grp] == p.res_depth) { slot[grp] = 0; sphase[grp] ^= 1; }
-                    grp = (grp + 1) & (kEpiGroups - 1);
+                    ++seq;
                 }
             }
         }
@@ -1165,7 +1173,9 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
         const char* rd_env = getenv("ORIENMASK_B200_RESDEPTH");
         if (p.has_res && rd_env && atoi(rd_env) >= 1 && atoi(rd_env) <= 2) p.res_depth = atoi(rd_env);
     }
-    const int epi_bytes = p.has_res ? kEpiGroups * p.res_depth * p.res_buf_bytes : 0;
+    p.res_bufs = kEpiGroups * p.res_depth;
+    p.res_bufs_log2 = p.res_bufs == 4 ? 2 : 3;
+    const int epi_bytes = p.has_res ? p.res_bufs * p.res_buf_bytes : 0;
     constexpr int kMaxSmem = 227 * 1024;
     const int fixed = 1024 + epi_bytes + (4 * kMaxStages + 2 * kMaxAcc + 2 * kMaxResBufs) * 8 + 16 + cout_pad * 4;
     {

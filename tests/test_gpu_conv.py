@@ -25,6 +25,7 @@ CASES = [
     (2, 512, 256, 12, 12, 1, 1, ACT, False, True),
     (1, 128, 256, 136, 136, 3, 1, ACT, False, False),
     (1, 128, 256, 68, 68, 3, 1, ACT, True, False),        # halo tiles with a partial last tile column (68 = 8*8 + 4)
+    (8, 128, 256, 68, 68, 3, 1, ACT, True, False),        # ... several tiles per CTA, N = 256: 64-column residual chunks in two shared buffers
     (2, 64, 64, 24, 72, 3, 1, ACT, False, False),
     (3, 32, 64, 40, 16, 3, 1, ACT, True, False),          # 64-byte pixels (SWIZZLE_64B halo)
     (2, 256, 128, 17, 17, 1, 1, ACT, False, False),

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 evidence visit: every GPU test, the bench (+ reference arm), ncu launch lists / traffic / full captures, sanitizer.  -> gpurun_out/
 mkdir -p gpurun_out
-what="${*:-tests bench ncu full sanitizer}"
+what="${*:-tests bench timeline ncu full sanitizer}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 if [[ $what == *tests* ]]; then
   for f in test_gpu_conv test_gpu_post test_gpu_forward test_prep test_coco_format test_visualizer test_gpu_eager_bar test_gpu_reference_dropin; do
@@ -26,8 +26,17 @@ if [[ $what == *ncu* ]]; then
       python tools/profile_step.py --steps 1 --precision parity --coco 0 > gpurun_out/ncu_launches_parity.log 2>&1; echo "ncu parity launches exit $?"
   timeout 600 python tools/profile_step.py --steps 1 --events 10 --coco 0 > /dev/null 2>&1; cp gpurun_out/layer_events.json gpurun_out/layer_events_fp16.json
 fi
+if [[ $what == *timeline* ]]; then
+  timeout 300 python tools/timeline.py --md gpurun_out/timeline.md > gpurun_out/timeline.log 2>&1; tail -1 gpurun_out/timeline.log
+  timeout 300 python tools/timeline.py --batch 1 --md gpurun_out/timeline_bs1.md > gpurun_out/timeline_bs1.log 2>&1; tail -1 gpurun_out/timeline_bs1.log
+  timeout 300 python tools/timeline.py --precision parity --md gpurun_out/timeline_parity.md > gpurun_out/timeline_parity.log 2>&1; tail -1 gpurun_out/timeline_parity.log
+  timeout 300 python tools/timeline.py --variants unfused:ORIENMASK_B200_FUSED_STEM=0,ORIENMASK_B200_FUSED_BLOCK=0 fused: --md gpurun_out/timeline_fusion_ab.md > /dev/null 2>&1
+  timeout 120 python tools/phase_log.py > gpurun_out/phase_log_stem_fused.txt 2>&1
+fi
 if [[ $what == *full* ]]; then
-  for spec in "conv_tc2_kernel 84 fp16 prof_conv136" "conv_tc2_kernel 84 parity prof_conv136_parity" "conv_tc2_kernel 44 fp16 prof_conv17_flat" "stem_tc_kernel 0 fp16 prof_stem"; do
+  # conv_tc2 launch index = layer index - 2 in the fp16 schedule (fused stem + conv2.0, fused block), layer index - 1 in the parity one
+  for spec in "conv_tc2_kernel 81 fp16 prof_conv136" "conv_tc2_kernel 84 parity prof_conv136_parity" "conv_tc2_kernel 43 fp16 prof_conv17_flat" \
+              "conv_tc2_kernel 7 fp16 prof_conv68_res" "stem_fused_kernel 0 fp16 prof_stem_fused" "dark_block_kernel 0 fp16 prof_block" "stem_tc_kernel 0 parity prof_stem"; do
     set -- $spec
     timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$1 -s $2 -c 1 -f -o gpurun_out/$4 \
         python tools/profile_step.py --steps 2 --precision $3 --coco 0 > gpurun_out/ncu_$4.log 2>&1; echo "ncu full $4 exit $?"
