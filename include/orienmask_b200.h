@@ -268,7 +268,7 @@ int32_t om_engine_create(const om_engine_config* cfg, const om_tensor* weights, 
                          size_t workspace_bytes, void* stream, om_engine** out);
 /*
  * forward(x) -> ((bbox32, orien32), (bbox16, orien16), (bbox8, orien8)), model/orienmask_yolo_fpnplus.py:74-90.
- *   image    device fp32 NCHW [batch, 3, height, width]
+ *   image    device fp32 NCHW [batch, 3, height, width]; 16-byte aligned for OM_PREC_F16 (its first launch stages the image by TMA)
  *   bbox[3]  device fp32 NCHW [batch, A*(5+C), height/s, width/s] for s = 32, 16, 8
  *   orien    device fp32 NCHW [batch, 6*A, height/4, width/4]: channels [0,2A) belong to stride 32, [2A,4A) to 16, [4A,6A) to 8
  *            (the reference's torch.split(oriens, 2A, dim=1), :88)

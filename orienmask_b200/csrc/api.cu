@@ -43,7 +43,7 @@ struct om_conv {
     void* tc_plan;       // CTA-pair tcgen05 plan (OM_PREC_F16 / OM_PREC_SPLIT); null for the FFMA engine
 };
 
-extern "C" int32_t om_abi_version(void) { return 7; }
+extern "C" int32_t om_abi_version(void) { return 8; }
 extern "C" const char* om_last_error(void) { return om::error_buffer(); }
 extern "C" int64_t om_launch_count(void) { return om::g_launches; }
 extern "C" void om_launch_count_reset(void) { om::g_launches = 0; }

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(handle, name), name
-    assert _lib.lib().om_abi_version() == 7
+    assert _lib.lib().om_abi_version() == 8
 
 
 def test_header_is_plain_c_and_links(tmp_path):
