@@ -32,13 +32,17 @@ for a, b in (('parity_e2e_parity.json', 'r02_parity_e2e_parity.json'), ('parity_
              ('dropin_test_py_parity.json', 'r02_dropin_test_py_parity.json'), ('reference_gpu_bar.json', 'r02_reference_gpu_bar.json'),
              ('drift.json', 'r02_forward_drift.json'), ('fp16_agreement.json', 'r02_fp16_detection_agreement.json'),
              ('fp16_error_on_trained_like_heads.json', 'r02_fp16_error_on_trained_like_heads.json'), ('eager_bar.json', 'r02_eager_pytorch_bar.json'),
-             ('launches.csv', 'r02_launches_step.csv'), ('launches_parity.csv', 'r02_launches_step_parity.csv')):
+             ('launches.csv', 'r02_launches_step.csv'), ('launches_parity.csv', 'r02_launches_step_parity.csv'),
+             ('timeline.md', 'r02_timeline.md'), ('timeline_bs1.md', 'r02_timeline_bs1.md'), ('timeline_parity.md', 'r02_timeline_parity.md'),
+             ('timeline_fusion_ab.md', 'r02_timeline_fusion_ab.md'), ('phase_log_stem_fused.txt', 'r02_phase_log_stem_fused.txt'),
+             ('tl_ab3.md', 'r02_timeline_l2hint_ab.md'), ('tl_ab1.md', 'r02_timeline_resdirect_ab.md')):
     cp(a, b)
 for a, b in (('bench.log', 'r02_bench_1gpu.json'), ('bench_10steps.log', 'r02_bench_1gpu_10steps.json'), ('bench_parity.log', 'r02_bench_1gpu_parity.json'),
              ('bench_ref.log', 'r02_bench_reference_arm.json')):
     bench_line(a, b)
-reps = [os.path.join(G, n) for n in ('prof_conv136.ncu-rep', 'prof_conv136_parity.ncu-rep', 'prof_conv17_flat.ncu-rep', 'prof_stem.ncu-rep',
-                                      'prof_block.ncu-rep', 'prof_post.ncu-rep') if os.path.exists(os.path.join(G, n))]
+reps = [os.path.join(G, n) for n in ('prof_conv136.ncu-rep', 'prof_conv136_parity.ncu-rep', 'prof_conv17_flat.ncu-rep', 'prof_conv68_res.ncu-rep',
+                                      'prof_stem_fused.ncu-rep', 'prof_block.ncu-rep', 'prof_stem.ncu-rep', 'prof_post.ncu-rep')
+        if os.path.exists(os.path.join(G, n))]
 if reps:
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'ncu_summary.py')] + reps, capture_output=True, text=True).stdout
     open(os.path.join(P, 'r02_ncu_summary.txt'), 'w').write(out)
@@ -50,7 +54,7 @@ if os.path.exists(san):
     open(os.path.join(P, 'r02_sanitizer.txt'), 'w').write(
         'compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_conv.py -q -m gpu -x -k "split_precision_engine or head_channel or parity_split_layouts"\n'
         + '\n'.join(keep) + '\n\ncompute-sanitizer --tool memcheck python -m pytest tests/test_gpu_forward.py -q -m gpu -x -k "c_engine or fp16_small or parity_small"'
-        '   (C engine, fused block, TMA stem, all precisions)\n' + '\n'.join(keep2) + '\n')
+        '   (C engine, fused stem + conv2.0, fused block, TMA stem, all precisions)\n' + '\n'.join(keep2) + '\n')
 path = os.path.join(G, 'launches_bench_step.csv')
 if os.path.exists(path):
     rows, tot = collections.OrderedDict(), 0.0

@@ -47,4 +47,6 @@ fi
 if [[ $what == *sanitizer* ]]; then
   timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_conv.py -q -m gpu -x -k "split_precision_engine or head_channel or parity_split_layouts" > gpurun_out/sanitizer.log 2>&1
   echo "sanitizer exit $?: $(grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer.log | tail -2 | tr '\n' ' ')"
+  timeout 1200 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_forward.py -q -m gpu -x -k "c_engine or fp16_small or parity_small" > gpurun_out/sanitizer_fwd.log 2>&1
+  echo "sanitizer (forward: C engine, fused stem, fused block) exit $?: $(grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitizer_fwd.log | tail -2 | tr '\n' ' ')"
 fi
