@@ -627,7 +627,7 @@ def main():
                                           '(measured < algorithmic: consecutive layers hit in the 126 MB L2)'
                                           % (traffic['launches'], traffic['file'])) if traffic else None,
                          'kernel': 'conv engine = the model forward: %d launches (conv_tc2_kernel, tcgen05 cta_group::2; fused DarkNet block; '
-                                   'TMA-fed tensor-core stem), %.3f ms of %.3f ms per step' % (len(eng.layers), fwd_ms, total_ms / args.steps),
+                                   'TMA-fed tensor-core stem, fused with the stride-2 layer behind it in the fp16 engine), %.3f ms of %.3f ms per step' % (len(eng.layers), fwd_ms, total_ms / args.steps),
                          'algorithmic': '%.3f GFLOP/image x %d images per forward' % (GFLOP_PER_IMAGE, B),
                          'peak_source': peaks['source']},
         }
