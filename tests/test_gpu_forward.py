@@ -286,6 +286,46 @@ def test_c_engine_matches_the_python_schedule(plus, monkeypatch):
             assert torch.equal(b0, b1) and torch.equal(o0, o1), (prec, float((b0 - b1).abs().max()), float((o0 - o1).abs().max()))
 
 
+def test_sub_schedules_and_the_launch_trace():
+    """om_engine_run_layers over the whole schedule reproduces om_forward bit for bit; om_debug_trace hands one record to every conv-engine
+    launch, each with first CTA start <= dependencies resolved <= last CTA end, launches in stream order; om_debug_phase_log is filled by
+    the fused stem kernel.  (tools/timeline.py and tools/phase_log.py are built on these.)"""
+    import ctypes
+    from orienmask_b200 import _lib
+    from orienmask_b200.synthetic import synthetic_images
+    m = _model('fp16')
+    x = synthetic_images(2, 96, 160, seed=3).cuda()
+    ref = m(x)
+    torch.cuda.synchronize()
+    eng = next(iter(m._engines.values()))
+    lib = eng.lib
+    n = len(eng.layers)
+    assert eng.layers[0]['name'].startswith('backbone.conv1 + conv2.0') and 'fused block' in eng.layers[1]['name']
+    outs = eng._outputs()
+    bbox = (_lib.c_vp * 3)(*[t.data_ptr() for t in outs[:3]])
+    idx = (_lib.c_i32 * n)(*range(n))
+    rec = torch.empty(n, 4, dtype=torch.int64, device='cuda:0')
+    rec[:, 0:2] = -1
+    rec[:, 2:4] = 0
+    log = torch.zeros(16, 8, dtype=torch.int64, device='cuda:0')
+    torch.cuda.synchronize()
+    assert lib.om_debug_trace(_lib.ptr(rec), n) >= 0
+    _lib.check(lib.om_debug_phase_log(_lib.ptr(log)), 'om_debug_phase_log')
+    _lib.check(lib.om_engine_run_layers(eng.handle, idx, n, _lib.ptr(x), bbox, _lib.ptr(outs[3]), _lib.stream_ptr()), 'om_engine_run_layers')
+    torch.cuda.synchronize()
+    assert lib.om_debug_trace(None, 0) == n
+    _lib.check(lib.om_debug_phase_log(None), 'om_debug_phase_log')
+    for (b0, o0), (b1, o1) in zip(ref, eng._tuple(outs)):
+        assert torch.equal(b0, b1) and torch.equal(o0, o1)
+    r = rec.cpu().numpy().astype(np.uint64)
+    assert (r[:, 0] <= r[:, 1]).all() and (r[:, 1] <= r[:, 2]).all() and (r[:, 0] <= r[:, 3]).all() and (r[:, 3] <= r[:, 2]).all()
+    assert (r[1:, 1] >= r[:-1, 2]).all()          # a launch's dependencies resolve after its predecessor's last CTA has ended
+    t = log.cpu().numpy()
+    assert (t[0, :7] > 0).all() and (np.diff(t[0, :7]) >= 0).all()
+    bad = (_lib.c_i32 * 1)(n)
+    assert lib.om_engine_run_layers(eng.handle, bad, 1, _lib.ptr(x), bbox, _lib.ptr(outs[3]), _lib.stream_ptr()) != 0
+
+
 def test_c_engine_errors_are_loud():
     """om_engine_create validates the state dict against the architecture and the workspace against the plan."""
     import ctypes

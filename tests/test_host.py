@@ -39,7 +39,7 @@ def test_header_is_plain_c_and_links(tmp_path):
                            '-o', exe, '-L', libdir, '-lorienmask_b200', '-Wl,-rpath,' + libdir])
     words = subprocess.check_output([exe]).decode().split()
     got = {words[i]: int(words[i + 1]) for i in range(0, len(words), 2)}
-    assert got["abi"] == 7 and got['entries'] == len(_lib.SIGNATURES)
+    assert got["abi"] == 8 and got['entries'] == len(_lib.SIGNATURES)
     assert got['sizeof(om_post_config)'] == ctypes.sizeof(_lib.PostConfig)
     assert got['sizeof(om_conv_desc)'] == ctypes.sizeof(_lib.ConvDesc)
     assert got['sizeof(om_prep_config)'] == ctypes.sizeof(_lib.PrepConfig)
@@ -50,6 +50,17 @@ def test_header_is_plain_c_and_links(tmp_path):
                                   'om_prep_config.pad_value': (_lib.PrepConfig, 'pad_value'), 'om_rle_image.vflip': (_lib.RleImage, 'vflip'),
                                   'om_blend_config.alpha': (_lib.BlendConfig, 'alpha')}.items():
         assert got['offsetof(%s)' % name] == getattr(struct, field).offset, name
+
+
+def test_fastdiv_is_exact(tmp_path):
+    """csrc/common.cuh FastDiv (tile decode by multiply-high in every persistent kernel): n / d for all 0 <= n < 2^31 -- checked here
+    on the host for every divisor up to 70 000 (tile counts, row pitches, channel chunks) against corner and random numerators."""
+    import subprocess
+    exe = str(tmp_path / 'fastdiv_check')
+    cuda_inc = '/usr/local/cuda/include'
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-I', cuda_inc, '-I', os.path.join(ROOT, 'include'),
+                           os.path.join(ROOT, 'tests', 'c_abi', 'fastdiv_check.cpp'), '-o', exe])
+    assert subprocess.check_output([exe]).decode().strip() == 'bad 0'
 
 
 def test_built_library_contains_blackwell_tensor_and_tma_code():
@@ -72,6 +83,9 @@ def test_built_library_contains_blackwell_tensor_and_tma_code():
         assert c['UTCHMMA'] > 100 and c['UTMALDG'] >= 5 and c['LDTM'] >= 4 and c['UTCBAR'] >= 2 and c['ACQBULK'] >= 1, (name, dict(c))
     assert counts['stem_tc_kernel<true, false>']['UTCHMMA'] >= 2 and counts['stem_tc_kernel<true, false>']['LDTM'] >= 1
     assert counts['stem_tc_kernel<true, false>']['UTMALDG'] >= 1            # the 544x544 input tiles are staged by TMA
+    for name in ('stem_fused_kernel', 'dark_block_kernel'):                 # the two fused launches: two MMA stages each, TMA-fed, FADD2 / FMUL2 epilogues
+        c = counts[name]
+        assert c['UTCHMMA'] >= 20 and c['UTMALDG'] >= 1 and c['LDTM'] >= 2, (name, dict(c))
     assert all(c['HMMA'] == 0 and c['HGMMA'] == 0 for c in counts.values())
     for name in ('mask_kernel', 'conf_compact_kernel', 'select_edge_kernel', 'select_tail_kernel', 'nms_kernel<true>', 'prep_kernel<unsigned char>',
                  'mask_rle_kernel', 'mask_blend_kernel'):
