@@ -1104,13 +1104,22 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
         return fail(OM_ERR_INVALID, "this stride-2 layer needs in_rows == 2*out_rows (only im2col-gathered tiles are free of it)");
     }
     p.halo_s2 = d.ksize == 3 && d.stride == 2 && d.in_s2d && d.out_kind != OM_OUT_NCHW && (d.out_w % 8 == 0 || d.out_w >= 64) &&
-                !(halo_env && halo_env[0] == '0') && !getenv("ORIENMASK_B200_NO_HALO_S2") && !split;
+                !(halo_env && halo_env[0] == '0') && !getenv("ORIENMASK_B200_NO_HALO_S2");
     if (p.halo_s2) {
-        // only where all weights stay resident next to two halo stages (the 32 -> 64 layer): with a weight ring the four plane
-        // boxes leave too few stages and the layer gets slower than with per-tap boxes (64 -> 128 @136: 113 -> 165 us)
         const size_t chunk = ((size_t)(9 * 17) * bk * 2 + 1023) / 1024 * 1024;
-        const size_t need = 2 * 4 * (d.cin / bk) * chunk + (size_t)9 * (d.cin / bk) * (bn / 2) * bk * 2 + 8 * 1024;
-        if (cout_pad / bn != 1 || need > 227 * 1024) p.halo_s2 = 0;
+        const size_t halo2 = 2 * 4 * (size_t)((split ? 2 : 1) * (d.cin / bk)) * chunk;          // two stages of four plane boxes per chunk
+        if (!split) {
+            // only where all weights stay resident next to two halo stages (the 32 -> 64 layer): with a weight ring the four plane
+            // boxes leave too few stages and the layer gets slower than with per-tap boxes (64 -> 128 @136: 113 -> 165 us)
+            const size_t need = halo2 + (size_t)9 * (d.cin / bk) * (bn / 2) * bk * 2 + 8 * 1024;
+            if (cout_pad / bn != 1 || need > 227 * 1024) p.halo_s2 = 0;
+        } else {
+            // split precision (no resident weights): per-tap boxes make this layer TMA-row bound -- 27 (tap, pass) blocks x (128 + 32)
+            // rows per tile = 15 000 cycles of TMA at ~3.5 cycles per row against 1 700 cycles of MMA (993 us for backbone.conv2.0 in
+            // the parity-mode timeline); the plane boxes are 1 224 rows per tile.  Needs room for a ring of >= 8 weight blocks.
+            const size_t need = halo2 + (size_t)8 * (bn / 2) * bk * 2 + 8 * 1024;
+            if (need > 227 * 1024) p.halo_s2 = 0;
+        }
     }
     if (p.halo_s2) p.halo = 1;
     p.halo_planes = p.halo_s2 ? 4 : 1;
