@@ -2,7 +2,7 @@
 //
 // The launch schedule of OrienMaskYOLOFPNPlus.forward (model/orienmask_yolo_fpnplus.py:74-90 over DarkNet53.forward,
 // model/backbone/darknet.py:47-54) lives HERE: a C caller hands over the reference's state dict as named fp32 device tensors plus one
-// workspace and gets the 95-launch forward behind a single call.  What the schedule does (same as the Python-scheduled engine it
+// workspace and gets the 93-launch (fp16; 95 in the other precisions) forward behind a single call.  What the schedule does (same as the Python-scheduled engine it
 // replaces, which tests keep as a bit-exact cross-check):
 //   * BatchNorm folded into the convolution weights in fp32 on the device (W' = W * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps),
 //     model/base.py:104-137), packed once into the engine layout of the chosen precision (om_conv_desc.weights);
