@@ -34,6 +34,10 @@ CASES = [
     (7, 128, 64, 17, 17, 1, 1, ACT, False, False),
     (4, 64, 128, 34, 34, 3, 2, ACT, False, False),
     (3, 256, 512, 34, 34, 3, 1, ACT, True, False),
+    # ... enough pixel tiles for N = 256 and several waves: with and without a residual, stride 2
+    (16, 256, 512, 34, 34, 3, 1, ACT, True, False),
+    (32, 512, 1024, 17, 17, 3, 1, ACT, False, False),
+    (16, 256, 512, 68, 68, 3, 2, ACT, False, False),
     (3, 96, 64, 10, 14, 3, 1, ACT, False, False),         # 64-byte pixels (BK = 32), three chunks
     (2, 64, 128, 34, 34, 1, 1, PARTIAL, False, False),
 ]
