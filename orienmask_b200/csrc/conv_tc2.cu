@@ -1069,7 +1069,7 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
             const long long steps = (long long)d.ksize * d.ksize * (d.cin / 16) * (split ? 3 : 1);
             long long best_t = -1;
             int best_bn = bn;
-            for (int cand = bn; cand >= 64; cand >>= 1) {
+            for (int cand = bn; cand >= 32; cand >>= 1) {          // (N = 32 where it still fits one wave: bs 1, 17x17 3x3 layers -10 %, A/B)
                 if (cout_pad % cand || cand % 32) continue;
                 const long long pairs = m_pairs * (cout_pad / cand);
                 const long long waves = (pairs + clusters - 1) / clusters;

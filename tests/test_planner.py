@@ -41,7 +41,9 @@ for plus, B, H, W in [(True, 32, 544, 544), (True, 1, 544, 544), (True, 8, 960, 
         planned_split = len(rows)
         worst_smem = max(worst_smem, max(r['smem'] for r in rows))
         split_modes[str((B, H, W))] = collections.Counter(pt.mode(r) for r in rows)
-        bad = [r['name'] for r in rows if r['halo_s2'] or r['b_resident'] or r['has_res'] == 1 or r['acc_stages'] * r['block_n'] > 512]
+        # (parity-plane halo boxes only for backbone.conv2.0, never with resident weights or a TMA-staged residual)
+        bad = [r['name'] for r in rows if (r['halo_s2'] and r['name'] != 'backbone.conv2.0') or r['b_resident'] or r['has_res'] == 1
+               or r['acc_stages'] * r['block_n'] > 512]
         if bad:
             failures.append((('parity', plus, B, H, W), 'implausible plan: %%s' %% bad[:3]))
     except Exception as e:                            # noqa: BLE001
@@ -75,8 +77,9 @@ def test_planner_sweep_and_north_star_plan_without_a_gpu():
     # the plan the round-1 measurements were taken with (profiles/r01_plan_bs32_544.md): a change here is a change of the tuned schedule
     assert res['modes_544'] == res['modes_960'] == {'flat': 56, 'halo': 19, 'per-tap': 18, 'halo-s2': 1}
     #                    mode, tw, th, N tile, N tiles, addend (1 TMA fp16, 2 TMA up-add), direct residual, resident weights
-    # split precision: no parity-plane halo / resident weights / TMA-staged fp16 residual (the epilogue reads hi and lo itself)
-    assert sum(res['split_modes']['(32, 544, 544)'].values()) == 94 and 'halo-s2' not in res['split_modes']['(32, 544, 544)']
+    # split precision: no resident weights / TMA-staged fp16 residual (the epilogue reads hi and lo itself); parity-plane halo boxes for
+    # backbone.conv2.0 only (its per-tap boxes were TMA-row bound)
+    assert sum(res['split_modes']['(32, 544, 544)'].values()) == 94 and res['split_modes']['(32, 544, 544)'].get('halo-s2', 0) == 1
     assert res['neck4.1'] == ['halo', 8, 16, 256, 1, 0, 0, 0]                    # 3x3 128->256 @136x136: a third of all FLOPs
     assert res['conv2.0'] == ['halo-s2', 8, 16, 64, 1, 0, 0, 1]                  # parity-plane halo boxes, all weights resident
     assert res['conv4.0'] == ['flat', 128, 1, 256, 1, 0, 0, 0]                   # stride 2 over 137 -> 72-row images: im2col-gathered
