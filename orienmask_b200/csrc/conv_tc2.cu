@@ -94,6 +94,7 @@ struct Tc2Params {
     const float* upadd;
     void* output;
     unsigned long long* trace;           // om_debug_trace record of this launch, or nullptr
+    int epi_sleep_ns;                    // back-off of the epilogue warps' wait for an accumulator (see mbar_wait_relaxed)
     int hint_a, hint_w, hint_res, hint_out;   // L2 eviction priority of the activation / weight / residual loads and of the fp16 output stores
 };
 
@@ -164,6 +165,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(ok) : "r"(addr), "r"(parity), "r"(hint) : "memory");
         if (ok) return;
+        if ((spins & 63u) == 0u && clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+
+// The epilogue warps' wait for the next accumulator lasts most of a tile (7 us on the tensor-bound layers) and has a whole tile of
+// slack: between polls they sleep.  (The hinted try_wait above returns after ~150 cycles whatever the hint says; with 16 warps waiting
+// the polls were 47 % of the warp instructions of a tensor-bound layer -- ncu source view of backbone.conv4.1.conv.1.)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, int sleep_ns) {
+    if (sleep_ns <= 0) { mbar_wait(bar, parity); return; }
+    const uint32_t addr = smem_u32(bar);
+    const long long t0 = clock64();
+    for (uint32_t spins = 1;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        __nanosleep((unsigned)sleep_ns);
         if ((spins & 63u) == 0u && clock64() - t0 > 4000000000ll) __trap();
     }
 }
@@ -376,7 +397,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
             // Narrow tiles (N = 32 / 64) give work to one or two of the four groups; the others only keep the accumulator
             // barrier in step, without the tile's coordinate arithmetic (with all 16 warps doing it, a memory-bound 1x1
             // 64 -> 32 tile cost 3850 warp instructions at IPC 2: issue-bound, not HBM-bound).
-            mbar_wait(&c.tmem_full[as], aphase);
+            mbar_wait_relaxed(&c.tmem_full[as], aphase, p.epi_sleep_ns);
             tc_fence_after();
             tc_fence_before();
             __syncwarp();
@@ -406,7 +427,7 @@ __device__ __forceinline__ void epilogue_loop(const Tc2Params& p, const EpiCtx& 
             rsrc = reinterpret_cast<const __half*>(p.residual) + ((size_t)Y * p.out_w + x) * (SPLIT ? p.pix_stride : p.cout_stride) + n0;
             if (!SPLIT && valid && j_first < n_chunks) ldg_res32(rr, rsrc + j_first * 32);
         }
-        mbar_wait(&c.tmem_full[as], aphase);
+        mbar_wait_relaxed(&c.tmem_full[as], aphase, p.epi_sleep_ns);
         if (pair == c.first_pair) tick(6, c.warp == kEpiWarp0 && c.lane == 0);
         tc_fence_after();
         const uint32_t taddr = c.tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * p.block_n);
@@ -1243,6 +1264,11 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
     p.up_rows = d.up_rows; p.bias = d.bias; p.upadd = d.upadd;
     p.cout_stride = d.cout_stride; p.output = d.output;
     p.out_s2d = d.out_s2d; p.s2d_plane = (long long)d.batch * d.out_rows / 2 * (d.out_w / 2);
+    {
+        const char* se = getenv("ORIENMASK_B200_EPI_SLEEP");
+        p.epi_sleep_ns = se ? atoi(se) : 250;        // time-neutral in the interleaved A/B (100 .. 1000 ns), +0.1 .. 0.7 % in 60-step runs under the
+        if (p.epi_sleep_ns < 0 || p.epi_sleep_ns > 100000) p.epi_sleep_ns = 0;   // power cap (fewer instructions per joule-limited step)
+    }
     {
         // L2 eviction priorities (experiment: ORIENMASK_B200_L2HINT=mode)
         const char* he = getenv("ORIENMASK_B200_L2HINT");
