@@ -4,6 +4,10 @@ each group.  ncu's per-launch times are serialised and cold-cache; this is what 
     python tools/insitu.py [--batch 32] [--size 544] [--iters 20] [--json gpurun_out/insitu.json]
 
 Skipped layers leave the previous pass's (realistic) data in their output buffers, so the remaining launches do the same work.
+
+Caveat (measured): on a power-capped part the clocks move when a group is removed, so marginal costs of small groups are noisy
+(single layers: +-100 us on a 6 ms forward).  tools/timeline.py stamps every launch in the unmodified forward and is the instrument
+of record; this tool only answers "what would the forward cost without this group".
 """
 import argparse
 import json
