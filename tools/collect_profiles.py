@@ -38,7 +38,8 @@ for a, b in (('parity_e2e_parity.json', 'r02_parity_e2e_parity.json'), ('parity_
              ('tl_ab3.md', 'r02_timeline_l2hint_ab.md'), ('tl_ab1.md', 'r02_timeline_resdirect_ab.md')):
     cp(a, b)
 for a, b in (('bench.log', 'r02_bench_1gpu.json'), ('bench_10steps.log', 'r02_bench_1gpu_10steps.json'), ('bench_parity.log', 'r02_bench_1gpu_parity.json'),
-             ('bench_ref.log', 'r02_bench_reference_arm.json'), ('bench_2gpu.log', 'r02_bench_2gpu.json'), ('bench_8gpu.log', 'r02_bench_8gpu.json')):
+             ('bench_ref.log', 'r02_bench_reference_arm.json'), ('bench_2gpu.log', 'r02_bench_2gpu.json'), ('bench_4gpu.log', 'r02_bench_4gpu.json'),
+             ('bench_8gpu.log', 'r02_bench_8gpu.json')):
     bench_line(a, b)
 reps = [os.path.join(G, n) for n in ('prof_conv136.ncu-rep', 'prof_conv136_parity.ncu-rep', 'prof_conv17_flat.ncu-rep', 'prof_conv68_res.ncu-rep',
                                       'prof_stem_fused.ncu-rep', 'prof_block.ncu-rep', 'prof_stem.ncu-rep', 'prof_post.ncu-rep')
