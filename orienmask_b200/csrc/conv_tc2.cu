@@ -94,6 +94,9 @@ struct Tc2Params {
     const float* upadd;
     void* output;
     unsigned long long* trace;           // om_debug_trace record of this launch, or nullptr
+    int h_halves;                        // split precision with ONE halo stage: its lo half (read by pass 0 only) and its hi half (passes 1, 2)
+                                         // have their own barrier pairs, so the next tile's lo half loads under passes 1-2 of this tile and
+                                         // its hi half under ITS pass 0: the halo load of a tile is no longer exposed (see the planner)
     int epi_sleep_ns;                    // back-off of the epilogue warps' wait for an accumulator (see mbar_wait_relaxed)
     int hint_a, hint_w, hint_res, hint_out;   // L2 eviction priority of the activation / weight / residual loads and of the fp16 output stores
 };
@@ -637,7 +640,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
         if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a0));
         if (lane == 1) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b));
         if (lane < p.stages) { mbar_init(&s_full[lane], 1); mbar_init(&s_empty[lane], 1); }
-        if (lane >= 8 && lane - 8 < p.h_stages) { mbar_init(&h_full[lane - 8], 1); mbar_init(&h_empty[lane - 8], 1); }
+        if (lane >= 8 && lane - 8 < (p.h_halves ? 2 : p.h_stages)) { mbar_init(&h_full[lane - 8], 1); mbar_init(&h_empty[lane - 8], 1); }
         if (lane >= 16 && lane < 16 + kMaxAcc) { mbar_init(&tmem_full[lane - 16], 1); mbar_init(&tmem_empty[lane - 16], 8 * kEpiGroups); }
         if (lane >= 24 && lane - 24 < kMaxResBufs) { mbar_init(&res_full[lane - 24], 1); mbar_init(&res_empty[lane - 24], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -697,7 +700,21 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 FlatOrigin fo = {0, 0, 0};
                 if (p.flat) fo = flat_origin(p, 2 * t.py + (int)rank);
                 const int fw = fo.x * p.stride - p.pad, fh = fo.y * p.stride - p.pad;
-                if (p.halo) {
+                // half-stage mode: barrier pair 1 = the lo chunks [kr, 2 kr) of the one stage, pair 0 = the hi chunks [0, kr); h_phase toggles per tile
+                auto load_half = [&](int half) {
+                    mbar_wait(&h_empty[half], h_phase ^ 1);
+                    const uint32_t lb = mapa(smem_u32(&h_full[half]), 0);
+                    if (lane == 0 && rank == 0) mbar_expect_tx(&h_full[half], h_tx >> 1);
+                    if (lane < p.split_kr) {
+                        const int kc = half * p.split_kr + lane;
+                        tma_load_3d_pair(h_ring + (size_t)kc * p.h_chunk_bytes, &maps_a.m[0], lb, kc * BK, x0 - 1, y0 - 1, pol_a);
+                    }
+                    __syncwarp();
+                };
+                if (p.halo && p.h_halves) {
+                    if (pair == first_pair) { pdl_wait(); tick(2, lane == 0); if (lane == 0) trace_dep(p.trace); }
+                    load_half(1);                                  // lo first: pass 0 reads it; the hi half follows in front of pass 1 (below)
+                } else if (p.halo) {
                     mbar_wait(&h_empty[hs], h_phase ^ 1);
                     const uint32_t lb = mapa(smem_u32(&h_full[hs]), 0);
                     if (pair == first_pair) { pdl_wait(); tick(2, lane == 0); if (lane == 0) trace_dep(p.trace); }
@@ -710,6 +727,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     if (++hs == p.h_stages) { hs = 0; h_phase ^= 1; }
                 }
                 for (int g = 0; g < n_groups; ++g) {
+                    if (p.h_halves && 3 * g == n_groups) { load_half(0); h_phase ^= 1; }     // the hi half, in front of the first block of pass 1
                     mbar_wait(&s_empty[st], s_phase ^ 1);
                     const uint32_t lb = mapa(smem_u32(&s_full[st]), 0);
                     uint8_t* sb = s_ring + (size_t)st * stage_bytes;
@@ -780,7 +798,7 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
                 uint64_t ad_tile = 0;
                 if (p.halo) {
-                    mbar_wait(&h_full[hs], h_phase);
+                    mbar_wait(&h_full[p.h_halves ? 1 : hs], h_phase);          // (half-stage mode: the lo half; the hi half is awaited in front of pass 1)
                     ad_tile = hi_a | (uint64_t)(((h_ring_addr + (uint32_t)(hs * p.h_stage_bytes)) & 0x3FFFF) >> 4);
                 }
                 tc_fence_after();
@@ -805,6 +823,12 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                     int pass = 0;                                             // split precision: see the producer
                     const int kc_end = SPLIT ? p.split_kr : p.k_chunks;
                     for (int g = 0; g < n_groups; ++g) {
+                        if (p.h_halves && 3 * g == n_groups) {             // pass 0 is issued: the lo half is free once it completes; pass 1 needs the hi half
+                            if (elect_one()) umma_commit_pair(&h_empty[1]);
+                            __syncwarp();
+                            mbar_wait(&h_full[0], h_phase);
+                            tc_fence_after();
+                        }
                         mbar_wait(&s_full[st], s_phase);
                         if (pair == first_pair && g == 0) tick(4, lane == 0);
                         tc_fence_after();
@@ -833,7 +857,10 @@ conv_tc2_kernel(const __grid_constant__ AMaps maps_a, const __grid_constant__ CU
                         if (++st == p.stages) { st = 0; s_phase ^= 1; }
                     }
                 }
-                if (p.halo) {
+                if (p.halo && p.h_halves) {
+                    if (elect_one()) umma_commit_pair(&h_empty[0]);
+                    h_phase ^= 1;
+                } else if (p.halo) {
                     if (elect_one()) umma_commit_pair(&h_empty[hs]);
                     if (++hs == p.h_stages) { hs = 0; h_phase ^= 1; }
                 }
@@ -1247,6 +1274,10 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
         if (p.stages > kMaxStages) p.stages = kMaxStages;
         if (p.stages < 2) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
         if (p.b_resident) { p.n_sub = total; p.stages = 1; }          // the "ring" is the resident weight tensor
+        // one halo stage of a split-precision layer: lo and hi halves behind their own barriers, when the passes are whole groups
+        const char* hh = getenv("ORIENMASK_B200_HHALVES");
+        p.h_halves = (split && p.halo && !p.halo_s2 && p.h_stages == 1 && !p.b_resident && (p.taps * p.split_kr) % p.n_sub == 0 &&
+                      !(hh && hh[0] == '0')) ? 1 : 0;
     }
     // 4 accumulators at most: 2 / 4 / 8 in flight measured identical on the narrow memory-bound layers (ORIENMASK_B200_ACC, up to
     // kMaxAcc, for experiments), and a smaller TMEM allocation lets the next layer's prologue allocate earlier
