@@ -1272,6 +1272,8 @@ static int32_t plan_create(const om_conv_desc& d, void** out, bool allow_halo, b
         p.n_sub = best;
         p.stages = ring_budget / (best * sub_bytes);
         if (p.stages > kMaxStages) p.stages = kMaxStages;
+        if (getenv("ORIENMASK_B200_MAXSTAGES") && atoi(getenv("ORIENMASK_B200_MAXSTAGES")) >= 2 && p.stages > atoi(getenv("ORIENMASK_B200_MAXSTAGES")))
+            p.stages = atoi(getenv("ORIENMASK_B200_MAXSTAGES"));           // experiment: sensitivity to the depth of the block ring
         if (p.stages < 2) { delete plan; return fail(OM_ERR_INVALID, "tile does not fit shared memory"); }
         if (p.b_resident) { p.n_sub = total; p.stages = 1; }          // the "ring" is the resident weight tensor
         // one halo stage of a split-precision layer: lo and hi halves behind their own barriers, when the passes are whole groups
