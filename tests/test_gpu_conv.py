@@ -24,6 +24,7 @@ CASES = [
     (2, 64, 128, 12, 12, 1, 1, PARTIAL, False, True),
     (2, 512, 256, 12, 12, 1, 1, ACT, False, True),
     (1, 128, 256, 136, 136, 3, 1, ACT, False, False),
+    (8, 128, 256, 136, 136, 3, 1, ACT, False, False),     # eight tiles per CTA pair: halo stages (split precision: lo / hi half stages) recycle
     (1, 128, 256, 68, 68, 3, 1, ACT, True, False),        # halo tiles with a partial last tile column (68 = 8*8 + 4)
     (8, 128, 256, 68, 68, 3, 1, ACT, True, False),        # ... several tiles per CTA, N = 256: 64-column residual chunks in two shared buffers
     (2, 64, 64, 24, 72, 3, 1, ACT, False, False),
